@@ -1,0 +1,13 @@
+"""gp_emulator_b200 -- B200-native prediction engine behind the gp_emulator Python API.
+
+Same public names as the reference package for the prediction path (reference gp_emulator/__init__.py:1-2):
+``GaussianProcess``, ``k_fold_cross_validation``, ``MultivariateEmulator``; plus the device handles
+``DeviceModel`` / ``DeviceBank`` for callers that keep data on the GPU.
+"""
+from .engine import DeviceBank, DeviceModel
+from .gaussian_process import GaussianProcess, k_fold_cross_validation
+from .multivariate import MultivariateEmulator
+from ._lib import GpemuError, measure_fp64_peaks
+
+__all__ = ["GaussianProcess", "k_fold_cross_validation", "MultivariateEmulator", "DeviceModel", "DeviceBank",
+           "GpemuError", "measure_fp64_peaks"]

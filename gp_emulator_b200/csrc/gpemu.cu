@@ -1,0 +1,639 @@
+// libgpemu.so -- C ABI implementation (see include/gpemu.h for the contract and reference citations).
+//
+// Host responsibilities: validate, lay the trained model out for the kernels (done once per model, the
+// reference re-uploads and re-transposes it for every 2e5-point block: gp_emulator/gpu/predict.cu:11-34,
+// _gpu_predict.cpp:129-132), pick the kernel configuration, launch, and -- for host-resident callers --
+// stream test points through a two-slot pinned pipeline (replaces the Python chunk loop of
+// GaussianProcess.gpu_predict / get_gpu_block, gp_emulator/GaussianProcess.py:253-323).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gpemu.h"
+#include "launch.h"
+
+using namespace gpe;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(GPE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr uint32_t kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int64_t kPipeChunk = 1 << 18;  // points per host-streaming chunk
+
+inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+struct FullPlan {
+    bool valid = false;
+    int cfg = 0, TN = 0, WC = 0, GH = 1;
+    int Mp = 0, nt_act = 0, kblk = 0, kbps = 0, nit = 0, nstage = 0, JC = 0, nchunks = 0;
+    uint32_t off_bar = 0, off_sqw = 0, off_ks = 0, off_bst = 0, off_xc = 0, off_ts = 0, off_pa = 0, off_vred = 0;
+    uint32_t stage_bytes = 0, smem = 0;
+};
+
+struct MeanPlan {
+    int JC = 0, nchunks = 0;
+    uint32_t off_xc = 0, off_ts = 0, off_out = 0, smem = 0, smem_hess = 0;
+};
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    double* d_in = nullptr;
+    double* d_out = nullptr;   // mu | var | deriv | hess, sized for the flags of the first use
+    double* h_in = nullptr;    // pinned staging (pageable callers only)
+    double* h_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0, h_in_cap = 0, h_out_cap = 0;
+    // pending copy-out for the staging path
+    bool pending = false;
+    int64_t pend_n0 = 0, pend_n = 0;
+};
+
+}  // namespace
+
+struct gpe_model {
+    int device = 0, M = 0, D = 0, DP = 0, sms = 0;
+    double b = 0;
+    double sqrt_w[32];
+    bool has_invQ = false;
+    FullPlan full;
+    MeanPlan mean;
+    double* d_xchunks_full = nullptr;
+    double* d_stiled = nullptr;
+    double* d_xchunks_mean = nullptr;
+    Slot slots[2];
+};
+
+struct gpe_bank {
+    int device = 0, E = 0, M = 0, D = 0, W = 0;
+    std::vector<gpe_model*> models;
+    double* d_basis = nullptr;
+};
+
+namespace {
+
+int pick_dp(int D) {
+    for (int i = 0; i < kNumDp; ++i)
+        if (kDpList[i] >= D) return kDpList[i];
+    return -1;
+}
+
+cudaError_t launch_full(int DP, int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (DP) {
+        case 2: return launch_full_dp2(cfg, p, grid, smem, st);
+        case 4: return launch_full_dp4(cfg, p, grid, smem, st);
+        case 6: return launch_full_dp6(cfg, p, grid, smem, st);
+        case 8: return launch_full_dp8(cfg, p, grid, smem, st);
+        case 10: return launch_full_dp10(cfg, p, grid, smem, st);
+        case 12: return launch_full_dp12(cfg, p, grid, smem, st);
+        case 16: return launch_full_dp16(cfg, p, grid, smem, st);
+        case 24: return launch_full_dp24(cfg, p, grid, smem, st);
+        case 32: return launch_full_dp32(cfg, p, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (DP) {
+        case 2: return launch_mean_dp2(hess, p, grid, smem, st);
+        case 4: return launch_mean_dp4(hess, p, grid, smem, st);
+        case 6: return launch_mean_dp6(hess, p, grid, smem, st);
+        case 8: return launch_mean_dp8(hess, p, grid, smem, st);
+        case 10: return launch_mean_dp10(hess, p, grid, smem, st);
+        case 12: return launch_mean_dp12(hess, p, grid, smem, st);
+        case 16: return launch_mean_dp16(hess, p, grid, smem, st);
+        case 24: return launch_mean_dp24(hess, p, grid, smem, st);
+        case 32: return launch_mean_dp32(hess, p, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// Decide tile shape, pipeline depth and the shared-memory carve-up of the fused kernel for (M, D).
+FullPlan plan_full(int M, int D, int DP) {
+    FullPlan f;
+    const int m32 = (M + 31) / 32 * 32, m64 = (M + 63) / 64 * 64;
+    if (m32 <= 256) {
+        f.cfg = 0; f.TN = 64; f.WC = 4; f.GH = 1; f.Mp = m32; f.nt_act = m32 / 32;
+    } else if (m64 <= 512) {
+        f.cfg = 1; f.TN = 32; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64;
+    } else if (m64 <= 1024) {
+        f.cfg = 2; f.TN = 16; f.WC = 8; f.GH = 4; f.Mp = m64; f.nt_act = m64 / 64;
+    } else {
+        return f;  // invalid: variance contraction unsupported for this M
+    }
+    f.kblk = (M + 3) / 4;
+    f.kbps = std::max(1, 16384 / (f.Mp * 32));
+    f.nit = (f.kblk + f.kbps - 1) / f.kbps;
+    f.stage_bytes = (uint32_t)f.kbps * f.Mp * 32u;
+
+    uint32_t off = 0;
+    f.off_bar = off; off += 192;
+    f.off_sqw = off; off += 256;
+    f.off_ks = off; off += (uint32_t)f.TN * (f.Mp + 4) * 8u;
+    f.off_ts = off; off += align_up((uint32_t)f.TN * (D + 1) * 8u, 16);
+    f.off_pa = off; off += (f.GH > 1) ? align_up((uint32_t)f.GH * f.TN * (D + 1) * 8u, 16) : 0;
+    f.off_vred = off; off += (uint32_t)f.WC * f.TN * 8u;
+    off = align_up(off, 128);
+    const uint32_t fixed = off;
+    const int m4 = (M + 3) / 4 * 4;
+    const uint32_t row = (uint32_t)(DP + 1) * 8u;
+    for (int ns : {4, 2}) {
+        const uint32_t need = fixed + (uint32_t)ns * f.stage_bytes;
+        if (need + 64 * row > kSmemMax) continue;
+        const int jc_max = (int)((kSmemMax - need) / row) / 4 * 4;
+        if (jc_max >= m4) {  // whole training set resident for the lifetime of the CTA
+            f.nstage = ns; f.JC = m4; f.nchunks = 1;
+            break;
+        }
+        if (f.nstage == 0) {  // remember the deepest ring that leaves room for a useful chunk
+            f.nstage = ns; f.JC = std::min(jc_max, 256); f.nchunks = (M + f.JC - 1) / f.JC;
+        }
+    }
+    if (f.nstage == 0) return f;
+    f.off_bst = fixed;
+    f.off_xc = fixed + (uint32_t)f.nstage * f.stage_bytes;
+    f.smem = f.off_xc + (uint32_t)f.JC * row;
+    f.valid = f.smem <= kSmemMax;
+    return f;
+}
+
+MeanPlan plan_mean(int M, int D, int DP) {
+    MeanPlan m;
+    const int m4 = (M + 3) / 4 * 4;
+    m.JC = std::min(m4, 256);
+    m.nchunks = (M + m.JC - 1) / m.JC;
+    uint32_t off = 0;
+    m.off_xc = off; off += align_up((uint32_t)m.JC * (DP + 1) * 8u, 16);
+    m.off_ts = off; off += align_up((uint32_t)kMeanTN * (D + 1) * 8u, 16);
+    m.off_out = off;
+    m.smem = off;
+    m.smem_hess = off + (uint32_t)kMeanTN * D * D * 8u;
+    return m;
+}
+
+// [nchunks][ JC*DP sqrt(w)-scaled inputs | JC b*alpha ], zero padded
+std::vector<double> pack_xchunks(int M, int D, int DP, int JC, int nchunks, const double* inputs,
+                                 const double* sqrt_w, const double* invQt, double b) {
+    std::vector<double> buf((size_t)nchunks * JC * (DP + 1), 0.0);
+    for (int j = 0; j < M; ++j) {
+        const int c = j / JC, jl = j - c * JC;
+        double* base = buf.data() + (size_t)c * JC * (DP + 1);
+        for (int d = 0; d < D; ++d) base[(size_t)jl * DP + d] = sqrt_w[d] * inputs[(size_t)j * D + d];
+        base[(size_t)JC * DP + jl] = b * invQt[j];
+    }
+    return buf;
+}
+
+int check_device(int device, int* sms) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(GPE_ERR_NO_DEVICE, "no CUDA device available (%s); libgpemu has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(GPE_ERR_INVALID, "device %d out of range [0, %d)", device, n);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GPE_ERR_NO_DEVICE, "device %d is sm_%d%d; libgpemu kernels are built for sm_100a only", device,
+                    prop.major, prop.minor);
+    *sms = prop.multiProcessorCount;
+    return GPE_OK;
+}
+
+void free_slot(Slot& s) {
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.st) cudaStreamDestroy(s.st);
+    s = Slot();
+}
+
+// Launch the kernels for device-resident data on `st`.  Output strides allow bank (point-major) layouts.
+int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                   double* hess, int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess,
+                   cudaStream_t st) {
+    if (N == 0) return GPE_OK;
+    bool mean_done = false;
+    if (var != nullptr) {
+        if (!m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
+        if (!m->full.valid)
+            return fail(GPE_ERR_UNSUPPORTED, "variance contraction supports M <= %d (got M = %d)", GPE_MAX_TRAIN, m->M);
+        const FullPlan& f = m->full;
+        FullParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
+        p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
+        p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
+        p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk; p.kbps = f.kbps;
+        p.nit = f.nit; p.nstage = f.nstage; p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b;
+        p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
+        p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;
+        p.stage_bytes = f.stage_bytes;
+        memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
+        const int64_t ntiles = (N + f.TN - 1) / f.TN;
+        const int grid = (int)std::min<int64_t>(ntiles, m->sms);
+        CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem, st));
+        mean_done = true;
+    }
+    const bool need_mean = !mean_done && (mu != nullptr || deriv != nullptr);
+    if (need_mean || hess != nullptr) {
+        const bool do_hess = hess != nullptr;
+        if (do_hess && m->DP > 12)
+            return fail(GPE_ERR_UNSUPPORTED, "Hessian output supports D <= 12 (got D = %d)", m->D);
+        MeanParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing; p.N = N;
+        p.mu = mean_done ? nullptr : mu;
+        p.deriv = mean_done ? nullptr : deriv;
+        p.hess = hess;
+        p.ld_mu = ld_mu; p.ld_deriv = ld_deriv; p.ld_hess = ld_hess;
+        p.xchunks = m->d_xchunks_mean; p.M = m->M; p.D = m->D; p.JC = m->mean.JC; p.nchunks = m->mean.nchunks;
+        p.off_xc = m->mean.off_xc; p.off_ts = m->mean.off_ts; p.off_out = m->mean.off_out;
+        memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
+        const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * 8);
+        const size_t smem = do_hess ? m->mean.smem_hess : m->mean.smem;
+        CUDA_TRY(launch_mean(m->DP, do_hess, p, grid, smem, st));
+    }
+    return GPE_OK;
+}
+
+bool is_pinned_or_null(const void* p) {
+    if (p == nullptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int ensure(double** ptr, size_t* cap, size_t need, bool host) {
+    if (*cap >= need) return GPE_OK;
+    if (*ptr) {
+        if (host) cudaFreeHost(*ptr); else cudaFree(*ptr);
+        *ptr = nullptr; *cap = 0;
+    }
+    if (host) CUDA_TRY(cudaMallocHost((void**)ptr, need));
+    else CUDA_TRY(cudaMalloc((void**)ptr, need));
+    *cap = need;
+    return GPE_OK;
+}
+
+// Host-resident caller: stream chunks through two slots so the H2D copy of chunk i+1, the kernels of chunk i
+// and the D2H copy of chunk i-1 overlap.  Pinned caller buffers are DMA'd directly; pageable ones are staged.
+int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                 double* hess) {
+    const int D = m->D;
+    const int64_t per_out = (mu ? 1 : 0) + (var ? 1 : 0) + (deriv ? D : 0) + (hess ? (int64_t)D * D : 0);
+    const bool direct = is_pinned_or_null(testing) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
+                        is_pinned_or_null(deriv) && is_pinned_or_null(hess);
+    const int64_t CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(N, 1));
+    for (auto& s : m->slots) {
+        if (!s.st) CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        int rc = ensure(&s.d_in, &s.d_in_cap, (size_t)CH * D * 8, false);
+        if (rc) return rc;
+        rc = ensure(&s.d_out, &s.d_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * 8, false);
+        if (rc) return rc;
+        if (!direct) {
+            rc = ensure(&s.h_in, &s.h_in_cap, (size_t)CH * D * 8, true);
+            if (rc) return rc;
+            rc = ensure(&s.h_out, &s.h_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * 8, true);
+            if (rc) return rc;
+        }
+        s.pending = false;
+    }
+    auto drain = [&](Slot& s) -> int {
+        if (!s.pending) return GPE_OK;
+        CUDA_TRY(cudaEventSynchronize(s.done));
+        const int64_t n0 = s.pend_n0, n = s.pend_n;
+        const double* src = s.h_out;
+        if (mu) { memcpy(mu + n0, src, (size_t)n * 8); src += n; }
+        if (var) { memcpy(var + n0, src, (size_t)n * 8); src += n; }
+        if (deriv) { memcpy(deriv + n0 * D, src, (size_t)n * D * 8); src += n * D; }
+        if (hess) { memcpy(hess + n0 * D * D, src, (size_t)n * D * D * 8); }
+        s.pending = false;
+        return GPE_OK;
+    };
+    int which = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
+        Slot& s = m->slots[which];
+        const int64_t n = std::min(CH, N - n0);
+        double* o = s.d_out;
+        double* d_mu = mu ? o : nullptr;   if (mu) o += n;
+        double* d_var = var ? o : nullptr; if (var) o += n;
+        double* d_der = deriv ? o : nullptr; if (deriv) o += n * D;
+        double* d_hes = hess ? o : nullptr;
+        if (direct) {
+            CUDA_TRY(cudaMemcpyAsync(s.d_in, testing + n0 * D, (size_t)n * D * 8, cudaMemcpyHostToDevice, s.st));
+        } else {
+            int rc = drain(s);  // the slot's previous results must leave the staging buffer first
+            if (rc) return rc;
+            memcpy(s.h_in, testing + n0 * D, (size_t)n * D * 8);
+            CUDA_TRY(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)n * D * 8, cudaMemcpyHostToDevice, s.st));
+        }
+        int rc = predict_device(m, s.d_in, n, d_mu, d_var, d_der, d_hes, 1, 1, D, (int64_t)D * D, s.st);
+        if (rc) return rc;
+        if (direct) {
+            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, d_mu, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st));
+            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, d_var, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st));
+            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, d_der, (size_t)n * D * 8, cudaMemcpyDeviceToHost, s.st));
+            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, d_hes, (size_t)n * D * D * 8, cudaMemcpyDeviceToHost, s.st));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * 8, cudaMemcpyDeviceToHost, s.st));
+            CUDA_TRY(cudaEventRecord(s.done, s.st));
+            s.pending = true; s.pend_n0 = n0; s.pend_n = n;
+        }
+    }
+    for (auto& s : m->slots) {
+        if (direct) CUDA_TRY(cudaStreamSynchronize(s.st));
+        else { int rc = drain(s); if (rc) return rc; }
+    }
+    return GPE_OK;
+}
+
+// ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
+constexpr int kProjRows = 4, kProjCols = 256;
+__global__ void __launch_bounds__(kProjCols) k_project(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
+                                                       int64_t lde, int64_t ldd, const double* __restrict__ basis,
+                                                       int E, int W, double* __restrict__ out) {
+    // CTA: 32 rows x 256 columns; thread: one column, 4 rows at a time; A rows staged in smem (broadcast reads)
+    __shared__ double a_s[32][33];
+    const int w = blockIdx.x * kProjCols + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * 32;
+    for (int i = threadIdx.x; i < 32 * E; i += kProjCols) {
+        const int rr = i / E, e = i - rr * E;
+        const int64_t r = r0 + rr;
+        a_s[rr][e] = (r < R) ? A[(r / RD) * ldn + (int64_t)e * lde + (r % RD) * ldd] : 0.0;
+    }
+    __syncthreads();
+    if (w >= W) return;
+    for (int rb = 0; rb < 32; rb += kProjRows) {
+        double acc[kProjRows] = {0, 0, 0, 0};
+        for (int e = 0; e < E; ++e) {
+            const double bv = __ldg(basis + (size_t)e * W + w);
+#pragma unroll
+            for (int i = 0; i < kProjRows; ++i) acc[i] = fma(a_s[rb + i][e], bv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kProjRows; ++i) {
+            const int64_t r = r0 + rb + i;
+            if (r < R) out[r * W + w] = acc[i];
+        }
+    }
+}
+
+uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
+    const uint64_t* p = (const uint64_t*)data;
+    const size_t n = bytes / 8;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+std::mutex g_wrap_mu;
+gpe_model* g_wrap_model = nullptr;
+uint64_t g_wrap_key = 0;
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* gpe_last_error(void) { return g_err; }
+int gpe_version(void) { return GPE_VERSION; }
+int64_t gpe_launch_count(void) { return g_launches.load(); }
+
+int gpe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gpe_model_create(int device, int M, int D, const double* inputs, const double* expX, const double* invQt,
+                     const double* invQ, gpe_model** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!inputs || !expX || !invQt) return fail(GPE_ERR_INVALID, "inputs, expX and invQt must be non-NULL");
+    if (M < 1) return fail(GPE_ERR_INVALID, "M must be >= 1 (got %d)", M);
+    if (D < 1 || D > GPE_MAX_INPUTS) return fail(GPE_ERR_INVALID, "D must be in [1, %d] (got %d)", GPE_MAX_INPUTS, D);
+    int sms = 0;
+    int rc = check_device(device, &sms);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    gpe_model* m = new gpe_model();
+    m->device = device; m->M = M; m->D = D; m->DP = pick_dp(D); m->sms = sms;
+    m->b = expX[D];
+    for (int d = 0; d < 32; ++d) m->sqrt_w[d] = (d < D) ? std::sqrt(expX[d]) : 0.0;
+    m->has_invQ = invQ != nullptr;
+    m->mean = plan_mean(M, D, m->DP);
+    {
+        std::vector<double> xc = pack_xchunks(M, D, m->DP, m->mean.JC, m->mean.nchunks, inputs, m->sqrt_w, invQt, m->b);
+        cudaError_t e = cudaMalloc((void**)&m->d_xchunks_mean, xc.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_xchunks_mean, xc.data(), xc.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
+    }
+    if (invQ) {
+        m->full = plan_full(M, D, m->DP);
+        if (m->full.valid) {
+            const FullPlan& f = m->full;
+            std::vector<double> xc = pack_xchunks(M, D, m->DP, f.JC, f.nchunks, inputs, m->sqrt_w, invQt, m->b);
+            // s_tiled[kb][j][c] = invQ[j][4 kb + c]
+            std::vector<double> st((size_t)f.kblk * f.Mp * 4, 0.0);
+            for (int j = 0; j < M; ++j)
+                for (int i = 0; i < M; ++i)
+                    st[((size_t)(i >> 2) * f.Mp + j) * 4 + (i & 3)] = invQ[(size_t)j * M + i];
+            cudaError_t e = cudaMalloc((void**)&m->d_xchunks_full, xc.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_xchunks_full, xc.data(), xc.size() * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_stiled, st.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_stiled, st.data(), st.size() * 8, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
+        }
+    }
+    *out = m;
+    return GPE_OK;
+}
+
+int gpe_model_destroy(gpe_model* m) {
+    if (!m) return GPE_OK;
+    cudaSetDevice(m->device);
+    for (auto& s : m->slots) free_slot(s);
+    if (m->d_xchunks_full) cudaFree(m->d_xchunks_full);
+    if (m->d_stiled) cudaFree(m->d_stiled);
+    if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
+    delete m;
+    return GPE_OK;
+}
+
+int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                unsigned flags, void* stream) {
+    if (!m) return fail(GPE_ERR_INVALID, "model is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing) return fail(GPE_ERR_INVALID, "testing is NULL");
+    if (!(flags & GPE_WANT_MU)) mu = nullptr;
+    if (!(flags & GPE_WANT_VAR)) var = nullptr;
+    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
+    if (!(flags & GPE_WANT_HESS)) hess = nullptr;
+    if ((flags & GPE_WANT_MU) && !mu) return fail(GPE_ERR_INVALID, "GPE_WANT_MU set but mu is NULL");
+    if ((flags & GPE_WANT_VAR) && !var) return fail(GPE_ERR_INVALID, "GPE_WANT_VAR set but var is NULL");
+    if ((flags & GPE_WANT_DERIV) && !deriv) return fail(GPE_ERR_INVALID, "GPE_WANT_DERIV set but deriv is NULL");
+    if ((flags & GPE_WANT_HESS) && !hess) return fail(GPE_ERR_INVALID, "GPE_WANT_HESS set but hess is NULL");
+    if (!mu && !var && !deriv && !hess) return fail(GPE_ERR_INVALID, "no output requested");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (flags & GPE_HOST_PTRS) return predict_host(m, testing, N, mu, var, deriv, hess);
+    return predict_device(m, testing, N, mu, var, deriv, hess, 1, 1, m->D, (int64_t)m->D * m->D,
+                          (cudaStream_t)stream);
+}
+
+int gpe_predict_wrap(const double* expX, const double* inputs, const double* invQt, const double* invQ,
+                     const double* testing, double* result, double* error, double* deriv, int Npredict, int Ntrain,
+                     int Ninputs, int theta_size) {
+    if (theta_size < Ninputs + 1) return fail(GPE_ERR_INVALID, "theta_size %d < Ninputs + 1", theta_size);
+    if (!expX || !inputs || !invQt || !invQ || !testing || !result || !error || !deriv)
+        return fail(GPE_ERR_INVALID, "NULL array argument");
+    if (Npredict < 0) return fail(GPE_ERR_INVALID, "Npredict < 0");
+    std::lock_guard<std::mutex> lock(g_wrap_mu);
+    uint64_t key = 1469598103934665603ull ^ ((uint64_t)Ntrain << 32 | (uint32_t)Ninputs);
+    key = fnv1a(expX, (size_t)(Ninputs + 1) * 8, key);
+    key = fnv1a(inputs, (size_t)Ntrain * Ninputs * 8, key);
+    key = fnv1a(invQt, (size_t)Ntrain * 8, key);
+    key = fnv1a(invQ, (size_t)Ntrain * Ntrain * 8, key);
+    if (!g_wrap_model || key != g_wrap_key) {
+        if (g_wrap_model) { gpe_model_destroy(g_wrap_model); g_wrap_model = nullptr; }
+        int rc = gpe_model_create(0, Ntrain, Ninputs, inputs, expX, invQt, invQ, &g_wrap_model);
+        if (rc) return rc;
+        g_wrap_key = key;
+    }
+    if (Npredict == 0) return GPE_OK;
+    std::vector<double> nd((size_t)Npredict * Ninputs);
+    int rc = gpe_predict(g_wrap_model, testing, Npredict, result, error, nd.data(), nullptr,
+                         GPE_WANT_MU | GPE_WANT_VAR | GPE_WANT_DERIV | GPE_HOST_PTRS, nullptr);
+    if (rc) return rc;
+    // the legacy extension hands deriv back as (Ninputs, Npredict); its caller transposes (GaussianProcess.py:321)
+    for (int n = 0; n < Npredict; ++n)
+        for (int d = 0; d < Ninputs; ++d) deriv[(size_t)d * Npredict + n] = nd[(size_t)n * Ninputs + d];
+    return GPE_OK;
+}
+
+int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const double* expX, const double* invQt,
+                    const double* invQ, const double* basis, int W, gpe_bank** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (E < 1) return fail(GPE_ERR_INVALID, "E must be >= 1");
+    if (basis && W < 1) return fail(GPE_ERR_INVALID, "basis given but W < 1");
+    gpe_bank* b = new gpe_bank();
+    b->device = device; b->E = E; b->M = M; b->D = D; b->W = basis ? W : 0;
+    for (int e = 0; e < E; ++e) {
+        gpe_model* m = nullptr;
+        int rc = gpe_model_create(device, M, D, inputs, expX + (size_t)e * (D + 1), invQt + (size_t)e * M,
+                                  invQ ? invQ + (size_t)e * M * M : nullptr, &m);
+        if (rc) { gpe_bank_destroy(b); return rc; }
+        b->models.push_back(m);
+    }
+    if (basis) {
+        cudaError_t e = cudaMalloc((void**)&b->d_basis, (size_t)E * W * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, basis, (size_t)E * W * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "basis upload failed: %s", cudaGetErrorString(e)); }
+    }
+    *out = b;
+    return GPE_OK;
+}
+
+int gpe_bank_destroy(gpe_bank* b) {
+    if (!b) return GPE_OK;
+    for (gpe_model* m : b->models) gpe_model_destroy(m);
+    if (b->d_basis) { cudaSetDevice(b->device); cudaFree(b->d_basis); }
+    delete b;
+    return GPE_OK;
+}
+
+int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                     double* hess, unsigned flags, void* stream) {
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (flags & GPE_HOST_PTRS) return fail(GPE_ERR_UNSUPPORTED, "gpe_bank_predict takes device pointers");
+    if (!testing) return fail(GPE_ERR_INVALID, "testing is NULL");
+    if (!(flags & GPE_WANT_MU)) mu = nullptr;
+    if (!(flags & GPE_WANT_VAR)) var = nullptr;
+    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
+    if (!(flags & GPE_WANT_HESS)) hess = nullptr;
+    if (!mu && !var && !deriv && !hess) return fail(GPE_ERR_INVALID, "no output requested");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int64_t E = b->E, D = b->D;
+    for (int64_t e = 0; e < E; ++e) {
+        int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var ? var + e : nullptr,
+                                deriv ? deriv + e * D : nullptr, hess ? hess + e * D * D : nullptr, E, E, E * D,
+                                E * D * D, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return GPE_OK;
+}
+
+int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t N, double* fwd, double* deriv_full,
+                     void* stream) {
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (!b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
+    if (N <= 0) return N == 0 ? GPE_OK : fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (b->E > 32) return fail(GPE_ERR_UNSUPPORTED, "back-projection supports E <= 32 (got %d)", b->E);
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int E = b->E, D = b->D, W = b->W;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned gx = (W + kProjCols - 1) / kProjCols;
+    if (fwd) {
+        if (!mu) return fail(GPE_ERR_INVALID, "fwd requested but mu is NULL");
+        int64_t R = N;
+        for (int64_t r0 = 0; r0 < R; r0 += 65535ll * 32) {  // gridDim.y limit
+            const int64_t rows = std::min<int64_t>(R - r0, 65535ll * 32);
+            dim3 grid(gx, (unsigned)((rows + 31) / 32));
+            g_launches.fetch_add(1);
+            k_project<<<grid, kProjCols, 0, st>>>(mu + r0 * E, rows, 1, E, 1, 0, b->d_basis, E, W, fwd + r0 * W);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (deriv_full) {
+        if (!deriv) return fail(GPE_ERR_INVALID, "deriv_full requested but deriv is NULL");
+        const int64_t R = N * D;
+        const int64_t step = (65535ll * 32) / D * D;  // whole points per launch
+        for (int64_t r0 = 0; r0 < R; r0 += step) {
+            const int64_t rows = std::min<int64_t>(R - r0, step);
+            dim3 grid(gx, (unsigned)((rows + 31) / 32));
+            g_launches.fetch_add(1);
+            k_project<<<grid, kProjCols, 0, st>>>(deriv + (r0 / D) * E * D, rows, D, (int64_t)E * D, D, 1, b->d_basis, E,
+                                                 W, deriv_full + r0 * W);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    return GPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// Host-side declarations of the per-DP kernel launchers (defined in predict_full_inst.cu, one object per DP).
+#pragma once
+#include <cuda_runtime.h>
+#include "predict_full.cuh"
+#include "predict_mean.cuh"
+
+namespace gpe {
+
+#define GPE_DECL_DP(DPV)                                                                                          \
+    cudaError_t launch_full_dp##DPV(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st);         \
+    cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st);
+
+GPE_DECL_DP(2)
+GPE_DECL_DP(4)
+GPE_DECL_DP(6)
+GPE_DECL_DP(8)
+GPE_DECL_DP(10)
+GPE_DECL_DP(12)
+GPE_DECL_DP(16)
+GPE_DECL_DP(24)
+GPE_DECL_DP(32)
+#undef GPE_DECL_DP
+
+// padded input dimensions that have compiled kernels, ascending
+static const int kDpList[] = {2, 4, 6, 8, 10, 12, 16, 24, 32};
+static const int kNumDp = sizeof(kDpList) / sizeof(kDpList[0]);
+
+}  // namespace gpe

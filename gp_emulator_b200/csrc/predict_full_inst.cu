@@ -1,0 +1,54 @@
+// Explicit instantiations of the fused predict kernels for one padded input dimension GPE_DP.
+// Compiled once per DP (-DGPE_DP=..) so the variants build in parallel; see Makefile.
+#include "predict_full.cuh"
+#include "predict_mean.cuh"
+#include "launch.h"
+
+#ifndef GPE_DP
+#error "compile with -DGPE_DP=<padded input dimension>"
+#endif
+
+#define GPE_CAT2(a, b) a##b
+#define GPE_CAT(a, b) GPE_CAT2(a, b)
+
+namespace gpe {
+
+template <int MT, int NT, int WR, int WC>
+static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = k_predict_full<MT, NT, WR, WC, GPE_DP>;
+    // per function AND per device: set on every launch (microseconds) so multi-device processes stay correct
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kFullThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_cfg<4, 8, 2, 4>(p, grid, smem, st);   // TN = 64, Mp <= 256
+        case 1: return launch_cfg<4, 8, 1, 8>(p, grid, smem, st);   // TN = 32, Mp <= 512
+        case 2: return launch_cfg<2, 16, 1, 8>(p, grid, smem, st);  // TN = 16, Mp <= 1024
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st) {
+    if (hess) {
+#if GPE_DP <= 12
+        auto kern = k_predict_mean<GPE_DP, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kMeanThreads, smem, st>>>(p);
+        return cudaGetLastError();
+#else
+        return cudaErrorNotSupported;
+#endif
+    }
+    auto kern = k_predict_mean<GPE_DP, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kMeanThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gpe

@@ -1,0 +1,171 @@
+// FP64 GP prediction without the variance: mean + input gradient (+ optional Hessian) in one pass.
+//
+//   mu_n    = sum_j k_nj alpha_j                                   reference GaussianProcess.py:237
+//   deriv_n = w_d sum_j k_nj alpha_j (x_jd - t_nd)                 reference GaussianProcess.py:244-247
+//   hess_n  = sum_j k_nj alpha_j [w_d (x_jd - t_nd) w_e (x_je - t_ne) - delta_de w_d]
+//                                                                  reference GaussianProcess.py:345-366
+// Used for predict(do_unc=False), for GaussianProcess.hessian and for models uploaded without invQ.
+// K* lives only in registers.  Thread (n, g): 8 points x 4 training-point lanes per warp, 4 warps per CTA
+// (32 points); the 4 lanes of a point are combined with two shuffle steps.  Outputs are staged through shared
+// memory so the (N, D) gradient and (N, D, D) Hessian rows are written fully coalesced.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gpe_math.cuh"
+
+namespace gpe {
+
+constexpr int kMeanThreads = 128;
+constexpr int kMeanTN = 32;
+
+struct MeanParams {
+    const double* testing;  // (N, D)
+    int64_t N;
+    double* mu;
+    double* deriv;
+    double* hess;
+    int64_t ld_mu, ld_deriv, ld_hess;  // element strides between consecutive points (1, D, D*D for a single GP)
+    const double* xchunks;  // [nchunks][ JC*DP xs | JC b*alpha ]
+    int M, D, JC, nchunks;
+    uint32_t off_xc, off_ts, off_out;  // smem byte offsets
+    double sqrt_w[32];
+};
+
+template <int DP, bool HESS>
+__global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams p) {
+    constexpr int TN = kMeanTN;
+    constexpr int NTRI = HESS ? DP * (DP + 1) / 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* Xc = reinterpret_cast<double*>(smem + p.off_xc);
+    double* ts_s = reinterpret_cast<double*>(smem + p.off_ts);   // [TN][D]; reused as [TN][D+1] outs
+    double* out_s = reinterpret_cast<double*>(smem + p.off_out); // HESS: [TN][D*D]
+    __shared__ double sqw_s[32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
+    const int D = p.D, M = p.M, DV = D + 1;
+    if (tid < 32) sqw_s[tid] = p.sqrt_w[tid];
+
+    const int64_t ntiles = (p.N + TN - 1) / TN;
+    bool x_resident = false;
+    const int chunk_doubles = p.JC * (DP + 1);
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = tile * TN;
+        const int npts = (int)min((int64_t)TN, p.N - n0);
+        __syncthreads();  // previous tile's staged outputs fully drained
+        for (int e = tid; e < TN * D; e += kMeanThreads) {
+            const int r = e / D;
+            const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
+            ts_s[e] = __ldg(p.testing + src);
+        }
+        __syncthreads();
+        double ts[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) ts[d] = (d < D) ? ts_s[n_loc * D + d] * sqw_s[d] : 0.0;
+
+        double mu = 0.0;
+        double g[DP];
+        double T[NTRI];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) g[d] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NTRI; ++i) T[i] = 0.0;
+
+        for (int c = 0; c < p.nchunks; ++c) {
+            if (!x_resident) {
+                __syncthreads();
+                const double2* src = reinterpret_cast<const double2*>(p.xchunks + (size_t)c * chunk_doubles);
+                double2* dst = reinterpret_cast<double2*>(Xc);
+                for (int e = tid; e < chunk_doubles / 2; e += kMeanThreads) dst[e] = __ldg(src + e);
+                __syncthreads();
+                if (p.nchunks == 1) x_resident = true;
+            }
+            const int jn = min(p.JC, M - c * p.JC);
+            const double* al = Xc + p.JC * DP;
+            for (int jl = g_low; jl < jn; jl += 4) {
+                const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
+                double u[DP];
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < DP; d += 2) {
+                    const double2 a = x1[d >> 1];
+                    u[d] = a.x - ts[d];
+                    u[d + 1] = a.y - ts[d + 1];
+                    r2 = fma(u[d], u[d], r2);
+                    r2 = fma(u[d + 1], u[d + 1], r2);
+                }
+                const double cj = exp_neg(-0.5 * r2) * al[jl];
+                mu += cj;
+                if (HESS) {
+                    int t = 0;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        const double cu = cj * u[d];
+                        g[d] += cu;
+#pragma unroll
+                        for (int e = d; e < DP; ++e) {
+                            T[t] = fma(cu, u[e], T[t]);
+                            ++t;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) g[d] = fma(cj, u[d], g[d]);
+                }
+            }
+        }
+
+        mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+        mu += __shfl_xor_sync(0xffffffffu, mu, 2);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            g[d] += __shfl_xor_sync(0xffffffffu, g[d], 1);
+            g[d] += __shfl_xor_sync(0xffffffffu, g[d], 2);
+        }
+        __syncthreads();  // everyone has read ts_s
+        double* outs = ts_s;
+        if (g_low == 0) {
+            outs[n_loc * DV] = mu;
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+                if (d < D) outs[n_loc * DV + 1 + d] = g[d];
+        }
+        if (HESS) {
+            int t = 0;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+#pragma unroll
+                for (int e = d; e < DP; ++e) {
+                    double v = T[t];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    ++t;
+                    if (g_low == 0 && e < D) {   // e < D implies d < D
+                        double h = sqw_s[d] * sqw_s[e] * v;
+                        if (d == e) h -= sqw_s[d] * sqw_s[d] * mu;
+                        out_s[n_loc * D * D + d * D + e] = h;
+                        out_s[n_loc * D * D + e * D + d] = h;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (p.mu != nullptr && tid < npts) p.mu[(n0 + tid) * p.ld_mu] = outs[tid * DV];
+        if (p.deriv != nullptr) {
+            for (int e = tid; e < npts * D; e += kMeanThreads) {
+                const int r = e / D, d = e - r * D;
+                p.deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
+            }
+        }
+        if (HESS && p.hess != nullptr) {
+            const int DD = D * D;
+            for (int e = tid; e < npts * DD; e += kMeanThreads) {
+                const int r = e / DD;
+                p.hess[(n0 + r) * p.ld_hess + (e - r * DD)] = out_s[e];
+            }
+        }
+    }
+}
+
+}  // namespace gpe

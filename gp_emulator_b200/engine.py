@@ -1,0 +1,175 @@
+"""Handles on device-resident models: thin, typed wrappers over the libgpemu C ABI.
+
+``DeviceModel`` is one trained GP on one GPU, ``DeviceBank`` is E GPs that share training inputs and test
+points (the per-PC emulators of a MultivariateEmulator, or a per-band bank).  Test points may be
+
+* numpy arrays (host): the library streams them through its pinned two-slot pipeline and the results
+  come back as numpy arrays; or
+* torch CUDA tensors (device): the call is asynchronous on torch's current stream and the results are
+  torch CUDA tensors -- PyTorch is used only to own the device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import WANT_DERIV, WANT_HESS, WANT_MU, WANT_VAR, HOST_PTRS, GpemuError, addr, check, f64c
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _current_stream_ptr(device_index):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class DeviceModel:
+    """One GP resident on one device.  Mirrors the state ``GaussianProcess.predict`` reads
+    (reference gp_emulator/GaussianProcess.py:228-249): inputs (M, D), theta (D+2), invQ (M, M), invQt (M)."""
+
+    def __init__(self, inputs, theta, invQt, invQ=None, device=0):
+        inputs = f64c(inputs)
+        if inputs.ndim != 2:
+            raise ValueError("inputs must be (M, D)")
+        self.M, self.D = inputs.shape
+        theta = f64c(theta).ravel()
+        if theta.size < self.D + 1:
+            raise ValueError(f"theta must hold at least D+1 = {self.D + 1} entries, got {theta.size}")
+        expx = np.exp(theta[: self.D + 1])
+        invQt = f64c(invQt).ravel()
+        if invQt.size != self.M:
+            raise ValueError("invQt must have M entries")
+        if invQ is not None:
+            invQ = f64c(invQ)
+            if invQ.shape != (self.M, self.M):
+                raise ValueError("invQ must be (M, M)")
+        self.device = int(device)
+        self.has_var = invQ is not None
+        h = C.c_void_p()
+        check(_lib.load().gpe_model_create(self.device, self.M, self.D, addr(inputs), addr(expx), addr(invQt),
+                                           addr(invQ), C.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, _lib.load().gpe_model_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def predict(self, testing, want_var=True, want_deriv=True, want_hess=False, want_mu=True):
+        """Returns a dict with the requested arrays among mu (N,), var (N,), deriv (N, D), hess (N, D, D)."""
+        lib = _lib.load()
+        D = self.D
+        if want_var and not self.has_var:
+            raise GpemuError("variance requested but the model was uploaded without invQ")
+        flags = (WANT_MU if want_mu else 0) | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0) | (
+            WANT_HESS if want_hess else 0)
+        if _is_torch(testing):
+            import torch
+            t = testing
+            if not t.is_cuda or t.device.index != self.device:
+                raise ValueError(f"torch test points must live on cuda:{self.device}")
+            if t.dtype != torch.float64 or t.dim() != 2 or t.shape[1] != D:
+                raise ValueError(f"testing must be float64 (N, {D})")
+            t = t.contiguous()
+            N = t.shape[0]
+            mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=t.device)
+            out = {}
+            if want_mu: out["mu"] = mk(N)
+            if want_var: out["var"] = mk(N)
+            if want_deriv: out["deriv"] = mk(N, D)
+            if want_hess: out["hess"] = mk(N, D, D)
+            check(lib.gpe_predict(self._h, addr(t), N, addr(out.get("mu")), addr(out.get("var")),
+                                  addr(out.get("deriv")), addr(out.get("hess")), flags,
+                                  _current_stream_ptr(self.device)))
+            return out
+        t = f64c(testing)
+        if t.ndim != 2 or t.shape[1] != D:
+            raise ValueError(f"testing must be (N, {D})")
+        N = t.shape[0]
+        out = {}
+        if want_mu: out["mu"] = np.empty(N)
+        if want_var: out["var"] = np.empty(N)
+        if want_deriv: out["deriv"] = np.empty((N, D))
+        if want_hess: out["hess"] = np.empty((N, D, D))
+        check(lib.gpe_predict(self._h, addr(t), N, addr(out.get("mu")), addr(out.get("var")),
+                              addr(out.get("deriv")), addr(out.get("hess")), flags | HOST_PTRS, None))
+        return out
+
+
+class DeviceBank:
+    """E GPs sharing training inputs and test points; optional PCA basis (E, W) for back-projection."""
+
+    def __init__(self, inputs, thetas, invQts, invQs=None, basis=None, device=0):
+        inputs = f64c(inputs)
+        self.M, self.D = inputs.shape
+        thetas = f64c(thetas)
+        if thetas.ndim != 2 or thetas.shape[1] < self.D + 1:
+            raise ValueError("thetas must be (E, >= D+1)")
+        self.E = thetas.shape[0]
+        expx = f64c(np.exp(thetas[:, : self.D + 1]))
+        invQts = f64c(invQts)
+        if invQts.shape != (self.E, self.M):
+            raise ValueError("invQts must be (E, M)")
+        if invQs is not None:
+            invQs = f64c(invQs)
+            if invQs.shape != (self.E, self.M, self.M):
+                raise ValueError("invQs must be (E, M, M)")
+        self.W = 0
+        if basis is not None:
+            basis = f64c(basis)
+            if basis.ndim != 2 or basis.shape[0] != self.E:
+                raise ValueError("basis must be (E, W)")
+            self.W = basis.shape[1]
+        self.device = int(device)
+        self.has_var = invQs is not None
+        h = C.c_void_p()
+        check(_lib.load().gpe_bank_create(self.device, self.E, self.M, self.D, addr(inputs), addr(expx),
+                                          addr(invQts), addr(invQs), addr(basis), self.W, C.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, _lib.load().gpe_bank_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def predict(self, testing, want_var=True, want_deriv=True, want_hess=False, project=False,
+                project_deriv=False):
+        """Point-major outputs: mu (N, E), var (N, E), deriv (N, E, D), hess (N, E, D, D);
+        with ``project``: fwd (N, W) = mu @ basis; with ``project_deriv``: deriv_full (N, D, W).
+        numpy in -> numpy out (copied through torch device buffers); torch CUDA in -> torch CUDA out."""
+        import torch
+        lib = _lib.load()
+        D, E = self.D, self.E
+        if want_var and not self.has_var:
+            raise GpemuError("variance requested but the bank was uploaded without invQ")
+        as_numpy = not _is_torch(testing)
+        dev = torch.device("cuda", self.device)
+        if as_numpy:
+            t = torch.from_numpy(f64c(testing)).to(dev)
+        else:
+            t = testing.contiguous()
+        if t.dim() != 2 or t.shape[1] != D or t.dtype != torch.float64:
+            raise ValueError(f"testing must be float64 (N, {D})")
+        N = t.shape[0]
+        mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
+        out = {"mu": mk(N, E)}
+        flags = WANT_MU
+        if want_var: out["var"] = mk(N, E); flags |= WANT_VAR
+        if want_deriv or project_deriv: out["deriv"] = mk(N, E, D); flags |= WANT_DERIV
+        if want_hess: out["hess"] = mk(N, E, D, D); flags |= WANT_HESS
+        st = _current_stream_ptr(self.device)
+        check(lib.gpe_bank_predict(self._h, addr(t), N, addr(out["mu"]), addr(out.get("var")),
+                                   addr(out.get("deriv")), addr(out.get("hess")), flags, st))
+        if project or project_deriv:
+            if self.W == 0:
+                raise GpemuError("bank has no basis functions to project onto")
+            if project: out["fwd"] = mk(N, self.W)
+            if project_deriv: out["deriv_full"] = mk(N, D, self.W)
+            check(lib.gpe_bank_project(self._h, addr(out["mu"]), addr(out.get("deriv")), N, addr(out.get("fwd")),
+                                       addr(out.get("deriv_full")), st))
+        if as_numpy:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out

@@ -1,0 +1,164 @@
+"""Drop-in ``GaussianProcess`` (same constructor, attributes and method names as the reference class in
+gp_emulator/GaussianProcess.py:28-366) whose prediction runs on the B200 engine.
+
+Training (``learn_hyperparameters`` and the invQ / invQt precompute) stays on the host in numpy, as the
+scope requires; it is restated here only so the class is usable under Python 3 (the reference file is
+Python 2).  ``predict`` and ``hessian`` always go through libgpemu: there is no CPU prediction path, and the
+``is_gpu`` / ``threshold`` arguments of the reference signature are accepted and ignored (chunking lives
+below the C ABI).  Model attributes (``inputs, theta, invQ, invQt``) stay plain numpy arrays and are
+re-read at every call -- the reference's own benchmark overwrites them between calls
+(tests/benchmark.py:11-15) -- with the device copy cached on their contents.
+"""
+from __future__ import annotations
+
+import warnings
+import zlib
+
+import numpy as np
+
+from .engine import DeviceModel
+
+
+def k_fold_cross_validation(X, K, randomise=False):
+    """K (training, validation) partitions of X (reference GaussianProcess.py:9-26)."""
+    import random
+    items = list(X)
+    if randomise:
+        random.shuffle(items)
+    for k in range(K):
+        yield ([x for i, x in enumerate(items) if i % K != k], [x for i, x in enumerate(items) if i % K == k])
+
+
+def _digest(*arrays):
+    h = 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h = zlib.crc32(memoryview(a).cast("B"), h)
+        h = zlib.crc32(repr(a.shape).encode(), h)
+    return h
+
+
+class GaussianProcess:
+    """Squared-exponential (ARD) GP emulator.  ``inputs`` (Ntrain, Ninputs), ``targets`` (Ntrain,)."""
+
+    def __init__(self, inputs, targets, device=0):
+        self.inputs = inputs
+        self.targets = targets
+        (self.n, self.D) = self.inputs.shape
+        self.device = device
+        self._dev_model = None
+        self._dev_key = None
+
+    # ------------------------------------------------------------------ host training path (numpy)
+    def _prepare_likelihood(self):
+        """Q, invQ, invQt, log|Q| for the current theta (reference GaussianProcess.py:52-75)."""
+        e = np.exp(self.theta)
+        x = np.asarray(self.inputs, dtype=np.float64)
+        diff2 = (x[:, None, :] - x[None, :, :]) ** 2
+        self.Z = e[self.D] * np.exp(-0.5 * np.tensordot(diff2, e[: self.D], axes=([2], [0])))
+        self.Q = self.Z + e[self.D + 1] * np.eye(self.n)
+        self.invQ = np.linalg.inv(self.Q)
+        self.invQt = np.dot(self.invQ, self.targets)
+        self.logdetQ = 2.0 * np.sum(np.log(np.diag(np.linalg.cholesky(self.Q))))
+
+    def loglikelihood(self, theta):
+        """Negative log marginal likelihood at ``theta`` (reference GaussianProcess.py:78-95)."""
+        self._set_params(theta)
+        ll = 0.5 * self.logdetQ + 0.5 * np.dot(self.targets, self.invQt) + 0.5 * self.n * np.log(2.0 * np.pi)
+        self.current_theta = theta
+        self.current_loglikelihood = ll
+        return ll
+
+    def partial_devs(self, theta):
+        """Gradient of ``loglikelihood`` w.r.t. theta (reference GaussianProcess.py:97-125)."""
+        out = np.zeros(self.D + 2)
+        x = np.asarray(self.inputs, dtype=np.float64)
+        a = self.invQt
+        for d in range(self.D):
+            V = (x[:, d][:, None] - x[:, d][None, :]) ** 2 * self.Z
+            out[d] = np.exp(self.theta[d]) * (np.dot(a, np.dot(V, a)) - np.sum(self.invQ * V)) / 4.0
+        out[self.D] = 0.5 * np.sum(self.invQ * self.Z) - 0.5 * np.dot(a, np.dot(self.Z, a))
+        noise = np.exp(self.theta[self.D + 1])
+        out[self.D + 1] = 0.5 * np.trace(self.invQ) * noise - 0.5 * np.dot(a, a) * noise
+        return out
+
+    def _set_params(self, theta):
+        """Fix the hyper-parameters and precompute what predict needs (reference GaussianProcess.py:127-139)."""
+        self.theta = theta
+        self._prepare_likelihood()
+
+    def _learn(self, theta0, verbose):
+        """One L-BFGS-B descent from ``theta0`` (reference GaussianProcess.py:141-181)."""
+        from scipy.optimize import fmin_l_bfgs_b
+        self._set_params(theta0)
+        try:
+            # (scipy >= 1.15 dropped the iprint argument the reference passes; verbose reports the result instead)
+            res = fmin_l_bfgs_b(self.loglikelihood, theta0, fprime=self.partial_devs, factr=0.1, pgtol=1e-20)
+            if verbose:
+                print("L-BFGS-B: cost %e after %d evaluations (%s)" % (res[1], res[2]["funcalls"], res[2]["task"]))
+        except np.linalg.LinAlgError:
+            warnings.warn("Optimisation resulted in linear algebra error. Returning last loglikelihood "
+                          "calculated, but this is fishy", RuntimeWarning)
+            res = [self.current_theta, 9999]
+        return res
+
+    def learn_hyperparameters(self, n_tries=15, verbose=False):
+        """Multi-start fit; returns (min cost, theta) (reference GaussianProcess.py:183-209)."""
+        costs, params = [], []
+        for theta in 5.0 * (np.random.rand(n_tries, self.D + 2) - 0.5):
+            T = self._learn(theta, verbose)
+            costs.append(T[1])
+            params.append(T[0])
+        costs = np.array(costs)
+        idx = int(np.argsort(costs)[0])
+        print("After %d, the minimum cost was %e" % (n_tries, costs[idx]))
+        self._set_params(params[idx])
+        return costs[idx], params[idx]
+
+    # ------------------------------------------------------------------ device prediction path
+    def _device_model(self):
+        """Device copy of the current numpy state, re-uploaded only when the arrays' contents change."""
+        invQ = getattr(self, "invQ", None)
+        arrays = (self.inputs, self.theta, self.invQt) + (() if invQ is None else (invQ,))
+        key = (_digest(*arrays), invQ is not None, self.device)
+        if self._dev_model is None or key != self._dev_key:
+            if self._dev_model is not None:
+                self._dev_model.close()
+            self._dev_model = DeviceModel(self.inputs, self.theta, self.invQt, invQ, device=self.device)
+            self._dev_key = key
+        return self._dev_model
+
+    def predict(self, testing, do_unc=True, do_deriv=True, is_gpu=True, precision=np.float64, threshold=2e5):
+        """Mean, variance and input gradient at ``testing`` (N, D)  (reference GaussianProcess.py:327-341).
+
+        Returns ``(mu, var, deriv)``; ``(mu, deriv)`` if ``do_unc`` is False (as the reference's CPU branch,
+        :248-251); ``(mu, var)`` / ``mu`` when ``do_deriv`` is False (the upstream-style signature).
+        ``deriv`` is (N, D).  Computation is FP64 on the GPU; ``precision`` only casts the numpy results.
+        ``testing`` may also be a float64 torch CUDA tensor, in which case torch tensors are returned.
+        """
+        if getattr(testing, "ndim", None) != 2 and not hasattr(testing, "dim"):
+            raise ValueError("testing must always be a 2-D array (N, D)")
+        if testing.shape[1] != self.D:
+            raise AssertionError("testing has %d columns, model has D = %d" % (testing.shape[1], self.D))
+        out = self._device_model().predict(testing, want_var=do_unc, want_deriv=do_deriv)
+        res = [out["mu"]]
+        if do_unc:
+            res.append(out["var"])
+        if do_deriv:
+            res.append(out["deriv"])
+        if isinstance(res[0], np.ndarray) and precision is not np.float64:
+            res = [precision(r) for r in res]
+        return tuple(res) if len(res) > 1 else res[0]
+
+    # the reference exposes these two names as well; both are the device path here
+    def gpu_predict(self, testing, precision=np.float64, threshold=2e5):
+        """``(result, error, deriv)`` as the reference GPU branch returns them (GaussianProcess.py:273-323)."""
+        return self.predict(testing, do_unc=True, do_deriv=True, precision=precision, threshold=threshold)
+
+    def hessian(self, testing):
+        """(N, D, D) Hessian of the predictive mean (reference GaussianProcess.py:345-366)."""
+        if testing.shape[1] != self.D:
+            raise AssertionError("testing has %d columns, model has D = %d" % (testing.shape[1], self.D))
+        out = self._device_model().predict(testing, want_mu=False, want_var=False, want_deriv=False,
+                                                want_hess=True)
+        return out["hess"]

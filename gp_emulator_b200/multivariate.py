@@ -1,0 +1,124 @@
+"""Drop-in ``MultivariateEmulator`` (reference gp_emulator/multivariate_gp.py:38-222): PCA-compressed
+multivariate output, one GP per principal component, prediction on the B200 engine.
+
+Construction (SVD, npz load/save, per-PC training) is host-side numpy, same npz wire format as the
+reference (``X, y, hyperparams, thresh, basis_functions, n_pcs``).  ``predict`` keeps the reference's
+single-point call and return shapes, and additionally accepts N > 1 points (the reference cannot:
+multivariate_gp.py:216 fails to broadcast), evaluated as one bank launch plus one back-projection.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+
+import numpy as np
+
+from .engine import DeviceBank
+from .gaussian_process import GaussianProcess
+
+
+class MultivariateEmulator(object):
+    def __init__(self, dump=None, X=None, y=None, hyperparams=None, thresh=0.98, n_tries=5, device=0):
+        """See reference multivariate_gp.py:40-121.  ``X`` (N_train, N_full) model outputs, ``y``
+        (N_train, N_params) the parameters that produced them, ``hyperparams`` (N_params + 2, n_pcs)."""
+        basis_functions = None
+        n_pcs = None
+        if dump is not None:
+            if X is not None or y is not None:
+                raise ValueError("You specified both a dump file and X and y")
+            with np.load(dump) as f:
+                X = f["X"]
+                y = f["y"]
+                hyperparams = f["hyperparams"]
+                if "thresh" in f:
+                    thresh = float(f["thresh"])
+                if "basis_functions" in f:
+                    basis_functions = f["basis_functions"]
+                    n_pcs = int(f["n_pcs"])
+            if basis_functions is None:
+                # older dumps carry no basis: decompose once and rewrite the file (reference :79-90)
+                self.calculate_decomposition(X, thresh)
+                basis_functions, n_pcs = self.basis_functions, self.n_pcs
+                tmp = os.path.join("/tmp", os.path.basename(dump))
+                np.savez_compressed(tmp, X=X, y=y, hyperparams=hyperparams, thresh=thresh,
+                                    basis_functions=basis_functions, n_pcs=n_pcs)
+                shutil.move(tmp if tmp.endswith(".npz") else tmp + ".npz", dump)
+        else:
+            if X is None or y is None:
+                raise ValueError("Need to specify both X and y")
+            assert X.shape[0] == y.shape[0]
+            assert X.ndim == 2
+            assert y.ndim == 2
+
+        self.X_train = X
+        self.y_train = y
+        self.thresh = thresh
+        self.device = device
+        if basis_functions is None:
+            self.calculate_decomposition(X, thresh)
+            basis_functions, n_pcs = self.basis_functions, self.n_pcs
+        self.n_pcs = int(n_pcs)
+        self.basis_functions = basis_functions
+        if hyperparams is not None:
+            assert (y.shape[1] + 2 == hyperparams.shape[0]) and (self.n_pcs == hyperparams.shape[1])
+        self._bank = None
+        self.train_emulators(X, y, hyperparams=hyperparams, n_tries=n_tries)
+
+    def dump_emulator(self, fname):
+        """Save for reuse, reference npz format (multivariate_gp.py:124-137)."""
+        np.savez_compressed(fname, X=self.X_train, y=self.y_train, hyperparams=self.hyperparams,
+                            thresh=self.thresh, basis_functions=self.basis_functions, n_pcs=self.n_pcs)
+
+    def calculate_decomposition(self, X, thresh):
+        """PCA by SVD; keep the components whose cumulative singular-value share is <= thresh
+        (reference multivariate_gp.py:140-160)."""
+        _, s, V = np.linalg.svd(X, full_matrices=True)
+        keep = (s.cumsum() / s.sum()) <= thresh
+        self.basis_functions = V[: keep.size][keep]
+        self.n_pcs = int(np.sum(keep))
+
+    def train_emulators(self, X, y, hyperparams, n_tries=2):
+        """One GP per PC on the compressed outputs (reference multivariate_gp.py:162-188)."""
+        self.emulators = []
+        train_data = self.compress(X)
+        self.hyperparams = np.zeros((2 + y.shape[1], self.n_pcs))
+        for i in range(self.n_pcs):
+            gp = GaussianProcess(np.atleast_2d(y), train_data[i], device=self.device)
+            if hyperparams is None:
+                self.hyperparams[:, i] = gp.learn_hyperparameters(n_tries=n_tries)[1]
+            else:
+                self.hyperparams[:, i] = hyperparams[:, i]
+                gp._set_params(hyperparams[:, i])
+            self.emulators.append(gp)
+        self._bank = None
+
+    def compress(self, X):
+        """Project full-rank vectors onto the PC basis (reference multivariate_gp.py:191-193)."""
+        return X.dot(self.basis_functions.T).T
+
+    def _device_bank(self):
+        if self._bank is None:
+            gps = self.emulators
+            self._bank = DeviceBank(np.atleast_2d(self.y_train), np.stack([g.theta for g in gps]),
+                                    np.stack([g.invQt for g in gps]), np.stack([g.invQ for g in gps]),
+                                    basis=self.basis_functions[: self.n_pcs], device=self.device)
+        return self._bank
+
+    def predict(self, y, do_deriv=True, is_gpu=True):
+        """Reconstruct the full output (and its Jacobian) at parameter vector(s) ``y``.
+
+        One point, as in the reference (multivariate_gp.py:195-222): returns ``fwd (N_full,)`` and
+        ``deriv (N_params, N_full)``.  N > 1 points (new): ``fwd (N, N_full)``, ``deriv (N, N_params, N_full)``.
+        """
+        y2 = np.atleast_2d(y)
+        out = self._device_bank().predict(y2, want_var=False, want_deriv=False, project=True,
+                                          project_deriv=do_deriv)
+        fwd = out["fwd"]
+        if y2.shape[0] == 1:
+            fwd = fwd[0]
+            return (fwd, out["deriv_full"][0]) if do_deriv else fwd
+        return (fwd, out["deriv_full"]) if do_deriv else fwd
+
+    def predict_pcs(self, y, do_unc=True, do_deriv=True):
+        """PC-space outputs for N points: dict with mu (N, P), var (N, P), deriv (N, P, D)."""
+        return self._device_bank().predict(np.atleast_2d(y), want_var=do_unc, want_deriv=do_deriv)

@@ -1,0 +1,123 @@
+/* gpemu.h -- C ABI of libgpemu.so: the B200-native GP-emulator prediction engine.
+ *
+ * Drop-in boundary for the prediction hot path of UCL/gp_emulator.  Every entry point states the
+ * reference interface it replaces (paths relative to the reference checkout).  Plain C: pointers and
+ * sizes only; no CPython, numpy or torch types.  All matrices are ROW-MAJOR (C order), exactly as
+ * numpy hands them over -- the reference's host-side transposes to column-major
+ * (gp_emulator/gpu/_gpu_predict.cpp:129-132) do not exist here.
+ *
+ * Error convention: every function returns GPE_OK (0) or a negative gpe_status; the message of the
+ * last failure on the calling thread is available from gpe_last_error().  Nothing here calls
+ * exit() (the reference does: gp_emulator/gpu/gpu_predict.h:131-154, kernel_cdist.cu:28-32).
+ *
+ * Threading: a handle may be used from one host thread at a time.  Calls with device pointers are
+ * asynchronous on the given stream; calls with host pointers return after the outputs are written.
+ */
+#ifndef GPEMU_H_
+#define GPEMU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPE_VERSION 100
+
+typedef enum gpe_status {
+    GPE_OK = 0,
+    GPE_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size) */
+    GPE_ERR_CUDA = -2,         /* a CUDA runtime call failed; see gpe_last_error() */
+    GPE_ERR_NO_DEVICE = -3,    /* no usable sm_100 device */
+    GPE_ERR_UNSUPPORTED = -4   /* valid request this build cannot serve (e.g. M > GPE_MAX_TRAIN) */
+} gpe_status;
+
+/* flags for the predict entry points */
+#define GPE_WANT_MU     0x01u
+#define GPE_WANT_VAR    0x02u  /* needs invQ at model creation */
+#define GPE_WANT_DERIV  0x04u
+#define GPE_WANT_HESS   0x08u
+#define GPE_HOST_PTRS   0x100u /* testing/outputs are host pointers: the library streams them */
+
+#define GPE_MAX_TRAIN 1024     /* largest M served by the register-resident variance contraction */
+#define GPE_MAX_INPUTS 32      /* largest D */
+
+typedef struct gpe_model gpe_model;  /* one trained GP resident on one device */
+typedef struct gpe_bank gpe_bank;    /* E GPs sharing training inputs (MultivariateEmulator / per-band bank) */
+
+const char* gpe_last_error(void);
+int gpe_version(void);
+int gpe_device_count(void);
+
+/* Upload one trained GP.
+ * Replaces the per-call model upload of gpuPredict::init_gpu (gp_emulator/gpu/predict.cu:11-34) and the
+ * model flattening in GaussianProcess.gpu_predict (gp_emulator/GaussianProcess.py:289-292); the model
+ * stays resident behind the handle instead of being re-sent for every 2e5-point block.
+ *   inputs  (M, D)  training inputs          == self.inputs
+ *   expX    (D+1)   exp(theta)[0..D]         == np.exp(self.theta): D inverse squared length scales, then
+ *                                               the signal variance (theta[D+1], the noise, is unused by predict)
+ *   invQt   (M)     == self.invQt
+ *   invQ    (M, M)  == self.invQ, may be NULL if variance is never requested
+ * All host pointers, float64. */
+int gpe_model_create(int device, int M, int D, const double* inputs, const double* expX,
+                     const double* invQt, const double* invQ, gpe_model** out);
+int gpe_model_destroy(gpe_model* m);
+
+/* Predict N test points: the whole of GaussianProcess.cpu_predict / gpu_predict
+ * (gp_emulator/GaussianProcess.py:211-251, :273-323) and gpuPredict::predict
+ * (gp_emulator/gpu/predict.cu:168-176) in one fused pass.
+ *   testing (N, D) row-major; mu (N); var (N); deriv (N, D) row-major -- NOT the (D, N) layout the
+ *   legacy extension returned (GaussianProcess.py:321).  hess (N, D, D) as GaussianProcess.hessian
+ *   (GaussianProcess.py:345-366).  Output pointers whose GPE_WANT_* bit is clear may be NULL.
+ *   Without GPE_HOST_PTRS all pointers are device pointers on the model's device and the call is
+ *   asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream).  Any N >= 0 is accepted
+ *   (the reference exits for N < 1000, kernel_cdist.cu:28-32, and for N*M > 6.7e7, kernel_matrixExp.cu:29-33). */
+int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                double* hess, unsigned flags, void* stream);
+
+/* Binary-compatible stand-in for the legacy native entry point
+ *   _gpu_predict.predict_wrap(expX, inputs, invQt, invQ, testing, result, error, deriv,
+ *                             Npredict, Ntrain, Ninputs, theta_size)
+ * (gp_emulator/gpu/_gpu_predict.cpp:115-159; call site gp_emulator/GaussianProcess.py:313-316):
+ * same argument order and meaning, host float64 arrays flattened row-major, outputs written in place,
+ * and -- for compatibility with the caller's reshape at GaussianProcess.py:321 -- deriv is written as
+ * (Ninputs, Npredict).  Uses device 0 and a cached model keyed on the argument contents. */
+int gpe_predict_wrap(const double* expX, const double* inputs, const double* invQt, const double* invQ,
+                     const double* testing, double* result, double* error, double* deriv,
+                     int Npredict, int Ntrain, int Ninputs, int theta_size);
+
+/* Bank of E GPs that share the training inputs (M, D) and the test points, each with its own
+ * hyper-parameters: the per-PC emulators of MultivariateEmulator (gp_emulator/multivariate_gp.py:176-188)
+ * and the per-band banks of tests/test_perband_emulator.py:22-37.
+ *   expX (E, D+1); invQt (E, M); invQ (E, M, M) or NULL;
+ *   basis (E, W) or NULL: MultivariateEmulator.basis_functions for the PCA back-projection. */
+int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const double* expX,
+                    const double* invQt, const double* invQ, const double* basis, int W, gpe_bank** out);
+int gpe_bank_destroy(gpe_bank* b);
+
+/* Bank prediction on shared test points.  Outputs are point-major:
+ *   mu (N, E), var (N, E), deriv (N, E, D), hess (N, E, D, D).
+ * Replaces the Python loop over emulators in MultivariateEmulator.predict
+ * (gp_emulator/multivariate_gp.py:214-218) and over bands in tests/test_perband_emulator.py:39-47. */
+int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var,
+                     double* deriv, double* hess, unsigned flags, void* stream);
+
+/* PCA back-projection of bank means: fwd (N, W) = mu (N, E) @ basis (E, W)
+ * (the accumulation `fwd += pred_mu * basis_functions[i]`, gp_emulator/multivariate_gp.py:216, batched
+ * over N points), and optionally deriv_full (N, D, W) = sum_e deriv[n, e, d] * basis[e, w] (:218).
+ * Device pointers; mu/deriv as produced by gpe_bank_predict. */
+int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t N, double* fwd,
+                     double* deriv_full, void* stream);
+
+/* FP64 pipe peaks of the device, measured live (roofline denominators the driver's
+ * MEASURED_PEAKS.json does not hold).  out9: DFMA TFLOP/s, DMMA TFLOP/s, mixed total, mixed DFMA part,
+ * mixed DMMA part, gpe exp Gexp/s, CUDA exp Gexp/s, SM MHz under FP64 load, SM count. */
+int gpe_measure_fp64_peaks(int device, double* out9);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches claim). */
+int64_t gpe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPEMU_H_ */

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Freeze outputs of the REFERENCE implementation into tests/golden/*.npz.
+
+Run in the build container only (needs /root/reference); the fixtures it writes are committed and travel
+to the GPU box, the reference does not.
+
+The reference package is Python 2 (print statements, xrange, tab/space mixing) and imports its compiled
+``_gpu_predict`` at module scope, so it cannot be imported.  This script reads the reference *source text*,
+applies a purely mechanical token-level py2->py3 conversion IN MEMORY (nothing is written to disk, no
+reference source enters this repository) and executes the result.  All arithmetic that produces the
+goldens is therefore the reference's own numpy/scipy code:
+
+  GaussianProcess.predict / cpu_predict   gp_emulator/GaussianProcess.py:211-251, 327-341
+  GaussianProcess.hessian                 gp_emulator/GaussianProcess.py:345-366
+  GaussianProcess._set_params             gp_emulator/GaussianProcess.py:52-75, 127-139
+  MultivariateEmulator (dump=...) .predict gp_emulator/multivariate_gp.py:40-121, 195-222
+
+    python tests/golden/make_golden.py
+"""
+import hashlib
+import os
+import re
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import gp_oracle as orc  # noqa: E402  (input generators only; outputs come from the reference)
+
+
+def py2to3(src):
+    src = src.expandtabs(8)
+    src = re.sub(r"^(\s*)import _gpu_predict\s*$", r"\1pass", src, flags=re.M)
+    src = src.replace("xrange", "range").replace("np.int(", "int(")
+    src = re.sub(r"^(\s*)print (.*?),?\s*$", r"\1print(\2)", src, flags=re.M)
+    src = re.sub(r"raise ValueError, (\".*?\")", r"raise ValueError(\1)", src)
+    src = src.replace("from GaussianProcess import GaussianProcess", "")
+    return src
+
+
+def load_reference():
+    gp_mod = types.ModuleType("ref_GaussianProcess")
+    with open(os.path.join(REF, "gp_emulator", "GaussianProcess.py")) as f:
+        exec(compile(py2to3(f.read()), "ref:GaussianProcess.py", "exec"), gp_mod.__dict__)
+    mv_mod = types.ModuleType("ref_multivariate_gp")
+    mv_mod.GaussianProcess = gp_mod.GaussianProcess
+    with open(os.path.join(REF, "gp_emulator", "multivariate_gp.py")) as f:
+        exec(compile(py2to3(f.read()), "ref:multivariate_gp.py", "exec"), mv_mod.__dict__)
+    return gp_mod.GaussianProcess, mv_mod.MultivariateEmulator
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
+def ref_gp(RefGP, inputs, theta, invQ, invQt):
+    gp = RefGP(inputs, [])
+    gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt      # exactly how tests/benchmark.py:11-15 sets them
+    return gp
+
+
+def main():
+    RefGP, RefMV = load_reference()
+
+    # ---- S: tests/benchmark.py-style all-U(0,1) model (config 1 and config 3 shapes) ---------------
+    for tag, (M, D, N, seed, nh) in {"S250": (250, 10, 300, 0, 40), "S1000": (1000, 10, 64, 3, 0),
+                                     "S37": (37, 3, 130, 5, 130)}.items():
+        inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed)
+        gp = ref_gp(RefGP, inputs, theta, invQ, invQt)
+        mu, var, deriv = gp.predict(testing)
+        mu2, deriv2 = gp.predict(testing, do_unc=False)
+        assert np.array_equal(mu, mu2) and np.array_equal(deriv, deriv2)
+        out = dict(M=M, D=D, N=N, seed=seed, input_sha=sha(inputs, theta, invQ, invQt, testing), mu=mu, var=var,
+                   deriv=deriv)
+        if nh:
+            out["hess"] = gp.hessian(testing[:nh])
+        np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)
+        print(tag, "mu[:2]", mu[:2], "var[:2]", var[:2])
+
+    # ---- T: genuinely conditioned model through the reference's own _set_params ---------------------
+    inputs, targets, theta, _, _, testing = orc.make_T_model(M=100, D=4, N=200, seed=1)
+    gp = RefGP(inputs, targets)
+    gp._set_params(theta)
+    mu, var, deriv = gp.predict(testing)
+    hess = gp.hessian(testing)
+    np.savez_compressed(os.path.join(HERE, "golden_T.npz"), inputs=inputs, targets=targets, theta=theta,
+                        invQ=gp.invQ, invQt=gp.invQt, testing=testing, mu=mu, var=var, deriv=deriv, hess=hess)
+    print("T   mu[:2]", mu[:2], "var[:2]", var[:2])
+
+    # ---- P: the reference's trained PROSAIL MultivariateEmulator (data/prosail_30_0_30_0.npz) -------
+    mv = RefMV(dump=os.path.join(REF, "data", "prosail_30_0_30_0.npz"))
+    y = mv.y_train
+    lo, hi = y.min(axis=0), y.max(axis=0)
+    rs = np.random.RandomState(11)
+    testing = lo + (hi - lo) * rs.random_sample((48, y.shape[1]))
+    P = mv.n_pcs
+    pc_mu = np.empty((48, P)); pc_var = np.empty((48, P)); pc_deriv = np.empty((48, P, y.shape[1]))
+    for i, g in enumerate(mv.emulators):
+        pc_mu[:, i], pc_var[:, i], pc_deriv[:, i, :] = g.predict(testing)
+    hess0 = mv.emulators[0].hessian(testing[:8])
+    pts = np.vstack([y[0], testing[0], testing[1]])
+    wsub = np.arange(0, mv.basis_functions.shape[1], 7)
+    fwd = np.empty((3, mv.basis_functions.shape[1])); dsub = np.empty((3, y.shape[1], wsub.size))
+    for k in range(3):
+        f, d = mv.predict(pts[k])
+        fwd[k] = f
+        dsub[k] = np.asarray(d)[:, wsub]
+    np.savez_compressed(
+        os.path.join(HERE, "golden_P.npz"), y=y, hyperparams=mv.hyperparams, basis_functions=mv.basis_functions,
+        n_pcs=P, train_data=mv.compress(mv.X_train), invQt=np.stack([g.invQt for g in mv.emulators]),
+        testing=testing, pc_mu=pc_mu, pc_var=pc_var, pc_deriv=pc_deriv, hess0=hess0, points=pts, fwd=fwd,
+        wsub=wsub, deriv_sub=dsub)
+    print("P   n_pcs", P, "fwd[0,:3]", fwd[0, :3])
+    for fn in sorted(os.listdir(HERE)):
+        if fn.endswith(".npz"):
+            print("%-18s %8d bytes" % (fn, os.path.getsize(os.path.join(HERE, fn))))
+
+
+if __name__ == "__main__":
+    main()
