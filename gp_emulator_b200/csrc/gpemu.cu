@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,10 +50,10 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 struct FullPlan {
     bool valid = false;
-    int cfg = 0, TN = 0, WC = 0, GH = 1;
+    int cfg = 0, TN = 0, WC = 0, GH = 1, alias_x = 0, ctas_per_sm = 1;
     int Mp = 0, nt_act = 0, kblk = 0, kbps = 0, nit = 0, nstage = 0, JC = 0, nchunks = 0;
     uint32_t off_bar = 0, off_sqw = 0, off_ks = 0, off_bst = 0, off_xc = 0, off_ts = 0, off_pa = 0, off_vred = 0;
-    uint32_t stage_bytes = 0, smem = 0;
+    uint32_t stage_bytes = 0, smem = 0, ts_bytes = 0;
 };
 
 struct MeanPlan {
@@ -135,11 +136,22 @@ cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, int grid, size_t
 }
 
 // Decide tile shape, pipeline depth and the shared-memory carve-up of the fused kernel for (M, D).
+//   cfg 3: Mp <= 256 -> TN = 32, 4 warps, TWO CTAs per SM: DFMA (phase A) and DMMA (phase B) share one FP64 pipe,
+//          so two co-resident CTAs whose phases drift apart keep it busy (ncu: 77% -> see profiles/).  To fit
+//          2 x ~100 KB the phase-A chunk buffer overlays the B-operand ring (alias_x).
+//   cfg 0: same Mp range, TN = 64, 8 warps, 1 CTA/SM (kept selectable with GPE_FULL_CFG=0 for comparison)
+//   cfg 1 / 2: Mp <= 512 / 1024, TN = 32 / 16, 8 warps, 1 CTA/SM
 FullPlan plan_full(int M, int D, int DP) {
     FullPlan f;
     const int m32 = (M + 31) / 32 * 32, m64 = (M + 63) / 64 * 64;
+    int force = -1;
+    if (const char* e = getenv("GPE_FULL_CFG")) force = atoi(e);
+    uint32_t smem_cap = kSmemMax;
     if (m32 <= 256) {
-        f.cfg = 0; f.TN = 64; f.WC = 4; f.GH = 1; f.Mp = m32; f.nt_act = m32 / 32;
+        f.Mp = m32; f.nt_act = m32 / 32;
+        if (force == 3) { f.cfg = 3; f.TN = 32; f.WC = 4; f.GH = 1; f.alias_x = 1; smem_cap = (233472 - 2 * 1024) / 2; }
+        else if (force == 4) { f.cfg = 4; f.TN = 64; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64; }
+        else { f.cfg = 0; f.TN = 64; f.WC = 4; f.GH = 1; }
     } else if (m64 <= 512) {
         f.cfg = 1; f.TN = 32; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64;
     } else if (m64 <= 1024) {
@@ -147,8 +159,9 @@ FullPlan plan_full(int M, int D, int DP) {
     } else {
         return f;  // invalid: variance contraction unsupported for this M
     }
+    f.ctas_per_sm = (f.cfg == 3) ? 2 : 1;
     f.kblk = (M + 3) / 4;
-    f.kbps = std::max(1, 16384 / (f.Mp * 32));
+    f.kbps = std::max(1, ((f.cfg == 3 || f.cfg == 4) ? 8192 : 16384) / (f.Mp * 32));
     f.nit = (f.kblk + f.kbps - 1) / f.kbps;
     f.stage_bytes = (uint32_t)f.kbps * f.Mp * 32u;
 
@@ -156,17 +169,30 @@ FullPlan plan_full(int M, int D, int DP) {
     f.off_bar = off; off += 192;
     f.off_sqw = off; off += 256;
     f.off_ks = off; off += (uint32_t)f.TN * (f.Mp + 4) * 8u;
-    f.off_ts = off; off += align_up((uint32_t)f.TN * (D + 1) * 8u, 16);
+    f.ts_bytes = align_up((uint32_t)f.TN * (D + 1) * 8u, 16);  // x2: current rows / output staging + prefetch
+    f.off_ts = off; off += 2 * f.ts_bytes;
     f.off_pa = off; off += (f.GH > 1) ? align_up((uint32_t)f.GH * f.TN * (D + 1) * 8u, 16) : 0;
     f.off_vred = off; off += (uint32_t)f.WC * f.TN * 8u;
     off = align_up(off, 128);
     const uint32_t fixed = off;
     const int m4 = (M + 3) / 4 * 4;
     const uint32_t row = (uint32_t)(DP + 1) * 8u;
-    for (int ns : {4, 2}) {
+    if (f.alias_x) {
+        // ring and chunk buffer share [fixed, fixed + max(ring, chunk))
+        if (fixed + 2 * f.stage_bytes > smem_cap) return f;
+        f.nstage = (fixed + 4 * f.stage_bytes <= smem_cap) ? 4 : 2;
+        const int jc_max = (int)((smem_cap - fixed) / row) / 4 * 4;
+        if (jc_max < 32) return f;
+        f.JC = std::min(jc_max, m4); f.nchunks = (M + f.JC - 1) / f.JC;
+        f.off_bst = fixed; f.off_xc = fixed;
+        f.smem = fixed + std::max((uint32_t)f.nstage * f.stage_bytes, (uint32_t)f.JC * row);
+        f.valid = f.smem <= smem_cap;
+        return f;
+    }
+    for (int ns : {4, 3, 2}) {
         const uint32_t need = fixed + (uint32_t)ns * f.stage_bytes;
-        if (need + 64 * row > kSmemMax) continue;
-        const int jc_max = (int)((kSmemMax - need) / row) / 4 * 4;
+        if (need + 64 * row > smem_cap) continue;
+        const int jc_max = (int)((smem_cap - need) / row) / 4 * 4;
         if (jc_max >= m4) {  // whole training set resident for the lifetime of the CTA
             f.nstage = ns; f.JC = m4; f.nchunks = 1;
             break;
@@ -179,7 +205,7 @@ FullPlan plan_full(int M, int D, int DP) {
     f.off_bst = fixed;
     f.off_xc = fixed + (uint32_t)f.nstage * f.stage_bytes;
     f.smem = f.off_xc + (uint32_t)f.JC * row;
-    f.valid = f.smem <= kSmemMax;
+    f.valid = f.smem <= smem_cap;
     return f;
 }
 
@@ -242,8 +268,9 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
                    cudaStream_t st) {
     if (N == 0) return GPE_OK;
     bool mean_done = false;
-    if (var != nullptr) {
-        if (!m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
+    static const bool force_full = getenv("GPE_FORCE_FULL") != nullptr;  // dev aid: time phase A alone
+    if (var != nullptr || (force_full && m->full.valid)) {
+        if (var != nullptr && !m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
         if (!m->full.valid)
             return fail(GPE_ERR_UNSUPPORTED, "variance contraction supports M <= %d (got M = %d)", GPE_MAX_TRAIN, m->M);
         const FullPlan& f = m->full;
@@ -253,13 +280,13 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
         p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
         p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk; p.kbps = f.kbps;
-        p.nit = f.nit; p.nstage = f.nstage; p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b;
+        p.nit = f.nit; p.nstage = f.nstage; p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b; p.alias_x = f.alias_x;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
         p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;
-        p.stage_bytes = f.stage_bytes;
+        p.stage_bytes = f.stage_bytes; p.ts_bytes = f.ts_bytes;
         memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
         const int64_t ntiles = (N + f.TN - 1) / f.TN;
-        const int grid = (int)std::min<int64_t>(ntiles, m->sms);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * f.ctas_per_sm);
         CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem, st));
         mean_done = true;
     }

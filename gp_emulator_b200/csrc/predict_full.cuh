@@ -3,18 +3,18 @@
 // For a tile of TN test points a persistent CTA
 //   phase A  forms K*[n][j] = exp(-1/2 sum_d (sqrt(w_d) x_jd - sqrt(w_d) t_nd)^2) in shared memory
 //            (never written to HBM) and, in the same sweep, the mean  sum_j K* (b alpha_j)  and the gradient
-//            sums  sum_j K* (b alpha_j) (xs_jd - ts_nd)  with warp-shuffle reductions
+//            sums  sum_j K* (b alpha_j) (xs_jd - ts_nd), combined across lanes by a shuffle reduce-scatter
 //            -- reference GaussianProcess.py:232-237 and the D-loop :244-247;
 //   phase B  contracts  G = K* (TN x M) . invQ^T (M x M)  on the FP64 tensor path (DMMA.8x8x4) with the whole
 //            TN x Mp accumulator tile resident in registers, invQ streamed L2 -> smem by TMA bulk copies through
 //            an mbarrier ring, then var_n = b - b^2 sum_j G_nj K*_nj  -- reference GaussianProcess.py:240.
+// The next tile's test rows are prefetched by a TMA bulk copy while the current tile computes.
 //
 // Layouts chosen for the hardware (built once at model upload, see gpemu.cu):
 //   xchunks : per chunk of JC training points  [JC][DP] sqrt(w)-scaled inputs | [JC] b*alpha  (one bulk copy)
 //   s_tiled : [ceil(M/4)][Mp][4]  s_tiled[kb][j][c] = invQ[j][4 kb + c], zero padded: a k-block of the B operand
 //             is one contiguous 32*Mp-byte run whose smem image is bank-conflict-free for DMMA B fragments.
-//   K* smem : [TN][Mp + 4] doubles; pitch = 4 (mod 16) doubles makes both the phase-A stores (8 rows x 4 columns
-//             per warp) and the DMMA A-fragment loads (same shape) conflict-free.
+//   K* smem : [TN][Mp + 4] doubles; pitch = 4 (mod 16) doubles keeps the DMMA A-fragment loads conflict-free.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,7 +23,6 @@
 
 namespace gpe {
 
-constexpr int kFullThreads = 256;
 constexpr int kMaxD = 32;
 
 struct FullParams {
@@ -41,34 +40,79 @@ struct FullParams {
     int kblk;       // ceil(M / 4) k-blocks
     int kbps;       // k-blocks per pipeline stage
     int nit;        // pipeline iterations per tile = ceil(kblk / kbps)
-    int nstage;     // ring depth (power of two)
+    int nstage;     // ring depth
     int JC;         // training points per phase-A chunk (multiple of 4)
+    int alias_x;    // 1: the chunk buffer overlays the B-operand ring (2-CTA/SM configuration)
     int nchunks;
     double b;       // signal variance exp(theta[D])
     // shared-memory carve-up (byte offsets)
     uint32_t off_bar, off_sqw, off_ks, off_bst, off_xc, off_ts, off_pa, off_vred;
+    uint32_t ts_bytes;     // size of ONE of the two test-row / output staging buffers at off_ts
     uint32_t stage_bytes;
     double sqrt_w[kMaxD];
 };
 
-template <int MT, int NT, int WR, int WC, int DP>
-__global__ void __launch_bounds__(kFullThreads, 1) k_predict_full(const FullParams p) {
+// Sum `NV` per-point values held by the 8 training-point lanes (lane bits 0..2) of two points a / b with a
+// shuffle reduce-scatter: 8-lane butterflies would need 3 * 2 * NV shuffles, this needs NV + NV/2 + NV/4.
+// On return lane (b2 b1 b0) holds the complete sums of point (b2 ? b : a) for value indices
+//   base + i,  i < H3,  base = (b1 ? H2 : 0) + (b0 ? H3 : 0)   (indices >= the half / NV are padding).
+template <int NV>
+struct RS {
+    static constexpr int H2 = (NV + 1) / 2;
+    static constexpr int H3 = (H2 + 1) / 2;
+    double r3[H3];
+    __device__ __forceinline__ void run(const double (&va)[NV], const double (&vb)[NV], int lane) {
+        const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+        double r1[2 * H2];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double send = b2 ? va[i] : vb[i];
+            const double keep = b2 ? vb[i] : va[i];
+            r1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int i = NV; i < 2 * H2; ++i) r1[i] = 0.0;
+        double r2[2 * H3];
+#pragma unroll
+        for (int i = 0; i < H2; ++i) {
+            const double send = b1 ? r1[i] : r1[H2 + i];
+            const double keep = b1 ? r1[H2 + i] : r1[i];
+            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int i = H2; i < 2 * H3; ++i) r2[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < H3; ++i) {
+            const double send = b0 ? r2[i] : r2[H3 + i];
+            const double keep = b0 ? r2[H3 + i] : r2[i];
+            r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+};
+
+template <int MT, int NT, int WR, int WC, int DP, int MINB>
+__global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullParams p) {
+    constexpr int NW = WR * WC;           // warps per CTA (power of two)
+    constexpr int NTHR = NW * 32;
     constexpr int TN = WR * MT * 8;       // test points per tile
     constexpr int NHI = TN / 8;           // warps along n in phase A
-    constexpr int GH = 8 / NHI;           // warps along j in phase A
-    static_assert(WR * WC == 8, "8 warps");
-    static_assert(NHI * GH == 8 && NHI >= 1, "TN in {8,16,32,64}");
+    constexpr int GH = NW / NHI;          // warps along j in phase A
+    constexpr int TPR = NTHR / TN;        // threads per test row when writing outputs
+    constexpr int NV = DP + 1;            // values reduced per point: mean + DP gradient sums
+    static_assert((NW & (NW - 1)) == 0, "warp count must be a power of two");
+    static_assert(NHI * GH == NW && NHI >= 1 && GH >= 1, "TN must be 8 * (a divisor of the warp count)");
+    static_assert(TPR >= 1 && TPR * TN == NTHR, "TN must divide the thread count");
     static_assert(DP % 2 == 0, "DP even (16-byte rows)");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
     uint64_t* bar_empty = bar_full + 8;
     uint64_t* bar_x = bar_full + 16;
+    uint64_t* bar_t = bar_full + 17;      // [2] test-row prefetch
     double* sqw_s = reinterpret_cast<double*>(smem + p.off_sqw);
     double* Ks = reinterpret_cast<double*>(smem + p.off_ks);
     unsigned char* Bst = smem + p.off_bst;
     double* Xc = reinterpret_cast<double*>(smem + p.off_xc);
-    double* ts_s = reinterpret_cast<double*>(smem + p.off_ts);   // [TN][D] raw test rows, later outs [TN][D+1]
     double* pa_s = reinterpret_cast<double*>(smem + p.off_pa);   // [GH][TN][D+1] (GH > 1 only)
     double* vred = reinterpret_cast<double*>(smem + p.off_vred); // [WC][TN]
 
@@ -76,195 +120,226 @@ __global__ void __launch_bounds__(kFullThreads, 1) k_predict_full(const FullPara
     const int D = p.D, M = p.M, Mp = p.Mp;
     const int pitch = Mp + 4;
     const int nstage = p.nstage;
+    const int DV = D + 1;
 
     const int64_t ntiles = (p.N + TN - 1) / TN;
-    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const bool want_var = (p.var != nullptr);
-    const int64_t total_it = want_var ? my_tiles * p.nit : 0;
+    const bool alias_x = p.alias_x != 0;
+    // bulk copies need 16-byte aligned sources; row blocks of full tiles are multiples of 64 bytes
+    const bool ts_tma_ok = (reinterpret_cast<uintptr_t>(p.testing) & 15) == 0;
+    const uint32_t ts_tile_bytes = (uint32_t)TN * D * 8u;
 
     // ---- one-time setup -------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 8);
+            mbar_init(&bar_empty[s], NW);
         }
         mbar_init(bar_x, 1);
+        mbar_init(&bar_t[0], 1);
+        mbar_init(&bar_t[1], 1);
         fence_mbar_init();
     }
     if (tid < kMaxD) sqw_s[tid] = p.sqrt_w[tid];
     // zero the K* columns [M, Mp + 4): phase A never writes them, phase B multiplies them by zero rows of invQ
-    for (int r = warp; r < TN; r += 8)
+    for (int r = warp; r < TN; r += NW)
         for (int c = M + lane; c < pitch; c += 32) Ks[r * pitch + c] = 0.0;
     __syncthreads();
 
-    // producer state (thread 0 only): next pipeline iteration to issue
-    int64_t issue_gi = 0;
-    int issue_it = 0, issue_s = 0;
-    auto issue_stage = [&]() {
-        const int kb0 = issue_it * p.kbps;
+    // B-operand ring.  Global iteration g uses stage g % nstage; (cs, cpar) track the stage / parity of the next
+    // iteration to consume.  Loads are issued by lane 0 of a rotating warp so no single warp carries the cost:
+    // a burst of min(nstage, nit) at the start of a tile (every earlier use was released before the end-of-tile
+    // barrier, so no wait is needed), then during iteration `it` the stage released in iteration it - 1 is
+    // refilled with k-blocks of iteration it - 1 + nstage, i.e. the copy runs nstage - 1 iterations ahead.
+    int cs = 0;
+    uint32_t cpar = 0;
+    auto issue = [&](int stage, int it_local) {
+        const int kb0 = it_local * p.kbps;
         const int nkb = min(p.kbps, p.kblk - kb0);
         const uint32_t bytes = (uint32_t)nkb * (uint32_t)Mp * 32u;
-        mbar_arrive_expect_tx(&bar_full[issue_s], bytes);
-        tma_bulk_g2s(Bst + (size_t)issue_s * p.stage_bytes, p.s_tiled + (size_t)kb0 * Mp * 4, bytes,
-                     &bar_full[issue_s]);
-        ++issue_gi;
-        if (++issue_it == p.nit) issue_it = 0;
-        if (++issue_s == nstage) issue_s = 0;
+        mbar_arrive_expect_tx(&bar_full[stage], bytes);
+        tma_bulk_g2s(Bst + (size_t)stage * p.stage_bytes, p.s_tiled + (size_t)kb0 * Mp * 4, bytes, &bar_full[stage]);
     };
-    if (tid == 0) {
-        for (int s = 0; s < nstage && issue_gi < total_it; ++s) issue_stage();
-    }
-
-    // consumer ring state (all threads)
-    int cs = 0;             // stage consumed next
-    uint32_t cpar = 0;      // its parity
-    int64_t cgi = 0;        // global pipeline iteration
-    int es = 0;             // producer: stage whose release is awaited next (lags the consumer by one)
-    uint32_t epar = 0;
+    auto issue_burst = [&]() {
+        int s = cs;
+        const int burst = min(nstage, p.nit);
+        for (int i = 0; i < burst; ++i) {
+            issue(s, i);
+            if (++s == nstage) s = 0;
+        }
+    };
     uint32_t xpar = 0;
     bool x_resident = false;
 
-    // phase-A thread coordinates
-    const int g_low = lane & 3, n_low = lane >> 2;
+    // test-row prefetch state
+    uint32_t tpar = 0;  // bit `buf` = parity of the next completion of bar_t[buf]
+    auto prefetch_rows = [&](int64_t tile, int buf) -> bool {  // thread 0 only; false if this tile must be loaded in-line
+        const int64_t n0 = tile * TN;
+        if (!ts_tma_ok || n0 + TN > p.N) return false;
+        fence_proxy_async();  // the buffer was last written through the generic proxy (output staging)
+        mbar_arrive_expect_tx(&bar_t[buf], ts_tile_bytes);
+        tma_bulk_g2s(smem + p.off_ts + (size_t)buf * p.ts_bytes, p.testing + n0 * D, ts_tile_bytes, &bar_t[buf]);
+        return true;
+    };
+    // whether tile `t` can be / was prefetched is a pure function of t, so every thread can evaluate it
+    auto rows_prefetched = [&](int64_t tile) { return ts_tma_ok && (tile * TN + TN <= p.N); };
+
+    // phase-A thread coordinates.  A warp owns 8 consecutive test rows; lane = 8 * n_low + g_low, g_low = training-
+    // point lane (0..7), n_low = 0..3; each thread carries TWO test rows (n_a and n_a + 4) so that every training
+    // row it pulls from shared memory feeds two (test, train) pairs.
+    const int g_low = lane & 7, n_low = lane >> 3;
     const int n_hi = warp % NHI, g_hi = warp / NHI;
-    const int n_loc = n_hi * 8 + n_low;
+    const int n_a = n_hi * 8 + n_low, n_b = n_a + 4;
     // phase-B warp coordinates
     const int wrow = warp / WC, wcol = warp % WC;
     const int nt_act = p.nt_act;
-    const int DV = D + 1;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int buf = 0;
+    if (tid == 0 && blockIdx.x < ntiles) prefetch_rows(blockIdx.x, 0);
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int64_t n0 = tile * TN;
         const int npts = (int)min((int64_t)TN, p.N - n0);
+        double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
+        // B-operand prefetch for this tile's contraction lands while phase A runs (unless the buffers are shared)
+        if (want_var && !alias_x && tid == 0) issue_burst();
 
-        // ---- stage the tile's test rows (coalesced), pull mine into registers pre-scaled --------------
-        for (int e = tid; e < TN * D; e += kFullThreads) {
-            const int r = e / D;
-            const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
-            ts_s[e] = __ldg(p.testing + src);
+        // ---- this tile's test rows: prefetched by TMA during the previous tile, or loaded in-line ------------
+        if (rows_prefetched(tile)) {
+            mbar_wait(&bar_t[buf], (tpar >> buf) & 1u);
+            tpar ^= 1u << buf;
+        } else {
+            for (int e = tid; e < TN * D; e += NTHR) {
+                const int r = e / D;
+                const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
+                ts_s[e] = __ldg(p.testing + src);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        double ts[DP];
+        double tsa[DP], tsb[DP];
 #pragma unroll
-        for (int d = 0; d < DP; ++d) ts[d] = (d < D) ? ts_s[n_loc * D + d] * sqw_s[d] : 0.0;
-        __syncthreads();  // ts_s is reused as the output staging area below
+        for (int d = 0; d < DP; ++d) {
+            tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
+            tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
+        }
+        // phase-A chunk 0 (unless resident) is requested before the barrier so its latency overlaps the barrier
+        if (!x_resident && tid == 0) {
+            const uint32_t bytes = (uint32_t)p.JC * (DP + 1) * 8u;
+            mbar_arrive_expect_tx(bar_x, bytes);
+            tma_bulk_g2s(Xc, p.xchunks, bytes, bar_x);
+        }
+        __syncthreads();  // ts_s is reused as the output staging area below; the other buffer is free for prefetch
+        {
+            const int64_t next = tile + gridDim.x;
+            if (tid == 0 && next < ntiles) prefetch_rows(next, buf ^ 1);
+        }
 
         // ---- phase A: K* tile + mean + gradient sums ----------------------------------------------------
-        double mu = 0.0;
-        double g[DP];
+        double va[NV], vb[NV];  // [0] mean, [1 + d] gradient sums of the two rows
 #pragma unroll
-        for (int d = 0; d < DP; ++d) g[d] = 0.0;
+        for (int i = 0; i < NV; ++i) va[i] = vb[i] = 0.0;
 
         for (int c = 0; c < p.nchunks; ++c) {
             if (!x_resident) {
-                if (tid == 0) {
+                if (c > 0 && tid == 0) {
                     const uint32_t bytes = (uint32_t)p.JC * (DP + 1) * 8u;
                     mbar_arrive_expect_tx(bar_x, bytes);
                     tma_bulk_g2s(Xc, p.xchunks + (size_t)c * p.JC * (DP + 1), bytes, bar_x);
                 }
                 mbar_wait(bar_x, xpar);
                 xpar ^= 1;
-                if (p.nchunks == 1) x_resident = true;
+                if (p.nchunks == 1 && !alias_x) x_resident = true;
             }
             const int jn = min(p.JC, M - c * p.JC);
             const double* al = Xc + p.JC * DP;
-            double* krow = Ks + n_loc * pitch + c * p.JC;
-            int jl = 4 * g_hi + g_low;
-            // two training points per trip: two independent exp chains in flight
-            for (; jl + 4 * GH < jn; jl += 8 * GH) {
-                const int jl2 = jl + 4 * GH;
-                const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
-                const double2* x2 = reinterpret_cast<const double2*>(Xc + jl2 * DP);
-                double u1[DP], u2[DP];
-                double r1 = 0.0, r2 = 0.0;
+            double* krow_a = Ks + n_a * pitch + c * p.JC;
+            double* krow_b = krow_a + 4 * pitch;
+            int jl = 8 * g_hi + g_low;
+            if (jl < jn) {
+                // software pipeline: the next training row and alpha are in flight while this one is consumed
+                double2 xn[DP / 2];
+                double aln;
+                {
+                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * DP);
 #pragma unroll
-                for (int d = 0; d < DP; d += 2) {
-                    const double2 a1 = x1[d >> 1], a2 = x2[d >> 1];
-                    u1[d] = a1.x - ts[d];
-                    u1[d + 1] = a1.y - ts[d + 1];
-                    u2[d] = a2.x - ts[d];
-                    u2[d + 1] = a2.y - ts[d + 1];
-                    r1 = fma(u1[d], u1[d], r1);
-                    r2 = fma(u2[d], u2[d], r2);
-                    r1 = fma(u1[d + 1], u1[d + 1], r1);
-                    r2 = fma(u2[d + 1], u2[d + 1], r2);
+                    for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
+                    aln = al[jl];
                 }
-                const double k1 = exp_neg(-0.5 * r1);
-                const double k2 = exp_neg(-0.5 * r2);
-                krow[jl] = k1;
-                krow[jl2] = k2;
-                const double c1 = k1 * al[jl], c2 = k2 * al[jl2];
-                mu += c1;
-                mu += c2;
+                for (; jl < jn; jl += 8 * GH) {
+                    double2 x[DP / 2];
 #pragma unroll
-                for (int d = 0; d < DP; ++d) {
-                    g[d] = fma(c1, u1[d], g[d]);
-                    g[d] = fma(c2, u2[d], g[d]);
+                    for (int q = 0; q < DP / 2; ++q) x[q] = xn[q];
+                    const double alj = aln;
+                    {
+                        const int jnx = min(jl + 8 * GH, jn - 1);
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * DP);
+#pragma unroll
+                        for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
+                        aln = al[jnx];
+                    }
+                    double ua[DP], ub[DP];
+                    double ra = 0.0, rb = 0.0;
+#pragma unroll
+                    for (int q = 0; q < DP / 2; ++q) {
+                        const int d = 2 * q;
+                        ua[d] = x[q].x - tsa[d];
+                        ub[d] = x[q].x - tsb[d];
+                        ua[d + 1] = x[q].y - tsa[d + 1];
+                        ub[d + 1] = x[q].y - tsb[d + 1];
+                        ra = fma(ua[d], ua[d], ra);
+                        rb = fma(ub[d], ub[d], rb);
+                        ra = fma(ua[d + 1], ua[d + 1], ra);
+                        rb = fma(ub[d + 1], ub[d + 1], rb);
+                    }
+                    const double ka = exp_neg(-0.5 * ra);
+                    const double kb = exp_neg(-0.5 * rb);
+                    krow_a[jl] = ka;
+                    krow_b[jl] = kb;
+                    const double ca = ka * alj, cb = kb * alj;
+                    va[0] += ca;
+                    vb[0] += cb;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        va[1 + d] = fma(ca, ua[d], va[1 + d]);
+                        vb[1 + d] = fma(cb, ub[d], vb[1 + d]);
+                    }
                 }
             }
-            for (; jl < jn; jl += 4 * GH) {
-                const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
-                double u1[DP];
-                double r1 = 0.0;
-#pragma unroll
-                for (int d = 0; d < DP; d += 2) {
-                    const double2 a1 = x1[d >> 1];
-                    u1[d] = a1.x - ts[d];
-                    u1[d + 1] = a1.y - ts[d + 1];
-                    r1 = fma(u1[d], u1[d], r1);
-                    r1 = fma(u1[d + 1], u1[d + 1], r1);
-                }
-                const double k1 = exp_neg(-0.5 * r1);
-                krow[jl] = k1;
-                const double c1 = k1 * al[jl];
-                mu += c1;
-#pragma unroll
-                for (int d = 0; d < DP; ++d) g[d] = fma(c1, u1[d], g[d]);
-            }
-            if (!x_resident) __syncthreads();  // all reads of Xc done before the next chunk lands
+            if (!x_resident) __syncthreads();  // all reads of Xc done before the next chunk (or the ring) lands
         }
 
-        // reduce the 4 j-lanes of each point, then (GH > 1) the j-warps through smem
-        mu += __shfl_xor_sync(0xffffffffu, mu, 1);
-        mu += __shfl_xor_sync(0xffffffffu, mu, 2);
-#pragma unroll
-        for (int d = 0; d < DP; ++d) {
-            if (d < D) {
-                g[d] += __shfl_xor_sync(0xffffffffu, g[d], 1);
-                g[d] += __shfl_xor_sync(0xffffffffu, g[d], 2);
-            }
-        }
+        // combine the 8 j-lanes of each point (reduce-scatter), then (GH > 1) the j-warps through smem
         double* outs = ts_s;  // [TN][D+1]: mean, then unscaled gradient sums
-        if (GH == 1) {
-            if (g_low == 0) {
-                outs[n_loc * DV] = mu;
+        {
+            RS<NV> rs;
+            rs.run(va, vb, lane);
+            double* dst = ((GH == 1) ? outs : pa_s + g_hi * TN * DV) + ((lane & 4) ? n_b : n_a) * DV;
+            const int half_base = (lane & 2) ? RS<NV>::H2 : 0;
+            const int base3 = (lane & 1) ? RS<NV>::H3 : 0;
 #pragma unroll
-                for (int d = 0; d < DP; ++d)
-                    if (d < D) outs[n_loc * DV + 1 + d] = g[d];
+            for (int i = 0; i < RS<NV>::H3; ++i) {
+                const int i2 = base3 + i;            // index inside this lane's half
+                const int idx = half_base + i2;      // value index: 0 mean, 1 + d gradient
+                if (i2 < RS<NV>::H2 && idx < DV) dst[idx] = rs.r3[i];
             }
             __syncthreads();
-        } else {
-            if (g_low == 0) {
-                double* dst = pa_s + (g_hi * TN + n_loc) * DV;
-                dst[0] = mu;
-#pragma unroll
-                for (int d = 0; d < DP; ++d)
-                    if (d < D) dst[1 + d] = g[d];
+            if (GH > 1) {
+                for (int e = tid; e < TN * DV; e += NTHR) {
+                    double sum = 0.0;
+                    for (int gh = 0; gh < GH; ++gh) sum += pa_s[gh * TN * DV + e];
+                    outs[e] = sum;
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            for (int e = tid; e < TN * DV; e += kFullThreads) {
-                double s = 0.0;
-                for (int gh = 0; gh < GH; ++gh) s += pa_s[gh * TN * DV + e];
-                outs[e] = s;
-            }
-            __syncthreads();
         }
         // K* tile and outs are now visible to every warp
-        if (p.mu != nullptr && tid < npts) p.mu[(n0 + tid) * p.ld_mu] = outs[tid * DV];
-        if (p.deriv != nullptr) {
-            for (int e = tid; e < npts * D; e += kFullThreads) {
-                const int r = e / D, d = e - r * D;
-                p.deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
+        {
+            const int r = tid / TPR, q = tid % TPR;
+            if (r < npts) {
+                if (p.mu != nullptr && q == 0) p.mu[(n0 + r) * p.ld_mu] = outs[r * DV];
+                if (p.deriv != nullptr) {
+                    for (int d = q; d < D; d += TPR) p.deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
+                }
             }
         }
 
@@ -279,13 +354,13 @@ __global__ void __launch_bounds__(kFullThreads, 1) k_predict_full(const FullPara
             const double* a_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + (lane & 3);
             const int b_off = (wcol * nt_act * 8 + (lane >> 2)) * 4 + (lane & 3);
 
+            if (alias_x && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
             for (int it = 0; it < p.nit; ++it) {
-                // producer: refill the stage released one iteration ago (its consumers are almost surely done),
-                // so the copy for iteration cgi - 1 + nstage overlaps the DMMAs of iterations cgi .. cgi + nstage - 2
-                if (tid == 0 && cgi >= 1 && issue_gi < total_it) {
-                    mbar_wait(&bar_empty[es], epar);
-                    if (++es == nstage) { es = 0; epar ^= 1; }
-                    issue_stage();
+                if (it >= 1 && lane == 0 && warp == (it & (NW - 1)) && it - 1 + nstage < p.nit) {
+                    const int ps = (cs == 0) ? nstage - 1 : cs - 1;          // stage of iteration it - 1
+                    const uint32_t ppar = (cs == 0) ? (cpar ^ 1) : cpar;     // parity of that use
+                    mbar_wait(&bar_empty[ps], ppar);
+                    issue(ps, it - 1 + nstage);
                 }
                 mbar_wait(&bar_full[cs], cpar);
                 const double* bs = reinterpret_cast<const double*>(Bst + (size_t)cs * p.stage_bytes) + b_off;
@@ -307,7 +382,6 @@ __global__ void __launch_bounds__(kFullThreads, 1) k_predict_full(const FullPara
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[cs]);
-                ++cgi;
                 if (++cs == nstage) { cs = 0; cpar ^= 1; }
             }
 
@@ -341,7 +415,7 @@ __global__ void __launch_bounds__(kFullThreads, 1) k_predict_full(const FullPara
                 p.var[(n0 + tid) * p.ld_var] = p.b - p.b * p.b * v;
             }
         }
-        __syncthreads();  // K*, outs, vred are free for the next tile
+        __syncthreads();  // K*, outs, vred (and the ring, if it doubles as chunk buffer) are free for the next tile
     }
 }
 

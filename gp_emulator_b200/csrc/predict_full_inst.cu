@@ -13,21 +13,23 @@
 
 namespace gpe {
 
-template <int MT, int NT, int WR, int WC>
+template <int MT, int NT, int WR, int WC, int MINB>
 static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = k_predict_full<MT, NT, WR, WC, GPE_DP>;
+    auto kern = k_predict_full<MT, NT, WR, WC, GPE_DP, MINB>;
     // per function AND per device: set on every launch (microseconds) so multi-device processes stay correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kFullThreads, smem, st>>>(p);
+    kern<<<grid, WR * WC * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_cfg<4, 8, 2, 4>(p, grid, smem, st);   // TN = 64, Mp <= 256
-        case 1: return launch_cfg<4, 8, 1, 8>(p, grid, smem, st);   // TN = 32, Mp <= 512
-        case 2: return launch_cfg<2, 16, 1, 8>(p, grid, smem, st);  // TN = 16, Mp <= 1024
+        case 0: return launch_cfg<4, 8, 2, 4, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 8 warps, 1 CTA/SM
+        case 1: return launch_cfg<4, 8, 1, 8, 1>(p, grid, smem, st);   // TN = 32, Mp <= 512, 8 warps, 1 CTA/SM
+        case 2: return launch_cfg<2, 16, 1, 8, 1>(p, grid, smem, st);  // TN = 16, Mp <= 1024, 8 warps, 1 CTA/SM
+        case 3: return launch_cfg<4, 8, 1, 4, 2>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
+        case 4: return launch_cfg<4, 4, 2, 8, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
         default: return cudaErrorInvalidValue;
     }
 }
