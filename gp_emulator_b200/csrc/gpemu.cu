@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/gpemu.h"
@@ -335,6 +336,27 @@ int ensure(double** ptr, size_t* cap, size_t need, bool host) {
     return GPE_OK;
 }
 
+// Staging copies for pageable callers: one core moves ~10 GB/s, the PCIe link 55 GB/s each way, so large copies
+// are split over a few threads (spawned per chunk: tens of microseconds against milliseconds of copy).
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), bytes / (2u << 20));
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t part = (bytes / nt + 63) & ~(size_t)63;
+    for (unsigned i = 1; i < nt; ++i) {
+        const size_t off = (size_t)i * part;
+        if (off >= bytes) break;
+        const size_t len = std::min(part, bytes - off);
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    memcpy(dst, src, std::min(part, bytes));
+    for (auto& t : th) t.join();
+}
+
 // Host-resident caller: stream chunks through two slots so the H2D copy of chunk i+1, the kernels of chunk i
 // and the D2H copy of chunk i-1 overlap.  Pinned caller buffers are DMA'd directly; pageable ones are staged.
 int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
@@ -364,10 +386,10 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
         CUDA_TRY(cudaEventSynchronize(s.done));
         const int64_t n0 = s.pend_n0, n = s.pend_n;
         const double* src = s.h_out;
-        if (mu) { memcpy(mu + n0, src, (size_t)n * 8); src += n; }
-        if (var) { memcpy(var + n0, src, (size_t)n * 8); src += n; }
-        if (deriv) { memcpy(deriv + n0 * D, src, (size_t)n * D * 8); src += n * D; }
-        if (hess) { memcpy(hess + n0 * D * D, src, (size_t)n * D * D * 8); }
+        if (mu) { par_memcpy(mu + n0, src, (size_t)n * 8); src += n; }
+        if (var) { par_memcpy(var + n0, src, (size_t)n * 8); src += n; }
+        if (deriv) { par_memcpy(deriv + n0 * D, src, (size_t)n * D * 8); src += n * D; }
+        if (hess) { par_memcpy(hess + n0 * D * D, src, (size_t)n * D * D * 8); }
         s.pending = false;
         return GPE_OK;
     };
@@ -385,7 +407,7 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
         } else {
             int rc = drain(s);  // the slot's previous results must leave the staging buffer first
             if (rc) return rc;
-            memcpy(s.h_in, testing + n0 * D, (size_t)n * D * 8);
+            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * 8);
             CUDA_TRY(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)n * D * 8, cudaMemcpyHostToDevice, s.st));
         }
         int rc = predict_device(m, s.d_in, n, d_mu, d_var, d_der, d_hes, 1, 1, D, (int64_t)D * D, s.st);

@@ -23,9 +23,6 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-_PIN_THRESHOLD = 1 << 16  # results of large host calls land in page-locked memory so the D2H copy is pure DMA
-
-
 def _pinned_empty(shape):
     """numpy array backed by torch's caching pinned-host allocator (the view keeps the block alive)."""
     import torch
@@ -68,14 +65,25 @@ class DeviceModel:
     def close(self):
         self._fin()
 
-    def predict(self, testing, want_var=True, want_deriv=True, want_hess=False, want_mu=True):
-        """Returns a dict with the requested arrays among mu (N,), var (N,), deriv (N, D), hess (N, D, D)."""
+    def predict(self, testing, want_var=True, want_deriv=True, want_hess=False, want_mu=True, out=None,
+                pinned=False):
+        """Returns a dict with the requested arrays among mu (N,), var (N,), deriv (N, D), hess (N, D, D).
+
+        ``out`` may hold preallocated result arrays under the same keys (float64, C-contiguous, right shape;
+        numpy for host calls, CUDA tensors for device calls): they are filled in place and returned.  Host
+        results are ordinary (pageable) numpy arrays by default, staged through the library's pinned
+        buffers; ``pinned=True`` allocates them page-locked instead, which lets the D2H copy DMA straight
+        into them but costs ~0.7 s per GB the first time a size is seen (torch's caching allocator then
+        reuses the blocks) -- worth it only for repeated calls.
+        """
         lib = _lib.load()
         D = self.D
         if want_var and not self.has_var:
             raise GpemuError("variance requested but the model was uploaded without invQ")
         flags = (WANT_MU if want_mu else 0) | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0) | (
             WANT_HESS if want_hess else 0)
+        wanted = [k for k, w in (("mu", want_mu), ("var", want_var), ("deriv", want_deriv), ("hess", want_hess)) if w]
+        out = dict(out) if out else {}
         if _is_torch(testing):
             import torch
             t = testing
@@ -85,29 +93,32 @@ class DeviceModel:
                 raise ValueError(f"testing must be float64 (N, {D})")
             t = t.contiguous()
             N = t.shape[0]
-            mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=t.device)
-            out = {}
-            if want_mu: out["mu"] = mk(N)
-            if want_var: out["var"] = mk(N)
-            if want_deriv: out["deriv"] = mk(N, D)
-            if want_hess: out["hess"] = mk(N, D, D)
+            shapes = {"mu": (N,), "var": (N,), "deriv": (N, D), "hess": (N, D, D)}
+            for k in wanted:
+                if k not in out:
+                    out[k] = torch.empty(shapes[k], dtype=torch.float64, device=t.device)
+                elif (tuple(out[k].shape) != shapes[k] or out[k].dtype != torch.float64 or not out[k].is_cuda
+                      or not out[k].is_contiguous()):
+                    raise ValueError(f"out[{k!r}] must be a contiguous float64 CUDA tensor of shape {shapes[k]}")
             check(lib.gpe_predict(self._h, addr(t), N, addr(out.get("mu")), addr(out.get("var")),
                                   addr(out.get("deriv")), addr(out.get("hess")), flags,
                                   _current_stream_ptr(self.device)))
-            return out
+            return {k: out[k] for k in wanted}
         t = f64c(testing)
         if t.ndim != 2 or t.shape[1] != D:
             raise ValueError(f"testing must be (N, {D})")
         N = t.shape[0]
-        mk = _pinned_empty if N >= _PIN_THRESHOLD else np.empty
-        out = {}
-        if want_mu: out["mu"] = mk((N,))
-        if want_var: out["var"] = mk((N,))
-        if want_deriv: out["deriv"] = mk((N, D))
-        if want_hess: out["hess"] = mk((N, D, D))
+        shapes = {"mu": (N,), "var": (N,), "deriv": (N, D), "hess": (N, D, D)}
+        mk = _pinned_empty if pinned else np.empty
+        for k in wanted:
+            if k not in out:
+                out[k] = mk(shapes[k])
+            elif (not isinstance(out[k], np.ndarray) or out[k].shape != shapes[k] or out[k].dtype != np.float64
+                  or not out[k].flags.c_contiguous):
+                raise ValueError(f"out[{k!r}] must be a C-contiguous float64 numpy array of shape {shapes[k]}")
         check(lib.gpe_predict(self._h, addr(t), N, addr(out.get("mu")), addr(out.get("var")),
                               addr(out.get("deriv")), addr(out.get("hess")), flags | HOST_PTRS, None))
-        return out
+        return {k: out[k] for k in wanted}
 
 
 class DeviceBank:

@@ -128,19 +128,22 @@ class GaussianProcess:
             self._dev_key = key
         return self._dev_model
 
-    def predict(self, testing, do_unc=True, do_deriv=True, is_gpu=True, precision=np.float64, threshold=2e5):
+    def predict(self, testing, do_unc=True, do_deriv=True, is_gpu=True, precision=np.float64, threshold=2e5,
+                out=None, pinned=False):
         """Mean, variance and input gradient at ``testing`` (N, D)  (reference GaussianProcess.py:327-341).
 
         Returns ``(mu, var, deriv)``; ``(mu, deriv)`` if ``do_unc`` is False (as the reference's CPU branch,
         :248-251); ``(mu, var)`` / ``mu`` when ``do_deriv`` is False (the upstream-style signature).
         ``deriv`` is (N, D).  Computation is FP64 on the GPU; ``precision`` only casts the numpy results.
         ``testing`` may also be a float64 torch CUDA tensor, in which case torch tensors are returned.
+        ``out`` (dict with any of "mu", "var", "deriv") supplies preallocated result buffers, ``pinned=True``
+        makes freshly allocated host results page-locked (see ``DeviceModel.predict``).
         """
         if getattr(testing, "ndim", None) != 2 and not hasattr(testing, "dim"):
             raise ValueError("testing must always be a 2-D array (N, D)")
         if testing.shape[1] != self.D:
             raise AssertionError("testing has %d columns, model has D = %d" % (testing.shape[1], self.D))
-        out = self._device_model().predict(testing, want_var=do_unc, want_deriv=do_deriv)
+        out = self._device_model().predict(testing, want_var=do_unc, want_deriv=do_deriv, out=out, pinned=pinned)
         res = [out["mu"]]
         if do_unc:
             res.append(out["var"])

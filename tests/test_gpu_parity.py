@@ -157,6 +157,27 @@ def test_pageable_and_pinned_host_paths_multi_chunk(gpemu):
     assert orc.ref_err(a["deriv"][idx], deriv) < TOL
 
 
+def test_preallocated_and_pinned_outputs(gpemu):
+    import torch
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 7, 70000, seed=6)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    ref = m.predict(testing)
+    out = {"mu": torch.empty(70000, dtype=torch.float64).pin_memory().numpy(), "deriv": np.empty((70000, 7))}
+    got = m.predict(testing, out=out)
+    assert got["mu"] is out["mu"] and got["deriv"] is out["deriv"]
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(got[k], ref[k])
+    got = m.predict(testing, pinned=True)
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(got[k], ref[k])
+    with pytest.raises(ValueError):
+        m.predict(testing, out={"mu": np.empty(5)})
+    t = torch.from_numpy(testing).cuda()
+    dout = {"var": torch.empty(70000, dtype=torch.float64, device="cuda")}
+    got = m.predict(t, out=dout)
+    assert got["var"] is dout["var"] and np.array_equal(got["var"].cpu().numpy(), ref["var"])
+
+
 def test_dropin_class_matches_reference_semantics(gpemu):
     """The reference's benchmark flow (tests/benchmark.py:11-60): overwrite attributes, call predict."""
     inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 2000, seed=0)
