@@ -28,6 +28,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+long long* g_trace = nullptr;  // dev aid: device buffer for per-tile phase timestamps (gpe_debug_trace)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -162,7 +163,7 @@ FullPlan plan_full(int M, int D, int DP) {
     }
     f.ctas_per_sm = (f.cfg == 3) ? 2 : 1;
     f.kblk = (M + 3) / 4;
-    f.kbps = std::max(1, ((f.cfg == 3 || f.cfg == 4) ? 8192 : 16384) / (f.Mp * 32));
+    f.kbps = (f.cfg == 0) ? 2 : 1;  // k-blocks (32 * Mp bytes each) per ring stage == template KB of the cfg
     f.nit = (f.kblk + f.kbps - 1) / f.kbps;
     f.stage_bytes = (uint32_t)f.kbps * f.Mp * 32u;
 
@@ -190,17 +191,20 @@ FullPlan plan_full(int M, int D, int DP) {
         f.valid = f.smem <= smem_cap;
         return f;
     }
-    for (int ns : {4, 3, 2}) {
-        const uint32_t need = fixed + (uint32_t)ns * f.stage_bytes;
-        if (need + 64 * row > smem_cap) continue;
-        const int jc_max = (int)((smem_cap - need) / row) / 4 * 4;
-        if (jc_max >= m4) {  // whole training set resident for the lifetime of the CTA
-            f.nstage = ns; f.JC = m4; f.nchunks = 1;
-            break;
+    // resident training set if it fits beside a ring of >= 3 stages, else chunks of <= 256 points; the ring then
+    // takes every stage that still fits (at most 8: the barrier arrays)
+    {
+        const uint32_t avail = smem_cap - fixed;
+        const uint32_t resident = (uint32_t)m4 * row;
+        if (avail >= resident + 3 * f.stage_bytes) {
+            f.JC = m4; f.nchunks = 1;
+        } else {
+            if (avail < 2 * f.stage_bytes + 64 * row) return f;
+            const int jc_max = (int)((avail - 2 * f.stage_bytes) / row) / 4 * 4;
+            f.JC = std::min(std::min(jc_max, 256), m4); f.nchunks = (M + f.JC - 1) / f.JC;
         }
-        if (f.nstage == 0) {  // remember the deepest ring that leaves room for a useful chunk
-            f.nstage = ns; f.JC = std::min(jc_max, 256); f.nchunks = (M + f.JC - 1) / f.JC;
-        }
+        f.nstage = (int)std::min<uint32_t>(8, (avail - (uint32_t)f.JC * row) / f.stage_bytes);
+        if (f.nstage < 2) return f;
     }
     if (f.nstage == 0) return f;
     f.off_bst = fixed;
@@ -280,12 +284,14 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
         p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
         p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
-        p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk; p.kbps = f.kbps;
-        p.nit = f.nit; p.nstage = f.nstage; p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b; p.alias_x = f.alias_x;
+        p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk;
+        p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1;
+        if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1)); p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b; p.alias_x = f.alias_x;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
         p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;
         p.stage_bytes = f.stage_bytes; p.ts_bytes = f.ts_bytes;
         memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
+        p.trace = g_trace;
         const int64_t ntiles = (N + f.TN - 1) / f.TN;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * f.ctas_per_sm);
         CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem, st));
@@ -480,6 +486,10 @@ extern "C" {
 const char* gpe_last_error(void) { return g_err; }
 int gpe_version(void) { return GPE_VERSION; }
 int64_t gpe_launch_count(void) { return g_launches.load(); }
+
+// Developer aid (not part of the public header): CTA 0 of the fused kernel records clock64() at its phase
+// boundaries for its first 64 tiles into `device_buf` (64 x 8 int64); pass NULL to switch tracing off.
+void gpe_debug_trace(long long* device_buf) { g_trace = device_buf; }
 
 int gpe_device_count(void) {
     int n = 0;

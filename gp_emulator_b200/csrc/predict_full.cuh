@@ -38,9 +38,9 @@ struct FullParams {
     int Mp;         // padded output width = WC * nt_act * 8
     int nt_act;     // active 8-column DMMA tiles per warp (<= NT)
     int kblk;       // ceil(M / 4) k-blocks
-    int kbps;       // k-blocks per pipeline stage
-    int nit;        // pipeline iterations per tile = ceil(kblk / kbps)
-    int nstage;     // ring depth
+    int nit;        // pipeline iterations per tile = ceil(kblk / KB), KB k-blocks per ring stage (template)
+    int nstage;     // ring depth (<= 8)
+    int lag;        // refill distance behind the consumer (1 or 2, < nstage)
     int JC;         // training points per phase-A chunk (multiple of 4)
     int alias_x;    // 1: the chunk buffer overlays the B-operand ring (2-CTA/SM configuration)
     int nchunks;
@@ -49,6 +49,7 @@ struct FullParams {
     uint32_t off_bar, off_sqw, off_ks, off_bst, off_xc, off_ts, off_pa, off_vred;
     uint32_t ts_bytes;     // size of ONE of the two test-row / output staging buffers at off_ts
     uint32_t stage_bytes;
+    long long* trace;      // dev aid (normally null): CTA 0 stores clock64() at phase boundaries of its first 64 tiles
     double sqrt_w[kMaxD];
 };
 
@@ -90,7 +91,7 @@ struct RS {
     }
 };
 
-template <int MT, int NT, int WR, int WC, int DP, int MINB>
+template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT>
 __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullParams p) {
     constexpr int NW = WR * WC;           // warps per CTA (power of two)
     constexpr int NTHR = NW * 32;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     const int D = p.D, M = p.M, Mp = p.Mp;
     const int pitch = Mp + 4;
     const int nstage = p.nstage;
+    const int lag = p.lag;
     const int DV = D + 1;
 
     const int64_t ntiles = (p.N + TN - 1) / TN;
@@ -149,14 +151,15 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     // B-operand ring.  Global iteration g uses stage g % nstage; (cs, cpar) track the stage / parity of the next
     // iteration to consume.  Loads are issued by lane 0 of a rotating warp so no single warp carries the cost:
     // a burst of min(nstage, nit) at the start of a tile (every earlier use was released before the end-of-tile
-    // barrier, so no wait is needed), then during iteration `it` the stage released in iteration it - 1 is
-    // refilled with k-blocks of iteration it - 1 + nstage, i.e. the copy runs nstage - 1 iterations ahead.
+    // barrier, so no wait is needed), then during iteration `it` the stage released in iteration it - lag is
+    // refilled with the k-blocks of iteration it - lag + nstage, i.e. the copy runs nstage - lag iterations ahead.
+    // lag = 2 when the ring is deep enough: with lag = 1 the issuing warp had to wait for the slowest warp of the
+    // previous iteration almost every time (ncu: 43 try_wait spins per refill), which re-synchronised the warps.
     int cs = 0;
     uint32_t cpar = 0;
-    auto issue = [&](int stage, int it_local) {
-        const int kb0 = it_local * p.kbps;
-        const int nkb = min(p.kbps, p.kblk - kb0);
-        const uint32_t bytes = (uint32_t)nkb * (uint32_t)Mp * 32u;
+    auto issue = [&](int stage, int it_local) {  // k-blocks [KB * it_local, +KB) -> ring stage
+        const int kb0 = it_local * KB;
+        const uint32_t bytes = (uint32_t)min(KB, p.kblk - kb0) * (uint32_t)Mp * 32u;
         mbar_arrive_expect_tx(&bar_full[stage], bytes);
         tma_bulk_g2s(Bst + (size_t)stage * p.stage_bytes, p.s_tiled + (size_t)kb0 * Mp * 4, bytes, &bar_full[stage]);
     };
@@ -192,15 +195,19 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     const int n_a = n_hi * 8 + n_low, n_b = n_a + 4;
     // phase-B warp coordinates
     const int wrow = warp / WC, wcol = warp % WC;
-    const int nt_act = p.nt_act;
+    const int nt_act = FULLNT ? NT : p.nt_act;  // FULLNT: every column tile active, no predicates around the DMMAs
 
     int buf = 0;
     if (tid == 0 && blockIdx.x < ntiles) prefetch_rows(blockIdx.x, 0);
+    int trace_tile = 0;
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && tid == 0;
+#define GPE_TRACE(k) do { if (tracing && trace_tile < 64) p.trace[trace_tile * 8 + (k)] = clock64(); } while (0)
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int64_t n0 = tile * TN;
         const int npts = (int)min((int64_t)TN, p.N - n0);
         double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
+        GPE_TRACE(0);
         // B-operand prefetch for this tile's contraction lands while phase A runs (unless the buffers are shared)
         if (want_var && !alias_x && tid == 0) issue_burst();
 
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             if (tid == 0 && next < ntiles) prefetch_rows(next, buf ^ 1);
         }
 
+        GPE_TRACE(1);
         // ---- phase A: K* tile + mean + gradient sums ----------------------------------------------------
         double va[NV], vb[NV];  // [0] mean, [1 + d] gradient sums of the two rows
 #pragma unroll
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             if (!x_resident) __syncthreads();  // all reads of Xc done before the next chunk (or the ring) lands
         }
 
+        GPE_TRACE(2);
         // combine the 8 j-lanes of each point (reduce-scatter), then (GH > 1) the j-warps through smem
         double* outs = ts_s;  // [TN][D+1]: mean, then unscaled gradient sums
         {
@@ -343,6 +352,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             }
         }
 
+        GPE_TRACE(3);
         // ---- phase B: variance contraction on the FP64 tensor path --------------------------------------
         if (want_var) {
             double acc[MT][NT][2];
@@ -355,28 +365,34 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             const int b_off = (wcol * nt_act * 8 + (lane >> 2)) * 4 + (lane & 3);
 
             if (alias_x && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
+            // KB k-blocks (4 values of the contraction index each) per ring stage, fully unrolled.  The A fragments
+            // come from the K* tile, not from the ring, so they are fetched before waiting on the stage barrier.
             for (int it = 0; it < p.nit; ++it) {
-                if (it >= 1 && lane == 0 && warp == (it & (NW - 1)) && it - 1 + nstage < p.nit) {
-                    const int ps = (cs == 0) ? nstage - 1 : cs - 1;          // stage of iteration it - 1
-                    const uint32_t ppar = (cs == 0) ? (cpar ^ 1) : cpar;     // parity of that use
+                if (it >= lag && lane == 0 && warp == (it & (NW - 1)) && it - lag + nstage < p.nit) {
+                    const int ps = (cs >= lag) ? cs - lag : cs - lag + nstage;   // stage of iteration it - lag
+                    const uint32_t ppar = (cs >= lag) ? cpar : (cpar ^ 1);      // parity of that use
                     mbar_wait(&bar_empty[ps], ppar);
-                    issue(ps, it - 1 + nstage);
+                    issue(ps, it - lag + nstage);
                 }
+                const int kb0 = it * KB;
+                double a[KB][MT];
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) a[kk][i] = a_base[i * 8 * pitch + (kb0 + kk) * 4];  // pad columns are 0
                 mbar_wait(&bar_full[cs], cpar);
                 const double* bs = reinterpret_cast<const double*>(Bst + (size_t)cs * p.stage_bytes) + b_off;
-                const int kb0 = it * p.kbps;
-                const int nkb = min(p.kbps, p.kblk - kb0);
-                for (int kk = 0; kk < nkb; ++kk) {
-                    double a[MT];
 #pragma unroll
-                    for (int i = 0; i < MT; ++i) a[i] = a_base[i * 8 * pitch + (kb0 + kk) * 4];
-                    const double* bk = bs + kk * Mp * 4;
+                for (int kk = 0; kk < KB; ++kk) {
+                    if (KB == 1 || kb0 + kk < p.kblk) {
+                        const double* bk = bs + kk * Mp * 4;
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        if (j < nt_act) {
-                            const double bf = bk[j * 32];
+                        for (int j = 0; j < NT; ++j) {
+                            if (FULLNT || j < nt_act) {
+                                const double bf = bk[j * 32];
 #pragma unroll
-                            for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bf);
+                                for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
+                            }
                         }
                     }
                 }
@@ -385,6 +401,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 if (++cs == nstage) { cs = 0; cpar ^= 1; }
             }
 
+            GPE_TRACE(4);
             // epilogue: var_n = b - b^2 sum_j G_nj K*_nj
             double vs[MT];
 #pragma unroll
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             const double* k_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + wcol * nt_act * 8 + 2 * (lane & 3);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                if (j < nt_act) {
+                if (FULLNT || j < nt_act) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
                         const double2 kk = *reinterpret_cast<const double2*>(k_base + i * 8 * pitch + j * 8);
@@ -416,7 +433,11 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             }
         }
         __syncthreads();  // K*, outs, vred (and the ring, if it doubles as chunk buffer) are free for the next tile
+        GPE_TRACE(5);
+        ++trace_tile;
     }
 }
+
+#undef GPE_TRACE
 
 }  // namespace gpe

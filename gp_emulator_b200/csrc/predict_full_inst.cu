@@ -13,9 +13,10 @@
 
 namespace gpe {
 
-template <int MT, int NT, int WR, int WC, int MINB>
+template <int MT, int NT, int WR, int WC, int MINB, int KB>
 static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = k_predict_full<MT, NT, WR, WC, GPE_DP, MINB>;
+    auto kern = (p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true>
+                                 : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false>;
     // per function AND per device: set on every launch (microseconds) so multi-device processes stay correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -25,11 +26,11 @@ static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaSt
 
 cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_cfg<4, 8, 2, 4, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 8 warps, 1 CTA/SM
-        case 1: return launch_cfg<4, 8, 1, 8, 1>(p, grid, smem, st);   // TN = 32, Mp <= 512, 8 warps, 1 CTA/SM
-        case 2: return launch_cfg<2, 16, 1, 8, 1>(p, grid, smem, st);  // TN = 16, Mp <= 1024, 8 warps, 1 CTA/SM
-        case 3: return launch_cfg<4, 8, 1, 4, 2>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
-        case 4: return launch_cfg<4, 4, 2, 8, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
+        case 0: return launch_cfg<4, 8, 2, 4, 1, 2>(p, grid, smem, st);   // TN = 64, Mp <= 256, 8 warps, 1 CTA/SM
+        case 1: return launch_cfg<4, 8, 1, 8, 1, 1>(p, grid, smem, st);   // TN = 32, Mp <= 512, 8 warps, 1 CTA/SM
+        case 2: return launch_cfg<2, 16, 1, 8, 1, 1>(p, grid, smem, st);  // TN = 16, Mp <= 1024, 8 warps, 1 CTA/SM
+        case 3: return launch_cfg<4, 8, 1, 4, 2, 1>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
+        case 4: return launch_cfg<4, 4, 2, 8, 1, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
         default: return cudaErrorInvalidValue;
     }
 }
