@@ -58,6 +58,12 @@ struct FullPlan {
     uint32_t stage_bytes = 0, smem = 0, ts_bytes = 0;
 };
 
+struct Tf32Plan {
+    bool valid = false;
+    int DP = 0, Mp = 0, nslab = 0;
+    uint32_t off_bar = 0, off_tmem = 0, off_a = 0, off_b = 0, off_x = 0, off_out = 0, off_vred = 0, bstage_bytes = 0, smem = 0;
+};
+
 struct MeanPlan {
     int JC = 0, nchunks = 0;
     uint32_t off_xc = 0, off_ts = 0, off_out = 0, smem = 0, smem_hess = 0;
@@ -88,6 +94,11 @@ struct gpe_model {
     double* d_xchunks_full = nullptr;
     double* d_stiled = nullptr;
     double* d_xchunks_mean = nullptr;
+    Tf32Plan tf;                 // single-precision tcgen05 path (M <= 256), built lazily by gpe_predict_f32
+    float* d_xa_f32 = nullptr;
+    uint32_t* d_bslabs = nullptr;
+    std::vector<double> h_inputs, h_invQt, h_invQ;  // host copy of the model for the lazy FP32 packing
+    double h_expx[33];
     Slot slots[2];
 };
 
@@ -467,6 +478,86 @@ __global__ void __launch_bounds__(kProjCols) k_project(const double* __restrict_
     }
 }
 
+// ---- single-precision (tcgen05 / TF32) path ------------------------------------------------------------------
+uint32_t host_tf32_rna(float x) {   // round-to-nearest (ties away) to 10 mantissa bits, as cvt.rna.tf32.f32
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return u;
+    return (u + 0x1000u) & 0xFFFFE000u;
+}
+
+int ensure_tf32(gpe_model* m) {
+    if (m->tf.valid) return GPE_OK;
+    const int M = m->M, D = m->D;
+    if (M > 256) return fail(GPE_ERR_UNSUPPORTED, "the single-precision tensor-core path supports M <= 256 (got %d)", M);
+    Tf32Plan t;
+    t.DP = -1;
+    for (int dp : kTfDpList) if (dp >= D) { t.DP = dp; break; }
+    if (t.DP < 0) return fail(GPE_ERR_UNSUPPORTED, "D = %d not supported by the single-precision path", D);
+    t.Mp = (M + 63) / 64 * 64;
+    t.nslab = (M + 31) / 32;
+    t.bstage_bytes = (uint32_t)t.Mp * 128u;
+    uint32_t off = 0;
+    t.off_bar = off; off += 128;
+    t.off_tmem = off; off += 16;
+    off = align_up(off, 1024);
+    t.off_a = off; off += (uint32_t)t.nslab * kTfTN * 128u;
+    t.off_b = off; off += 2 * t.bstage_bytes;
+    t.off_x = off; off += align_up((uint32_t)t.Mp * (t.DP + 1) * 4u, 16);
+    t.off_out = off; off += align_up((uint32_t)kTfTN * (D + 1) * 4u, 16);
+    t.off_vred = off; off += 2u * kTfTN * 4u;
+    t.smem = off;
+    if (t.smem > kSmemMax) return fail(GPE_ERR_UNSUPPORTED, "single-precision path needs %u bytes of shared memory", t.smem);
+    const float b = (float)m->b;
+    std::vector<float> xa((size_t)t.Mp * (t.DP + 1), 0.f);
+    for (int j = 0; j < M; ++j) {
+        for (int d = 0; d < D; ++d) xa[(size_t)j * t.DP + d] = (float)(m->sqrt_w[d] * m->h_inputs[(size_t)j * D + d]);
+        xa[(size_t)t.Mp * t.DP + j] = (float)(m->b * m->h_invQt[j]);
+    }
+    (void)b;
+    CUDA_TRY(cudaMalloc((void**)&m->d_xa_f32, xa.size() * 4));
+    CUDA_TRY(cudaMemcpy(m->d_xa_f32, xa.data(), xa.size() * 4, cudaMemcpyHostToDevice));
+    if (!m->h_invQ.empty()) {
+        // B operand: slab s holds invQ[j][32 s .. 32 s + 31] for every output column j as a [Mp][128 B] image with
+        // the 16-byte chunk index XOR-ed by (j % 8): exactly what a SWIZZLE_128B K-major UMMA descriptor reads
+        std::vector<uint32_t> bs((size_t)t.nslab * t.Mp * 32, 0u);
+        for (int j = 0; j < M; ++j)
+            for (int i = 0; i < M; ++i) {
+                const int s = i >> 5, c = (i & 31) >> 2, e = i & 3;
+                bs[(size_t)s * t.Mp * 32 + (size_t)j * 32 + (size_t)((c ^ (j & 7)) << 2) + e] =
+                    host_tf32_rna((float)m->h_invQ[(size_t)j * M + i]);
+            }
+        CUDA_TRY(cudaMalloc((void**)&m->d_bslabs, bs.size() * 4));
+        CUDA_TRY(cudaMemcpy(m->d_bslabs, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice));
+    }
+    t.valid = true;
+    m->tf = t;
+    return GPE_OK;
+}
+
+int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu, float* var, float* deriv,
+                       cudaStream_t st) {
+    if (N == 0) return GPE_OK;
+    int rc = ensure_tf32(m);
+    if (rc) return rc;
+    if (var && !m->d_bslabs) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
+    const Tf32Plan& t = m->tf;
+    Tf32Params p;
+    memset(&p, 0, sizeof(p));
+    p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
+    p.ld_mu = 1; p.ld_var = 1; p.ld_deriv = m->D;
+    p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs;
+    p.M = m->M; p.D = m->D; p.Mp = t.Mp; p.nslab = t.nslab; p.b = (float)m->b;
+    p.off_bar = t.off_bar; p.off_a = t.off_a; p.off_b = t.off_b; p.off_x = t.off_x; p.off_out = t.off_out;
+    p.off_vred = t.off_vred; p.off_tmem = t.off_tmem; p.bstage_bytes = t.bstage_bytes;
+    for (int d = 0; d < 32; ++d) p.sqrt_w[d] = (float)m->sqrt_w[d];
+    const int64_t ntiles = (N + kTfTN - 1) / kTfTN;
+    const int grid = (int)std::min<int64_t>(ntiles, m->sms);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(launch_tf32(t.DP, p, grid, t.smem, st));
+    return GPE_OK;
+}
+
 uint64_t fnv1a(const void* data, size_t bytes, uint64_t h) {
     const uint64_t* p = (const uint64_t*)data;
     const size_t n = bytes / 8;
@@ -513,6 +604,10 @@ int gpe_model_create(int device, int M, int D, const double* inputs, const doubl
     m->b = expX[D];
     for (int d = 0; d < 32; ++d) m->sqrt_w[d] = (d < D) ? std::sqrt(expX[d]) : 0.0;
     m->has_invQ = invQ != nullptr;
+    m->h_inputs.assign(inputs, inputs + (size_t)M * D);
+    m->h_invQt.assign(invQt, invQt + M);
+    if (invQ && M <= 256) m->h_invQ.assign(invQ, invQ + (size_t)M * M);
+    for (int d = 0; d <= D; ++d) m->h_expx[d] = expX[d];
     m->mean = plan_mean(M, D, m->DP);
     {
         std::vector<double> xc = pack_xchunks(M, D, m->DP, m->mean.JC, m->mean.nchunks, inputs, m->sqrt_w, invQt, m->b);
@@ -548,6 +643,8 @@ int gpe_model_destroy(gpe_model* m) {
     if (m->d_xchunks_full) cudaFree(m->d_xchunks_full);
     if (m->d_stiled) cudaFree(m->d_stiled);
     if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
+    if (m->d_xa_f32) cudaFree(m->d_xa_f32);
+    if (m->d_bslabs) cudaFree(m->d_bslabs);
     delete m;
     return GPE_OK;
 }
@@ -571,6 +668,46 @@ int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, doub
     if (flags & GPE_HOST_PTRS) return predict_host(m, testing, N, mu, var, deriv, hess);
     return predict_device(m, testing, N, mu, var, deriv, hess, 1, 1, m->D, (int64_t)m->D * m->D,
                           (cudaStream_t)stream);
+}
+
+int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, float* var, float* deriv, unsigned flags,
+                    void* stream) {
+    if (!m) return fail(GPE_ERR_INVALID, "model is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing) return fail(GPE_ERR_INVALID, "testing is NULL");
+    if (flags & GPE_WANT_HESS) return fail(GPE_ERR_UNSUPPORTED, "the single-precision path has no Hessian output");
+    if (!(flags & GPE_WANT_MU)) mu = nullptr;
+    if (!(flags & GPE_WANT_VAR)) var = nullptr;
+    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
+    if ((flags & GPE_WANT_MU) && !mu) return fail(GPE_ERR_INVALID, "GPE_WANT_MU set but mu is NULL");
+    if ((flags & GPE_WANT_VAR) && !var) return fail(GPE_ERR_INVALID, "GPE_WANT_VAR set but var is NULL");
+    if ((flags & GPE_WANT_DERIV) && !deriv) return fail(GPE_ERR_INVALID, "GPE_WANT_DERIV set but deriv is NULL");
+    if (!mu && !var && !deriv) return fail(GPE_ERR_INVALID, "no output requested");
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, (cudaStream_t)stream);
+    // host pointers: plain chunked copies on the default stream (the FP64 path has the overlapped pipeline)
+    const int D = m->D;
+    const int64_t CH = std::min<int64_t>(1 << 20, N);
+    float *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_in, (size_t)CH * D * 4));
+    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)CH * (D + 2) * 4);
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(GPE_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    int rc = GPE_OK;
+    for (int64_t n0 = 0; n0 < N && rc == GPE_OK; n0 += CH) {
+        const int64_t n = std::min(CH, N - n0);
+        float* o_mu = d_out; float* o_var = d_out + n; float* o_der = d_out + 2 * n;
+        e = cudaMemcpy(d_in, testing + n0 * D, (size_t)n * D * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) rc = predict_device_f32(m, d_in, n, mu ? o_mu : nullptr, var ? o_var : nullptr,
+                                                      deriv ? o_der : nullptr, nullptr);
+        if (rc == GPE_OK && e == cudaSuccess && mu) e = cudaMemcpy(mu + n0, o_mu, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (rc == GPE_OK && e == cudaSuccess && var) e = cudaMemcpy(var + n0, o_var, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (rc == GPE_OK && e == cudaSuccess && deriv) e = cudaMemcpy(deriv + n0 * D, o_der, (size_t)n * D * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(GPE_ERR_CUDA, "single-precision host path failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
 }
 
 int gpe_predict_wrap(const double* expX, const double* inputs, const double* invQt, const double* invQ,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
+#include "predict_tf32.cuh"
 
 namespace gpe {
 
@@ -20,6 +21,9 @@ GPE_DECL_DP(16)
 GPE_DECL_DP(24)
 GPE_DECL_DP(32)
 #undef GPE_DECL_DP
+
+cudaError_t launch_tf32(int DP, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
+static const int kTfDpList[] = {4, 8, 12, 16, 32};
 
 // padded input dimensions that have compiled kernels, ascending
 static const int kDpList[] = {2, 4, 6, 8, 10, 12, 16, 24, 32};

@@ -121,6 +121,44 @@ class DeviceModel:
         return {k: out[k] for k in wanted}
 
 
+    def predict_f32(self, testing, want_var=True, want_deriv=True):
+        """Single-precision prediction on the tcgen05 / TMEM path (M <= 256): float32 in, float32 out.
+
+        numpy float32 (N, D) -> numpy results; torch float32 CUDA tensor -> torch results (asynchronous).
+        The variance contraction runs on the tensor cores with TF32 inputs (see DESIGN.md for the error bound).
+        """
+        lib = _lib.load()
+        D = self.D
+        if want_var and not self.has_var:
+            raise GpemuError("variance requested but the model was uploaded without invQ")
+        flags = WANT_MU | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0)
+        if _is_torch(testing):
+            import torch
+            t = testing
+            if not t.is_cuda or t.device.index != self.device or t.dtype != torch.float32 or t.dim() != 2 \
+                    or t.shape[1] != D:
+                raise ValueError(f"testing must be a float32 (N, {D}) tensor on cuda:{self.device}")
+            t = t.contiguous()
+            N = t.shape[0]
+            mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=t.device)
+            out = {"mu": mk(N)}
+            if want_var: out["var"] = mk(N)
+            if want_deriv: out["deriv"] = mk(N, D)
+            check(lib.gpe_predict_f32(self._h, addr(t), N, addr(out["mu"]), addr(out.get("var")),
+                                      addr(out.get("deriv")), flags, _current_stream_ptr(self.device)))
+            return out
+        t = np.ascontiguousarray(testing, dtype=np.float32)
+        if t.ndim != 2 or t.shape[1] != D:
+            raise ValueError(f"testing must be (N, {D})")
+        N = t.shape[0]
+        out = {"mu": np.empty(N, dtype=np.float32)}
+        if want_var: out["var"] = np.empty(N, dtype=np.float32)
+        if want_deriv: out["deriv"] = np.empty((N, D), dtype=np.float32)
+        check(lib.gpe_predict_f32(self._h, addr(t), N, addr(out["mu"]), addr(out.get("var")),
+                                  addr(out.get("deriv")), flags | HOST_PTRS, None))
+        return out
+
+
 class DeviceBank:
     """E GPs sharing training inputs and test points; optional PCA basis (E, W) for back-projection."""
 

@@ -134,7 +134,9 @@ class GaussianProcess:
 
         Returns ``(mu, var, deriv)``; ``(mu, deriv)`` if ``do_unc`` is False (as the reference's CPU branch,
         :248-251); ``(mu, var)`` / ``mu`` when ``do_deriv`` is False (the upstream-style signature).
-        ``deriv`` is (N, D).  Computation is FP64 on the GPU; ``precision`` only casts the numpy results.
+        ``deriv`` is (N, D).  Computation is FP64 on the GPU unless ``precision=np.float32`` (or a float32 CUDA
+        tensor) is given and M <= 256: then the single-precision tensor-core path runs (for larger M the FP64
+        results are cast).
         ``testing`` may also be a float64 torch CUDA tensor, in which case torch tensors are returned.
         ``out`` (dict with any of "mu", "var", "deriv") supplies preallocated result buffers, ``pinned=True``
         makes freshly allocated host results page-locked (see ``DeviceModel.predict``).
@@ -143,7 +145,16 @@ class GaussianProcess:
             raise ValueError("testing must always be a 2-D array (N, D)")
         if testing.shape[1] != self.D:
             raise AssertionError("testing has %d columns, model has D = %d" % (testing.shape[1], self.D))
-        out = self._device_model().predict(testing, want_var=do_unc, want_deriv=do_deriv, out=out, pinned=pinned)
+        dm = self._device_model()
+        is_t = hasattr(testing, "dim")
+        f32_in = (is_t and str(testing.dtype) == "torch.float32") or (not is_t and precision is np.float32)
+        if f32_in and dm.M <= 256 and out is None:
+            # the reference's FP32 GPU build (precision=np.float32, GaussianProcess.py:289-316): single precision
+            # end to end, variance contraction on the tensor cores (tcgen05, TF32 inputs)
+            o = dm.predict_f32(testing, want_var=do_unc, want_deriv=do_deriv)
+            res = [o["mu"]] + ([o["var"]] if do_unc else []) + ([o["deriv"]] if do_deriv else [])
+            return tuple(res) if len(res) > 1 else res[0]
+        out = dm.predict(testing, want_var=do_unc, want_deriv=do_deriv, out=out, pinned=pinned)
         res = [out["mu"]]
         if do_unc:
             res.append(out["var"])

@@ -178,6 +178,42 @@ def test_preallocated_and_pinned_outputs(gpemu):
     assert got["var"] is dout["var"] and np.array_equal(got["var"].cpu().numpy(), ref["var"])
 
 
+@pytest.mark.parametrize("M,D,N", [(250, 10, 3000), (256, 10, 129), (64, 4, 500), (37, 3, 1), (100, 7, 257),
+                                   (200, 16, 300), (130, 12, 128), (10, 1, 40)])
+def test_single_precision_tensor_core_path(gpemu, M, D, N):
+    """tcgen05 / TMEM kernel.  Bars: mean and gradient at the reference's own FP32 pass criterion 1e-5
+    (tests/benchmark.py:56); variance 5e-4 = 2^-11, the TF32 input rounding (measured ~6e-5 at M = 250)."""
+    import torch
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    t32 = testing.astype(np.float32)
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, t32.astype(np.float64))
+    o = m.predict_f32(t32)
+    assert o["mu"].dtype == np.float32 and o["deriv"].shape == (N, D)
+    assert orc.ref_err(o["mu"], mu) < 1e-5 and orc.ref_err(o["deriv"], deriv) < 1e-5
+    assert orc.ref_err(o["var"], var) < 5e-4
+    o2 = m.predict_f32(t32, want_var=False)
+    assert np.array_equal(o2["mu"], o["mu"]) and np.array_equal(o2["deriv"], o["deriv"])
+    od = m.predict_f32(torch.from_numpy(t32).cuda())
+    torch.cuda.synchronize()
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(od[k].cpu().numpy(), o[k])
+
+
+def test_single_precision_limits_and_dropin_routing(gpemu):
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(300, 5, 50, seed=2)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    with pytest.raises(gpemu.GpemuError):
+        m.predict_f32(testing.astype(np.float32))          # M > 256: not served by the tensor-core path
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 5000, seed=0)
+    gp = gpemu.GaussianProcess(inputs, [])
+    gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt
+    mu_c, var_c, deriv_c = orc.predict(inputs, theta, invQ, invQt, testing)
+    mu, var, deriv = gp.predict(testing, precision=np.float32)    # the reference benchmark's GPU call
+    assert mu.dtype == np.float32
+    assert orc.ref_err(mu, mu_c) < 1e-5 and orc.ref_err(deriv, deriv_c) < 1e-5 and orc.ref_err(var, var_c) < 5e-4
+
+
 def test_dropin_class_matches_reference_semantics(gpemu):
     """The reference's benchmark flow (tests/benchmark.py:11-60): overwrite attributes, call predict."""
     inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 2000, seed=0)
