@@ -21,6 +21,7 @@
 
 #include "../../include/gpemu.h"
 #include "launch.h"
+#include "gpe_math.cuh"
 
 using namespace gpe;
 
@@ -105,7 +106,8 @@ struct gpe_model {
 struct gpe_bank {
     int device = 0, E = 0, M = 0, D = 0, W = 0;
     std::vector<gpe_model*> models;
-    double* d_basis = nullptr;
+    double* d_basis = nullptr;   // basis pre-tiled as [ceil(E/4)][Wp][4], Wp = W rounded up to 256
+    int Wp = 0;
 };
 
 namespace {
@@ -448,34 +450,113 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
 }
 
 // ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
-constexpr int kProjRows = 4, kProjCols = 256;
-__global__ void __launch_bounds__(kProjCols) k_project(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
-                                                       int64_t lde, int64_t ldd, const double* __restrict__ basis,
-                                                       int E, int W, double* __restrict__ out) {
-    // CTA: 32 rows x 256 columns; thread: one column, 4 rows at a time; A rows staged in smem (broadcast reads)
-    __shared__ double a_s[32][33];
-    const int w = blockIdx.x * kProjCols + threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.y * 32;
-    for (int i = threadIdx.x; i < 32 * E; i += kProjCols) {
-        const int rr = i / E, e = i - rr * E;
-        const int64_t r = r0 + rr;
-        a_s[rr][e] = (r < R) ? A[(r / RD) * ldn + (int64_t)e * lde + (r % RD) * ldd] : 0.0;
+// A skinny FP64 GEMM (K = E <= 32) whose output write is the HBM-bound part (W = 2101 doubles per row) and whose
+// 2 E W flop per row sit right at the FP64 ridge, so it runs on the FP64 tensor path.  CTA = 64 rows, 8 warps as
+// 2 (rows) x 4 (columns); a warp keeps its A fragments (32 rows x E) in registers for the whole sweep over W and
+// produces 32 x 32 output tiles with DMMA.8x8x4.  The basis is pre-tiled at bank creation as [ks][Wp][4]
+// (b_tiled[ks][w][c] = basis[4 ks + c][w], zero padded), the same conflict-free B-fragment image the variance
+// kernel uses, streamed in 128-column groups by TMA bulk copies through a two-stage mbarrier ring.  Output tiles
+// go through a per-warp smem buffer (16 rows x pitch 40 doubles = conflict-free 16-byte fragment stores) so
+// every global store instruction writes 256 contiguous bytes of one output row (rows are only 8-byte aligned:
+// W is odd).  Two CTAs per SM (<= 128 registers, 80 KB smem) so that one CTA's store burst drains -- HBM absorbs
+// ~25 B/clk per SM -- while the other's DMMAs run; ncu showed the single-CTA version lg_throttle-bound.
+constexpr int kProjThreads = 256, kProjRows = 64, kProjCols = 128;
+constexpr int kProjPitch = 40;  // doubles; = 8 (mod 16) so a quarter-warp's 16-byte fragment stores hit 32 banks
+template <int KS>   // k-steps of 4: E <= 4 KS
+__global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
+                                                             int64_t lde, int64_t ldd, const double* __restrict__ b_tiled,
+                                                             int E, int W, int Wp, double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(psm);          // [2]
+    double* stage = reinterpret_cast<double*>(psm + 128);       // [2][KS][128][4]
+    double* ctile = stage + 2 * (size_t)KS * kProjCols * 4;     // [8 warps][16][kProjPitch]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp >> 2, wc = warp & 3;
+    const int64_t r0 = (int64_t)blockIdx.x * kProjRows + wr * 32;
+    const int ngroups = Wp / kProjCols;
+    constexpr uint32_t ks_bytes = kProjCols * 4 * 8, stage_doubles = (uint32_t)KS * kProjCols * 4;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
     }
     __syncthreads();
-    if (w >= W) return;
-    for (int rb = 0; rb < 32; rb += kProjRows) {
-        double acc[kProjRows] = {0, 0, 0, 0};
-        for (int e = 0; e < E; ++e) {
-            const double bv = __ldg(basis + (size_t)e * W + w);
+    auto load_group = [&](int g, int st) {   // thread 0
+        mbar_arrive_expect_tx(&full[st], (uint32_t)KS * ks_bytes);
+        for (int ks = 0; ks < KS; ++ks)
+            tma_bulk_g2s(stage + (size_t)st * stage_doubles + (size_t)ks * kProjCols * 4,
+                         b_tiled + ((size_t)ks * Wp + (size_t)g * kProjCols) * 4, ks_bytes, &full[st]);
+    };
+    if (tid == 0) {
+        load_group(0, 0);
+        if (ngroups > 1) load_group(1, 1);
+    }
+    // A fragments: lane holds A[row = 8 i + lane / 4][k = 4 ks + lane % 4]
+    double a[4][KS];
 #pragma unroll
-            for (int i = 0; i < kProjRows; ++i) acc[i] = fma(a_s[rb + i][e], bv, acc[i]);
-        }
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + 8 * i + (lane >> 2);
+        const int64_t base = (r < R) ? (r / RD) * ldn + (r % RD) * ldd : 0;
 #pragma unroll
-        for (int i = 0; i < kProjRows; ++i) {
-            const int64_t r = r0 + rb + i;
-            if (r < R) out[r * W + w] = acc[i];
+        for (int ks = 0; ks < KS; ++ks) {
+            const int e = 4 * ks + (lane & 3);
+            a[i][ks] = (r < R && e < E) ? A[base + (int64_t)e * lde] : 0.0;
         }
     }
+    const int nrow = (int)max((int64_t)0, min((int64_t)32, R - r0));
+    double* ct = ctile + (size_t)warp * (16 * kProjPitch);
+    uint32_t par = 0;
+    for (int g = 0; g < ngroups; ++g) {
+        const int st = g & 1;
+        mbar_wait(&full[st], (par >> st) & 1u);
+        par ^= 1u << st;
+        const double* bs = stage + (size_t)st * stage_doubles + (size_t)(wc * 32 + (lane >> 2)) * 4 + (lane & 3);
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double bf = bs[(size_t)ks * kProjCols * 4 + j * 32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i][ks], bf);
+            }
+        }
+        const int w = g * kProjCols + wc * 32 + lane;
+        double* o = out + r0 * W + w;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {   // rows 0..15, then 16..31 of the warp tile
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2*>(ct + (8 * i + (lane >> 2)) * kProjPitch + 8 * j + 2 * (lane & 3)) =
+                        make_double2(acc[2 * half + i][j][0], acc[2 * half + i][j][1]);
+            __syncwarp();
+            if (w < W) {
+#pragma unroll 4
+                for (int rr = 0; rr < 16; ++rr)
+                    if (16 * half + rr < nrow) o[(int64_t)(16 * half + rr) * W] = ct[rr * kProjPitch + lane];
+            }
+        }
+        __syncthreads();   // every warp is done with this stage: refill it with group g + 2
+        if (tid == 0 && g + 2 < ngroups) load_group(g + 2, st);
+    }
+}
+
+template <int KS>
+cudaError_t launch_project(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd,
+                           const double* b_tiled, int E, int W, int Wp, double* out, cudaStream_t st) {
+    const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 8 * 16 * kProjPitch * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_project<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    if (e != cudaSuccess) return e;
+    k_project<KS><<<(unsigned)((R + kProjRows - 1) / kProjRows), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd,
+                                                                                          b_tiled, E, W, Wp, out);
+    return cudaGetLastError();
 }
 
 // ---- single-precision (tcgen05 / TF32) path ------------------------------------------------------------------
@@ -756,8 +837,14 @@ int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const
         b->models.push_back(m);
     }
     if (basis) {
-        cudaError_t e = cudaMalloc((void**)&b->d_basis, (size_t)E * W * 8);
-        if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, basis, (size_t)E * W * 8, cudaMemcpyHostToDevice);
+        const int ks_e = (E + 3) / 4;
+        const int ks_n = ks_e <= 3 ? 3 : (ks_e <= 5 ? 5 : 8);   // the k-step count of the kernel instantiation used
+        b->Wp = (W + kProjCols - 1) / kProjCols * kProjCols;
+        std::vector<double> bt((size_t)ks_n * b->Wp * 4, 0.0);
+        for (int e2 = 0; e2 < E; ++e2)
+            for (int w = 0; w < W; ++w) bt[((size_t)(e2 >> 2) * b->Wp + w) * 4 + (e2 & 3)] = basis[(size_t)e2 * W + w];
+        cudaError_t e = cudaMalloc((void**)&b->d_basis, bt.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "basis upload failed: %s", cudaGetErrorString(e)); }
     }
     *out = b;
@@ -804,30 +891,20 @@ int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t
     CUDA_TRY(cudaSetDevice(b->device));
     const int E = b->E, D = b->D, W = b->W;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned gx = (W + kProjCols - 1) / kProjCols;
+    auto run = [&](const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, double* o) {
+        g_launches.fetch_add(1);
+        const int ks = (E + 3) / 4;
+        if (ks <= 3) return launch_project<3>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
+        if (ks <= 5) return launch_project<5>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
+        return launch_project<8>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
+    };
     if (fwd) {
         if (!mu) return fail(GPE_ERR_INVALID, "fwd requested but mu is NULL");
-        int64_t R = N;
-        for (int64_t r0 = 0; r0 < R; r0 += 65535ll * 32) {  // gridDim.y limit
-            const int64_t rows = std::min<int64_t>(R - r0, 65535ll * 32);
-            dim3 grid(gx, (unsigned)((rows + 31) / 32));
-            g_launches.fetch_add(1);
-            k_project<<<grid, kProjCols, 0, st>>>(mu + r0 * E, rows, 1, E, 1, 0, b->d_basis, E, W, fwd + r0 * W);
-            CUDA_TRY(cudaGetLastError());
-        }
+        CUDA_TRY(run(mu, N, 1, E, 1, 0, fwd));
     }
     if (deriv_full) {
         if (!deriv) return fail(GPE_ERR_INVALID, "deriv_full requested but deriv is NULL");
-        const int64_t R = N * D;
-        const int64_t step = (65535ll * 32) / D * D;  // whole points per launch
-        for (int64_t r0 = 0; r0 < R; r0 += step) {
-            const int64_t rows = std::min<int64_t>(R - r0, step);
-            dim3 grid(gx, (unsigned)((rows + 31) / 32));
-            g_launches.fetch_add(1);
-            k_project<<<grid, kProjCols, 0, st>>>(deriv + (r0 / D) * E * D, rows, D, (int64_t)E * D, D, 1, b->d_basis, E,
-                                                 W, deriv_full + r0 * W);
-            CUDA_TRY(cudaGetLastError());
-        }
+        CUDA_TRY(run(deriv, N * D, D, (int64_t)E * D, D, 1, deriv_full));
     }
     return GPE_OK;
 }

@@ -1,0 +1,100 @@
+"""Secondary BASELINE.json configurations (3, 4, 5) on one GPU: device-resident throughput + parity spot checks.
+Writes one JSON object per configuration (profiles/r01_configs.json is a saved copy of this output)."""
+import json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gp_emulator_b200 as g
+from oracle import gp_oracle as orc
+
+peaks = g.measure_fp64_peaks(0)
+P64 = peaks["dmma_tflops"]
+
+
+def timeit(fn, reps=3, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        r = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3, r
+
+
+def F(M, D):
+    return 2 * M * M + M * (5 * D + 6) + D + 1
+
+
+out = []
+# ---- config 3: M = 1000, variance dominated -----------------------------------------------------------------
+M, D, N = 1000, 10, 1_000_000
+inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, 2000, seed=3)
+m = g.DeviceModel(inputs, theta, invQt, invQ)
+o = m.predict(testing)
+mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+t = torch.rand(N, D, dtype=torch.float64, device="cuda")
+s, _ = timeit(lambda: m.predict(t))
+out.append({"config": "3: M=1000 D=10 FP64 mu+var+grad", "N": N, "points_per_s": N / s,
+            "alg_tflops": N * F(M, D) / s / 1e12, "frac_of_dmma_peak": N * F(M, D) / s / 1e12 / P64,
+            "parity": {"mu": orc.ref_err(o["mu"], mu), "var": orc.ref_err(o["var"], var), "deriv": orc.ref_err(o["deriv"], deriv)},
+            "note": "single-precision tensor-core variant serves M <= 256 only (see config 1T below)"})
+del t
+
+# ---- config 1T: headline shape in single precision on tcgen05 -----------------------------------------------
+M, D, N = 250, 10, 40_000_000
+inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, 4000, seed=0)
+m = g.DeviceModel(inputs, theta, invQt, invQ)
+t32 = testing.astype(np.float32)
+o = m.predict_f32(t32)
+mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, t32.astype(np.float64))
+t = torch.rand(N, D, dtype=torch.float32, device="cuda")
+s, _ = timeit(lambda: m.predict_f32(t))
+out.append({"config": "1T: M=250 D=10 FP32/TF32 (tcgen05 + TMEM) mu+var+grad", "N": N, "points_per_s": N / s,
+            "tf32_tflops": N * 2 * 256 * 256 / s / 1e12,
+            "parity_vs_fp64_oracle": {"mu": orc.ref_err(o["mu"], mu), "var": orc.ref_err(o["var"], var), "deriv": orc.ref_err(o["deriv"], deriv)}})
+del t
+
+# ---- config 4: MultivariateEmulator, P = 20 PCs, W = 2101 wavelengths ---------------------------------------
+M, D, P, W, N = 250, 10, 20, 2101, 200_000
+rs = np.random.RandomState(4)
+inputs = rs.random_sample((M, D))
+thetas = rs.random_sample((P, D + 2)); invQts = rs.random_sample((P, M)); invQs = rs.random_sample((P, M, M))
+basis = np.linalg.qr(rs.standard_normal((W, P)))[0].T.copy()
+bank = g.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
+tt = rs.random_sample((64, D))
+ob = bank.predict(tt, want_var=True, want_deriv=True, project=True, project_deriv=True)
+models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(P)]
+fwd, mu_o, var_o, grad_o, dfull = orc.mv_predict_batch(models, basis, tt, want_deriv_full=True)
+par4 = {"fwd": orc.ref_err(ob["fwd"], fwd), "pc_mu": orc.ref_err(ob["mu"], mu_o), "pc_var": orc.ref_err(ob["var"], var_o),
+        "pc_grad": orc.ref_err(ob["deriv"], grad_o), "deriv_full": orc.ref_err(ob["deriv_full"], dfull)}
+t = torch.rand(N, D, dtype=torch.float64, device="cuda")
+s_pc, r = timeit(lambda: bank.predict(t, want_var=False, want_deriv=True))
+s_all, r = timeit(lambda: bank.predict(t, want_var=False, want_deriv=True, project=True))
+s_var, r = timeit(lambda: bank.predict(t, want_var=True, want_deriv=True))
+proj_s = s_all - s_pc
+out.append({"config": "4: MultivariateEmulator P=20 W=2101 M=250 D=10 FP64", "N": N,
+            "pc_mean_grad_points_per_s": N / s_pc, "pc_mean_var_grad_points_per_s": N / s_var,
+            "mean_grad_plus_backprojection_points_per_s": N / s_all,
+            "backprojection_only": {"seconds": proj_s, "output_GBps": N * W * 8 / proj_s / 1e9,
+                                    "fp64_tflops": N * 2 * P * W / proj_s / 1e12},
+            "parity": par4})
+del t, r
+
+# ---- config 5: bank of 64 per-band GPs with gradient and Hessian ---------------------------------------------
+M, D, E, N = 250, 10, 64, 100_000
+thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+bank = g.DeviceBank(inputs, thetas, invQts, invQs)
+tt = rs.random_sample((40, D))
+ob = bank.predict(tt, want_var=True, want_deriv=True, want_hess=True)
+models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(E)]
+mu_o, var_o, grad_o, hess_o = orc.bank_predict(models, tt, do_hess=True)
+par5 = {"mu": orc.ref_err(ob["mu"], mu_o), "var": orc.ref_err(ob["var"], var_o), "deriv": orc.ref_err(ob["deriv"], grad_o),
+        "hess": orc.ref_err(ob["hess"], hess_o)}
+t = torch.rand(N, D, dtype=torch.float64, device="cuda")
+s5, r = timeit(lambda: bank.predict(t, want_var=True, want_deriv=True, want_hess=True), reps=2, warm=1)
+Fh = F(M, D) + M * (D * D + 2 * D) + D
+out.append({"config": "5: bank of 64 GPs, shared test points, mu+var+grad+Hessian, M=250 D=10 FP64", "N": N,
+            "points_per_s": N / s5, "emulator_points_per_s": N * E / s5, "alg_tflops": N * E * Fh / s5 / 1e12,
+            "frac_of_dmma_peak": N * E * Fh / s5 / 1e12 / P64, "output_GBps": N * E * 112 * 8 / s5 / 1e9, "parity": par5})
+print(json.dumps({"fp64_peaks": peaks, "configs": out}, indent=1))
