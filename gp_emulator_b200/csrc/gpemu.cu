@@ -106,6 +106,7 @@ struct gpe_model {
 struct gpe_bank {
     int device = 0, E = 0, M = 0, D = 0, W = 0;
     std::vector<gpe_model*> models;
+    MeanBankEntry* d_entries = nullptr;  // per-emulator phase-A data for the one-launch bank mean / Hessian kernel
     double* d_basis = nullptr;   // basis pre-tiled as [ceil(E/4)][Wp][4], Wp = W rounded up to 256
     int Wp = 0;
 };
@@ -134,7 +135,7 @@ cudaError_t launch_full(int DP, int cfg, const FullParams& p, int grid, size_t s
     }
 }
 
-cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (DP) {
         case 2: return launch_mean_dp2(hess, p, grid, smem, st);
@@ -328,7 +329,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * 8);
         const size_t smem = do_hess ? m->mean.smem_hess : m->mean.smem;
-        CUDA_TRY(launch_mean(m->DP, do_hess, p, grid, smem, st));
+        CUDA_TRY(launch_mean(m->DP, do_hess, p, dim3(grid), smem, st));
     }
     return GPE_OK;
 }
@@ -836,6 +837,16 @@ int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const
         if (rc) { gpe_bank_destroy(b); return rc; }
         b->models.push_back(m);
     }
+    {
+        std::vector<MeanBankEntry> ent(E);
+        for (int e2 = 0; e2 < E; ++e2) {
+            ent[e2].xchunks = b->models[e2]->d_xchunks_mean;
+            memcpy(ent[e2].sqrt_w, b->models[e2]->sqrt_w, sizeof(ent[e2].sqrt_w));
+        }
+        cudaError_t e = cudaMalloc((void**)&b->d_entries, sizeof(MeanBankEntry) * E);
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_entries, ent.data(), sizeof(MeanBankEntry) * E, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "bank upload failed: %s", cudaGetErrorString(e)); }
+    }
     if (basis) {
         const int ks_e = (E + 3) / 4;
         const int ks_n = ks_e <= 3 ? 3 : (ks_e <= 5 ? 5 : 8);   // the k-step count of the kernel instantiation used
@@ -855,6 +866,7 @@ int gpe_bank_destroy(gpe_bank* b) {
     if (!b) return GPE_OK;
     for (gpe_model* m : b->models) gpe_model_destroy(m);
     if (b->d_basis) { cudaSetDevice(b->device); cudaFree(b->d_basis); }
+    if (b->d_entries) { cudaSetDevice(b->device); cudaFree(b->d_entries); }
     delete b;
     return GPE_OK;
 }
@@ -873,11 +885,35 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
     if (!mu && !var && !deriv && !hess) return fail(GPE_ERR_INVALID, "no output requested");
     CUDA_TRY(cudaSetDevice(b->device));
     const int64_t E = b->E, D = b->D;
-    for (int64_t e = 0; e < E; ++e) {
-        int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var ? var + e : nullptr,
-                                deriv ? deriv + e * D : nullptr, hess ? hess + e * D * D : nullptr, E, E, E * D,
-                                E * D * D, (cudaStream_t)stream);
-        if (rc) return rc;
+    const bool with_var = var != nullptr;
+    if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient)
+        for (int64_t e = 0; e < E; ++e) {
+            int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var + e, deriv ? deriv + e * D : nullptr,
+                                    nullptr, E, E, E * D, E * D * D, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    }
+    if (hess != nullptr || (!with_var && (mu != nullptr || deriv != nullptr))) {
+        // mean / gradient / Hessian of ALL emulators in one launch (blockIdx.y = emulator)
+        gpe_model* m0 = b->models[0];
+        const bool do_hess = hess != nullptr;
+        if (do_hess && m0->DP > 12) return fail(GPE_ERR_UNSUPPORTED, "Hessian output supports D <= 12 (got D = %d)", m0->D);
+        if (E > 65535) return fail(GPE_ERR_UNSUPPORTED, "bank size %d exceeds the grid limit", (int)E);
+        MeanParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing; p.N = N;
+        p.mu = with_var ? nullptr : mu;
+        p.deriv = with_var ? nullptr : deriv;
+        p.hess = hess;
+        p.ld_mu = E; p.ld_deriv = E * D; p.ld_hess = E * D * D;
+        p.eo_mu = 1; p.eo_deriv = D; p.eo_hess = D * D;
+        p.bank = b->d_entries;
+        p.M = m0->M; p.D = m0->D; p.JC = m0->mean.JC; p.nchunks = m0->mean.nchunks;
+        p.off_xc = m0->mean.off_xc; p.off_ts = m0->mean.off_ts; p.off_out = m0->mean.off_out;
+        const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
+        const int gx = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)m0->sms * 8 / E));
+        const size_t smem = do_hess ? m0->mean.smem_hess : m0->mean.smem;
+        CUDA_TRY(launch_mean(m0->DP, do_hess, p, dim3(gx, (unsigned)E), smem, (cudaStream_t)stream));
     }
     return GPE_OK;
 }

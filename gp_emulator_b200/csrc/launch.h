@@ -9,7 +9,7 @@ namespace gpe {
 
 #define GPE_DECL_DP(DPV)                                                                                          \
     cudaError_t launch_full_dp##DPV(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st);         \
-    cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st);
+    cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
 
 GPE_DECL_DP(2)
 GPE_DECL_DP(4)

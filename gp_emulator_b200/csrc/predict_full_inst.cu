@@ -35,7 +35,7 @@ cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int gr
     }
 }
 
-cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     if (hess) {
 #if GPE_DP <= 12
         auto kern = k_predict_mean<GPE_DP, true>;

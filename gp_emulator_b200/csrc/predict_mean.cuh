@@ -18,6 +18,12 @@ namespace gpe {
 constexpr int kMeanThreads = 128;
 constexpr int kMeanTN = 32;
 
+// One entry per emulator of a bank (same training inputs, own hyper-parameters): blockIdx.y selects it.
+struct MeanBankEntry {
+    const double* xchunks;
+    double sqrt_w[32];
+};
+
 struct MeanParams {
     const double* testing;  // (N, D)
     int64_t N;
@@ -29,6 +35,8 @@ struct MeanParams {
     int M, D, JC, nchunks;
     uint32_t off_xc, off_ts, off_out;  // smem byte offsets
     double sqrt_w[32];
+    const MeanBankEntry* bank;          // null: single GP.  Else gridDim.y emulators, outputs offset by e * eo_*
+    int64_t eo_mu, eo_deriv, eo_hess;   // element offsets per emulator into the point-major bank outputs
 };
 
 template <int DP, bool HESS>
@@ -44,7 +52,12 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M, DV = D + 1;
-    if (tid < 32) sqw_s[tid] = p.sqrt_w[tid];
+    const int em = blockIdx.y;
+    const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
+    if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
+    double* const o_mu = p.mu ? p.mu + em * p.eo_mu : nullptr;
+    double* const o_deriv = p.deriv ? p.deriv + em * p.eo_deriv : nullptr;
+    double* const o_hess = p.hess ? p.hess + em * p.eo_hess : nullptr;
 
     const int64_t ntiles = (p.N + TN - 1) / TN;
     bool x_resident = false;
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
         for (int c = 0; c < p.nchunks; ++c) {
             if (!x_resident) {
                 __syncthreads();
-                const double2* src = reinterpret_cast<const double2*>(p.xchunks + (size_t)c * chunk_doubles);
+                const double2* src = reinterpret_cast<const double2*>(xchunks + (size_t)c * chunk_doubles);
                 double2* dst = reinterpret_cast<double2*>(Xc);
                 for (int e = tid; e < chunk_doubles / 2; e += kMeanThreads) dst[e] = __ldg(src + e);
                 __syncthreads();
@@ -151,18 +164,18 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
             }
         }
         __syncthreads();
-        if (p.mu != nullptr && tid < npts) p.mu[(n0 + tid) * p.ld_mu] = outs[tid * DV];
-        if (p.deriv != nullptr) {
+        if (o_mu != nullptr && tid < npts) o_mu[(n0 + tid) * p.ld_mu] = outs[tid * DV];
+        if (o_deriv != nullptr) {
             for (int e = tid; e < npts * D; e += kMeanThreads) {
                 const int r = e / D, d = e - r * D;
-                p.deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
+                o_deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
             }
         }
-        if (HESS && p.hess != nullptr) {
+        if (HESS && o_hess != nullptr) {
             const int DD = D * D;
             for (int e = tid; e < npts * DD; e += kMeanThreads) {
                 const int r = e / DD;
-                p.hess[(n0 + r) * p.ld_hess + (e - r * DD)] = out_s[e];
+                o_hess[(n0 + r) * p.ld_hess + (e - r * DD)] = out_s[e];
             }
         }
     }

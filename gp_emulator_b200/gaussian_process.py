@@ -117,16 +117,31 @@ class GaussianProcess:
 
     # ------------------------------------------------------------------ device prediction path
     def _device_model(self):
-        """Device copy of the current numpy state, re-uploaded only when the arrays' contents change."""
+        """Device copy of the current numpy state, re-uploaded only when the arrays change.
+
+        The reference's benchmark REBINDS the attributes between calls (tests/benchmark.py:11-15), so the key
+        holds a CRC of the small arrays (inputs, theta, invQt) and, for the M x M ``invQ`` (500 KB at M = 250:
+        a full CRC would cost more than a small predict), its identity, address, shape and a CRC of every 61st
+        element.  After editing a few entries of ``invQ`` in place call ``invalidate_device()``.
+        """
         invQ = getattr(self, "invQ", None)
-        arrays = (self.inputs, self.theta, self.invQt) + (() if invQ is None else (invQ,))
-        key = (_digest(*arrays), invQ is not None, self.device)
+        key = [_digest(self.inputs, self.theta, self.invQt), self.device]
+        if invQ is not None:
+            q = np.asarray(invQ)
+            key += [id(invQ), q.__array_interface__["data"][0], q.shape, _digest(q.reshape(-1)[::61])]
+        key = tuple(key)
         if self._dev_model is None or key != self._dev_key:
             if self._dev_model is not None:
                 self._dev_model.close()
             self._dev_model = DeviceModel(self.inputs, self.theta, self.invQt, invQ, device=self.device)
             self._dev_key = key
         return self._dev_model
+
+    def invalidate_device(self):
+        """Drop the cached device copy (next predict re-uploads the model)."""
+        if self._dev_model is not None:
+            self._dev_model.close()
+        self._dev_model, self._dev_key = None, None
 
     def predict(self, testing, do_unc=True, do_deriv=True, is_gpu=True, precision=np.float64, threshold=2e5,
                 out=None, pinned=False):
