@@ -15,11 +15,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpemu.so")
 
 WANT_MU, WANT_VAR, WANT_DERIV, WANT_HESS, HOST_PTRS = 0x01, 0x02, 0x04, 0x08, 0x100
+OPT_SYMMETRIC_VARIANCE = 0x1
 MAX_TRAIN, MAX_INPUTS = 1024, 32
 
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
-    "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_destroy",
+    "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
     "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
     "gpe_bank_project", "gpe_measure_fp64_peaks", "gpe_launch_count",
 )
@@ -50,6 +51,8 @@ def load():
     lib.gpe_launch_count.restype = C.c_int64
     lib.gpe_model_create.restype = C.c_int
     lib.gpe_model_create.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_void_p)]
+    lib.gpe_model_create_ex.restype = C.c_int
+    lib.gpe_model_create_ex.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_uint, C.POINTER(C.c_void_p)]
     lib.gpe_model_destroy.restype = C.c_int
     lib.gpe_model_destroy.argtypes = [C.c_void_p]
     lib.gpe_predict.restype = C.c_int

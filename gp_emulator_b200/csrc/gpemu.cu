@@ -90,6 +90,7 @@ struct gpe_model {
     double b = 0;
     double sqrt_w[32];
     bool has_invQ = false;
+    bool symmetric = false;      // GPE_OPT_SYMMETRIC_VARIANCE: s_tiled holds the upper-triangular fold of invQ
     FullPlan full;
     MeanPlan mean;
     double* d_xchunks_full = nullptr;
@@ -299,7 +300,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
         p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
         p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk;
-        p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1;
+        p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1; p.symmetric = m->symmetric ? 1 : 0;
         if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1)); p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b; p.alias_x = f.alias_x;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
         p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;
@@ -672,6 +673,13 @@ int gpe_device_count(void) {
 
 int gpe_model_create(int device, int M, int D, const double* inputs, const double* expX, const double* invQt,
                      const double* invQ, gpe_model** out) {
+    unsigned options = 0;
+    if (const char* e = getenv("GPE_SYMMETRIC_VARIANCE")) options |= atoi(e) ? GPE_OPT_SYMMETRIC_VARIANCE : 0;
+    return gpe_model_create_ex(device, M, D, inputs, expX, invQt, invQ, options, out);
+}
+
+int gpe_model_create_ex(int device, int M, int D, const double* inputs, const double* expX, const double* invQt,
+                        const double* invQ, unsigned options, gpe_model** out) {
     if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (!inputs || !expX || !invQt) return fail(GPE_ERR_INVALID, "inputs, expX and invQt must be non-NULL");
@@ -686,6 +694,7 @@ int gpe_model_create(int device, int M, int D, const double* inputs, const doubl
     m->b = expX[D];
     for (int d = 0; d < 32; ++d) m->sqrt_w[d] = (d < D) ? std::sqrt(expX[d]) : 0.0;
     m->has_invQ = invQ != nullptr;
+    m->symmetric = (options & GPE_OPT_SYMMETRIC_VARIANCE) != 0;
     m->h_inputs.assign(inputs, inputs + (size_t)M * D);
     m->h_invQt.assign(invQt, invQt + M);
     if (invQ && M <= 256) m->h_invQ.assign(invQ, invQ + (size_t)M * M);
@@ -705,8 +714,12 @@ int gpe_model_create(int device, int M, int D, const double* inputs, const doubl
             // s_tiled[kb][j][c] = invQ[j][4 kb + c]
             std::vector<double> st((size_t)f.kblk * f.Mp * 4, 0.0);
             for (int j = 0; j < M; ++j)
-                for (int i = 0; i < M; ++i)
-                    st[((size_t)(i >> 2) * f.Mp + j) * 4 + (i & 3)] = invQ[(size_t)j * M + i];
+                for (int i = 0; i < M; ++i) {
+                    double v = invQ[(size_t)j * M + i];
+                    if (m->symmetric)   // k^T S k = k^T T k with T_ij = S_ij + S_ji (i < j), S_jj (i == j), 0 (i > j)
+                        v = (i < j) ? invQ[(size_t)j * M + i] + invQ[(size_t)i * M + j] : (i == j ? v : 0.0);
+                    st[((size_t)(i >> 2) * f.Mp + j) * 4 + (i & 3)] = v;
+                }
             cudaError_t e = cudaMalloc((void**)&m->d_xchunks_full, xc.size() * 8);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_xchunks_full, xc.data(), xc.size() * 8, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_stiled, st.size() * 8);

@@ -43,6 +43,7 @@ struct FullParams {
     int lag;        // refill distance behind the consumer (1 or 2, < nstage)
     int JC;         // training points per phase-A chunk (multiple of 4)
     int alias_x;    // 1: the chunk buffer overlays the B-operand ring (2-CTA/SM configuration)
+    int symmetric;  // 1: s_tiled holds the upper-triangular fold of invQ (opt-in, half the DMMAs)
     int nchunks;
     double b;       // signal variance exp(theta[D])
     // shared-memory carve-up (byte offsets)
@@ -91,7 +92,7 @@ struct RS {
     }
 };
 
-template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT>
+template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT, bool SYM>
 __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullParams p) {
     constexpr int NW = WR * WC;           // warps per CTA (power of two)
     constexpr int NTHR = NW * 32;
@@ -159,9 +160,23 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     uint32_t cpar = 0;
     auto issue = [&](int stage, int it_local) {  // k-blocks [KB * it_local, +KB) -> ring stage
         const int kb0 = it_local * KB;
-        const uint32_t bytes = (uint32_t)min(KB, p.kblk - kb0) * (uint32_t)Mp * 32u;
-        mbar_arrive_expect_tx(&bar_full[stage], bytes);
-        tma_bulk_g2s(Bst + (size_t)stage * p.stage_bytes, p.s_tiled + (size_t)kb0 * Mp * 4, bytes, &bar_full[stage]);
+        const int nkb = min(KB, p.kblk - kb0);
+        unsigned char* dst = Bst + (size_t)stage * p.stage_bytes;
+        if (!SYM) {
+            const uint32_t bytes = (uint32_t)nkb * (uint32_t)Mp * 32u;
+            mbar_arrive_expect_tx(&bar_full[stage], bytes);
+            tma_bulk_g2s(dst, p.s_tiled + (size_t)kb0 * Mp * 4, bytes, &bar_full[stage]);
+        } else {
+            // only columns >= 8 (kb / 2) of k-block kb are non-zero: copy that tail into place
+            uint32_t total = 0;
+            for (int kk = 0; kk < nkb; ++kk) total += (uint32_t)(Mp - 8 * ((kb0 + kk) >> 1)) * 32u;
+            mbar_arrive_expect_tx(&bar_full[stage], total);
+            for (int kk = 0; kk < nkb; ++kk) {
+                const int c0 = 8 * ((kb0 + kk) >> 1);
+                tma_bulk_g2s(dst + ((size_t)kk * Mp + c0) * 32, p.s_tiled + ((size_t)(kb0 + kk) * Mp + c0) * 4,
+                             (uint32_t)(Mp - c0) * 32u, &bar_full[stage]);
+            }
+        }
     };
     auto issue_burst = [&]() {
         int s = cs;
@@ -362,7 +377,9 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
             const double* a_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + (lane & 3);
-            const int b_off = (wcol * nt_act * 8 + (lane >> 2)) * 4 + (lane & 3);
+            // column tiles are dealt to the WC column-warps cyclically: warp wcol owns tiles wcol, wcol + WC, ...
+            // (keeps the warps balanced when SYM skips the tiles below the diagonal)
+            const int b_off = (wcol * 8 + (lane >> 2)) * 4 + (lane & 3);
 
             if (alias_x && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
             // KB k-blocks (4 values of the contraction index each) per ring stage, fully unrolled.  The A fragments
@@ -386,12 +403,29 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 for (int kk = 0; kk < KB; ++kk) {
                     if (KB == 1 || kb0 + kk < p.kblk) {
                         const double* bk = bs + kk * Mp * 4;
+                        // SYM: the B operand is the upper-triangular fold of invQ, column tile t is all zero for
+                        // k-block kb unless t >= kb / 2; this warp's tile j is t = wcol + WC j
+                        const int jmin = SYM ? ((((kb0 + kk) >> 1) - wcol + WC - 1) / WC) : 0;
+                        if (SYM) {
+                            // descending over this warp's tiles with a real (warp-uniform) exit: a predicated-off
+                            // DMMA still pays its issue stall, so predication alone saves nothing (measured)
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            if (FULLNT || j < nt_act) {
-                                const double bf = bk[j * 32];
+                            for (int j = NT - 1; j >= 0; --j) {
+                                if (j < jmin) break;
+                                if (FULLNT || j < nt_act) {
+                                    const double bf = bk[j * (WC * 32)];
 #pragma unroll
-                                for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
+                                    for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                if (FULLNT || j < nt_act) {
+                                    const double bf = bk[j * (WC * 32)];
+#pragma unroll
+                                    for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
+                                }
                             }
                         }
                     }
@@ -406,13 +440,13 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             double vs[MT];
 #pragma unroll
             for (int i = 0; i < MT; ++i) vs[i] = 0.0;
-            const double* k_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + wcol * nt_act * 8 + 2 * (lane & 3);
+            const double* k_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + wcol * 8 + 2 * (lane & 3);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 if (FULLNT || j < nt_act) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        const double2 kk = *reinterpret_cast<const double2*>(k_base + i * 8 * pitch + j * 8);
+                        const double2 kk = *reinterpret_cast<const double2*>(k_base + i * 8 * pitch + j * (WC * 8));
                         vs[i] = fma(acc[i][j][0], kk.x, vs[i]);
                         vs[i] = fma(acc[i][j][1], kk.y, vs[i]);
                     }

@@ -15,8 +15,10 @@ namespace gpe {
 
 template <int MT, int NT, int WR, int WC, int MINB, int KB>
 static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = (p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true>
-                                 : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false>;
+    auto kern = p.symmetric ? ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, true>
+                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, true>)
+                            : ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false>
+                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false>);
     // per function AND per device: set on every launch (microseconds) so multi-device processes stay correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -38,7 +38,9 @@ class DeviceModel:
     """One GP resident on one device.  Mirrors the state ``GaussianProcess.predict`` reads
     (reference gp_emulator/GaussianProcess.py:228-249): inputs (M, D), theta (D+2), invQ (M, M), invQt (M)."""
 
-    def __init__(self, inputs, theta, invQt, invQ=None, device=0):
+    def __init__(self, inputs, theta, invQt, invQ=None, device=0, symmetric_variance=False):
+        """``symmetric_variance=True`` opts into evaluating k^T invQ k through the upper-triangular fold of invQ
+        (exact identity for any invQ, half the tensor-core work, rounding differs at the 1e-16 level)."""
         inputs = f64c(inputs)
         if inputs.ndim != 2:
             raise ValueError("inputs must be (M, D)")
@@ -57,8 +59,10 @@ class DeviceModel:
         self.device = int(device)
         self.has_var = invQ is not None
         h = C.c_void_p()
-        check(_lib.load().gpe_model_create(self.device, self.M, self.D, addr(inputs), addr(expx), addr(invQt),
-                                           addr(invQ), C.byref(h)))
+        self.symmetric_variance = bool(symmetric_variance)
+        check(_lib.load().gpe_model_create_ex(self.device, self.M, self.D, addr(inputs), addr(expx), addr(invQt),
+                                              addr(invQ), _lib.OPT_SYMMETRIC_VARIANCE if symmetric_variance else 0,
+                                              C.byref(h)))
         self._h = h
         self._fin = weakref.finalize(self, _lib.load().gpe_model_destroy, h)
 

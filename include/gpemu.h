@@ -63,6 +63,16 @@ int gpe_model_create(int device, int M, int D, const double* inputs, const doubl
                      const double* invQt, const double* invQ, gpe_model** out);
 int gpe_model_destroy(gpe_model* m);
 
+/* Same, with options.  GPE_OPT_SYMMETRIC_VARIANCE: evaluate the quadratic form of the variance
+ * (`np.sum(a * np.dot(self.invQ, a), axis=0)`, gp_emulator/GaussianProcess.py:240) as k^T T k with T the
+ * upper-triangular fold of invQ (T_ij = invQ_ij + invQ_ji for i < j, invQ_jj on the diagonal, 0 below).  The
+ * identity is exact for ANY invQ, symmetric or not; only the rounding differs (by ~1e-16 of sum |terms|), and the
+ * tensor-core work is halved.  Off by default: the default path evaluates the dense formula as numpy does.
+ * gpe_model_create() honours the environment variable GPE_SYMMETRIC_VARIANCE=1 as the same opt-in. */
+#define GPE_OPT_SYMMETRIC_VARIANCE 0x1u
+int gpe_model_create_ex(int device, int M, int D, const double* inputs, const double* expX,
+                        const double* invQt, const double* invQ, unsigned options, gpe_model** out);
+
 /* Predict N test points: the whole of GaussianProcess.cpu_predict / gpu_predict
  * (gp_emulator/GaussianProcess.py:211-251, :273-323) and gpuPredict::predict
  * (gp_emulator/gpu/predict.cu:168-176) in one fused pass.

@@ -308,3 +308,25 @@ def test_full_size_properties_linearity_and_kernel_bound(gpemu):
     assert orc.ref_err(o1["mu"][ii].cpu().numpy(), mu) < TOL
     assert orc.ref_err(o1["var"][ii].cpu().numpy(), var) < TOL
     assert orc.ref_err(o1["deriv"][ii].cpu().numpy(), deriv) < TOL
+
+
+@pytest.mark.parametrize("M,D,N", [(250, 10, 1500), (1000, 10, 100), (300, 6, 200), (37, 3, 70), (200, 8, 130)])
+def test_symmetric_variance_option(gpemu, M, D, N):
+    """Opt-in k^T T k (upper-triangular fold of invQ): exact identity for ANY invQ, incl. the benchmark's
+    non-symmetric random matrix; same 1e-10 bar, mean / gradient bit-identical to the default path."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M)
+    m0 = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    m1 = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=True)
+    a, b = m0.predict(testing), m1.predict(testing)
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    assert orc.ref_err(b["var"], var) < TOL
+    assert np.array_equal(a["mu"], b["mu"]) and np.array_equal(a["deriv"], b["deriv"])
+
+
+def test_symmetric_variance_on_trained_model(gpemu):
+    g = golden("T")
+    m1 = gpemu.DeviceModel(g["inputs"], g["theta"], g["invQt"], g["invQ"], symmetric_variance=True)
+    out = m1.predict(g["testing"])
+    assert orc.var_cond_err(out["var"], g["var"], g["inputs"], g["theta"], g["invQ"], g["testing"]) < TOL
+    _, lvar, _ = orc.predict_longdouble(g["inputs"], g["theta"], g["invQ"], g["invQt"], g["testing"])
+    assert np.max(np.abs(out["var"] - lvar)) <= 2.0 * np.max(np.abs(g["var"] - lvar)) + 1e-18

@@ -13,7 +13,7 @@ from oracle import gp_oracle as orc
 
 M = int(os.environ.get("M", 250)); D = int(os.environ.get("D", 10)); N = int(float(os.environ.get("N", 4e6)))
 inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, 2000, seed=0)
-m = g.DeviceModel(inputs, theta, invQt, invQ)
+m = g.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=bool(int(os.environ.get("SYM", "0"))))
 out = m.predict(testing)
 mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
 errs = {k: orc.ref_err(out[k], r) for k, r in (("mu", mu), ("var", var), ("deriv", deriv))}

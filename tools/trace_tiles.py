@@ -7,7 +7,7 @@ from gp_emulator_b200 import _lib
 from oracle import gp_oracle as orc
 M = int(os.environ.get("M", 250))
 inputs, theta, invQ, invQt, _ = orc.make_S_model(M, 10, 1, seed=0)
-m = g.DeviceModel(inputs, theta, invQt, invQ)
+m = g.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=bool(int(os.environ.get("SYM", "0"))))
 t = torch.rand(int(float(os.environ.get("N", 2e6))), 10, dtype=torch.float64, device="cuda")
 m.predict(t); torch.cuda.synchronize()
 buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
