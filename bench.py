@@ -256,6 +256,33 @@ def main():
     if world > 1:
         e2e_s = sharding.max_over_ranks(e2e_s, device=dev)
 
+    # ---- opt-in variants of the same workload, reported beside the headline (short, outside every timed region) --
+    variants = None
+    if rank == 0:
+        def _rate(fn, n_pts, reps=3):
+            fn(); fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return n_pts * reps / (a.elapsed_time(b) * 1e-3)
+        nv = min(N, 20_000_000)
+        tv = testing[:nv]
+        sym = gpe.DeviceModel(model["inputs"], model["theta"], model["invQt"], model["invQ"], device=local_rank,
+                              symmetric_variance=True)
+        t32 = tv.to(torch.float32)
+        variants = {
+            "points": nv,
+            "fp64_symmetric_variance_points_per_s": _rate(lambda: sym.predict(tv), nv),
+            "fp32_tf32_tcgen05_points_per_s": _rate(lambda: dm.predict_f32(t32), nv),
+            "fp64_mean_gradient_only_points_per_s": _rate(lambda: dm.predict(tv, want_var=False), nv),
+            "note": "same model and test points; symmetric = opt-in upper-triangular fold of invQ (exact identity, "
+                    "half the DMMAs); tf32 = single precision with the variance contraction on tcgen05/TMEM",
+        }
+        del sym, t32, tv
     if rank == 0:
         from oracle import gp_oracle as orc
         mu_o, var_o, _ = orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], t_head)
@@ -292,6 +319,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "parity_vs_oracle": parity,
+            "variants": variants,
         }
         if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
             line["cpu_baseline"] = cpu_baseline(model, int(args.cpu_points))

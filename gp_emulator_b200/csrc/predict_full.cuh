@@ -421,11 +421,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                         } else {
 #pragma unroll
                             for (int j = 0; j < NT; ++j) {
-                                if (FULLNT || j < nt_act) {
-                                    const double bf = bk[j * (WC * 32)];
+                                if (!FULLNT && j >= nt_act) break;   // real exit: predicated-off DMMAs are not free
+                                const double bf = bk[j * (WC * 32)];
 #pragma unroll
-                                    for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
-                                }
+                                for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
                             }
                         }
                     }
