@@ -96,9 +96,11 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
             }
             const int jn = min(p.JC, M - c * p.JC);
             const double* al = Xc + p.JC * DP;
-            for (int jl = g_low; jl < jn; jl += 4) {
+            // Software pipeline over this lane's training points: the distance + exp chain of point i + 1 (a long
+            // dependent FP64 sequence) is issued in the same iteration as the independent accumulate FMAs of point i
+            // (D for the gradient, D (D + 1) / 2 for the Hessian), so the FP64 pipe always has ready work.
+            auto stage1 = [&](int jl, double (&u)[DP]) -> double {
                 const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
-                double u[DP];
                 double r2 = 0.0;
 #pragma unroll
                 for (int d = 0; d < DP; d += 2) {
@@ -108,23 +110,39 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
                     r2 = fma(u[d], u[d], r2);
                     r2 = fma(u[d + 1], u[d + 1], r2);
                 }
-                const double cj = exp_neg(-0.5 * r2) * al[jl];
-                mu += cj;
-                if (HESS) {
-                    int t = 0;
-#pragma unroll
-                    for (int d = 0; d < DP; ++d) {
-                        const double cu = cj * u[d];
-                        g[d] += cu;
-#pragma unroll
-                        for (int e = d; e < DP; ++e) {
-                            T[t] = fma(cu, u[e], T[t]);
-                            ++t;
-                        }
-                    }
-                } else {
+                return exp_neg(-0.5 * r2) * al[jl];
+            };
+            if (!HESS) {
+                // mean + gradient only: few registers -> many resident warps hide the chain; no pipelining needed
+                for (int jl = g_low; jl < jn; jl += 4) {
+                    double u[DP];
+                    const double cj = stage1(jl, u);
+                    mu += cj;
 #pragma unroll
                     for (int d = 0; d < DP; ++d) g[d] = fma(cj, u[d], g[d]);
+                }
+            } else if (g_low < jn) {
+                double uc[DP], un[DP];
+                double cc = stage1(g_low, uc);
+                for (int jl = g_low; jl < jn; jl += 4) {
+                    const double cn = stage1(min(jl + 4, jn - 1), un);   // next point (clamped; unused after the last)
+                    mu += cc;
+                    {
+                        int t = 0;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) {
+                            const double cu = cc * uc[d];
+                            g[d] += cu;
+#pragma unroll
+                            for (int e = d; e < DP; ++e) {
+                                T[t] = fma(cu, uc[e], T[t]);
+                                ++t;
+                            }
+                        }
+                    }
+                    cc = cn;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) uc[d] = un[d];
                 }
             }
         }
