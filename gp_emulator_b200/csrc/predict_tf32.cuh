@@ -41,6 +41,32 @@ struct Tf32Params {
     float sqrt_w[32];
 };
 
+// Packed FP32 pairs (Blackwell FFMA2 / FADD2: two FP32 operations per issue slot) -- phase A is issue bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, rel. error 2^-22, flushes denormals
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -209,42 +235,47 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
             const int64_t n0 = tile * TN;
             const int npts = (int)min((int64_t)TN, p.N - n0);
             const int64_t nrow = n0 + min(row, npts - 1);
-            float ts[DP];
+            f32x2 ts2[DP / 2];
 #pragma unroll
-            for (int d = 0; d < DP; ++d) ts[d] = (d < D) ? __ldg(p.testing + nrow * D + d) * p.sqrt_w[d] : 0.f;
+            for (int q = 0; q < DP / 2; ++q) {
+                const int d = 2 * q;
+                const float a = (d < D) ? __ldg(p.testing + nrow * D + d) * p.sqrt_w[d] : 0.f;
+                const float b2 = (d + 1 < D) ? __ldg(p.testing + nrow * D + d + 1) * p.sqrt_w[d + 1] : 0.f;
+                ts2[q] = pack2(a, b2);
+            }
 
             float mu = 0.f;
-            float g[DP];
+            f32x2 g2[DP / 2];
 #pragma unroll
-            for (int d = 0; d < DP; ++d) g[d] = 0.f;
+            for (int q = 0; q < DP / 2; ++q) g2[q] = 0ull;
 
-            // phase A: chunk c = 4 consecutive training points = one 16-byte unit of the row's 128-byte swizzle atom
+            // phase A: chunk c = 4 consecutive training points = one 16-byte unit of the row's 128-byte swizzle atom.
+            // All per-dimension arithmetic runs on packed pairs of dimensions (FADD2 / FFMA2).
             for (int c = h; c < nchunk; c += 2) {
                 float k4[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = 4 * c + q;
-                    const float4* xr = reinterpret_cast<const float4*>(Xs + j * DP);
-                    float u[DP];
-                    float r2 = 0.f;
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int j = 4 * c + q4;
+                    const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(Xs + j * DP);   // float4 = 2 packed pairs
+                    f32x2 u2[DP / 2];
+                    f32x2 racc = 0ull;
 #pragma unroll
                     for (int d4 = 0; d4 < DP / 4; ++d4) {
-                        const float4 x = xr[d4];
-                        u[4 * d4 + 0] = x.x - ts[4 * d4 + 0];
-                        u[4 * d4 + 1] = x.y - ts[4 * d4 + 1];
-                        u[4 * d4 + 2] = x.z - ts[4 * d4 + 2];
-                        u[4 * d4 + 3] = x.w - ts[4 * d4 + 3];
-                        r2 = fmaf(u[4 * d4 + 0], u[4 * d4 + 0], r2);
-                        r2 = fmaf(u[4 * d4 + 1], u[4 * d4 + 1], r2);
-                        r2 = fmaf(u[4 * d4 + 2], u[4 * d4 + 2], r2);
-                        r2 = fmaf(u[4 * d4 + 3], u[4 * d4 + 3], r2);
+                        const ulonglong2 x = xr[d4];
+                        u2[2 * d4] = sub2(x.x, ts2[2 * d4]);
+                        u2[2 * d4 + 1] = sub2(x.y, ts2[2 * d4 + 1]);
+                        racc = fma2(u2[2 * d4], u2[2 * d4], racc);
+                        racc = fma2(u2[2 * d4 + 1], u2[2 * d4 + 1], racc);
                     }
-                    const float k = exp2f(r2 * -0.72134752044448170368f);   // exp(-r2 / 2) = 2^(-r2 log2(e) / 2)
-                    k4[q] = k;
+                    float r_lo, r_hi;
+                    unpack2(racc, r_lo, r_hi);
+                    const float k = ex2_approx((r_lo + r_hi) * -0.72134752044448170368f);   // exp(-r2/2) = 2^(-r2 log2(e)/2)
+                    k4[q4] = k;
                     const float cj = k * al[j];
                     mu += cj;
+                    const f32x2 cj2 = pack2(cj, cj);
 #pragma unroll
-                    for (int d = 0; d < DP; ++d) g[d] = fmaf(cj, u[d], g[d]);
+                    for (int q = 0; q < DP / 2; ++q) g2[q] = fma2(cj2, u2[q], g2[q]);
                 }
                 if (want_var) {
                     const int slab = c >> 3, cc = c & 7;
@@ -260,6 +291,9 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
 
             // combine the two halves of every row (half 1 parks its sums in smem, half 0 adds its own), then write
             {
+                float g[DP];
+#pragma unroll
+                for (int q = 0; q < DP / 2; ++q) unpack2(g2[q], g[2 * q], g[2 * q + 1]);
                 float* dst = outs + row * DV;
                 if (h == 1) {
                     dst[0] = mu;

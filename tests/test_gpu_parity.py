@@ -330,3 +330,30 @@ def test_symmetric_variance_on_trained_model(gpemu):
     assert orc.var_cond_err(out["var"], g["var"], g["inputs"], g["theta"], g["invQ"], g["testing"]) < TOL
     _, lvar, _ = orc.predict_longdouble(g["inputs"], g["theta"], g["invQ"], g["invQt"], g["testing"])
     assert np.max(np.abs(out["var"] - lvar)) <= 2.0 * np.max(np.abs(g["var"] - lvar)) + 1e-18
+
+
+def test_documented_limits_raise_cleanly(gpemu):
+    """M > 1024 (variance) and D > 12 (Hessian) are reported as GPE_ERR_UNSUPPORTED, never a wrong answer."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(1100, 3, 20, seed=1)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    with pytest.raises(gpemu.GpemuError, match="M <= 1024"):
+        m.predict(testing)
+    o = m.predict(testing, want_var=False)               # mean + gradient have no M limit
+    mu, _, deriv = orc.predict(inputs, theta, invQ, invQt, testing, do_unc=False)
+    assert orc.ref_err(o["mu"], mu) < TOL and orc.ref_err(o["deriv"], deriv) < TOL
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(50, 13, 20, seed=1)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    with pytest.raises(gpemu.GpemuError, match="D <= 12"):
+        m.predict(testing, want_hess=True)
+
+
+def test_inplace_edit_needs_invalidate(gpemu):
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(64, 4, 50, seed=2)
+    gp = gpemu.GaussianProcess(inputs, [])
+    gp.theta, gp.invQ, gp.invQt = theta, invQ.copy(), invQt
+    _, v0, _ = gp.predict(testing)
+    gp.invQ[1, 2] += 0.5                                  # in-place edit of one entry
+    gp.invalidate_device()
+    _, v1, _ = gp.predict(testing)
+    _, var, _ = orc.predict(inputs, theta, gp.invQ, invQt, testing)
+    assert orc.ref_err(v1, var) < TOL and not np.array_equal(v0, v1)
