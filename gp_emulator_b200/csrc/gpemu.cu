@@ -62,6 +62,8 @@ struct FullPlan {
 struct Tf32Plan {
     bool valid = false;
     int DP = 0, Mp = 0, nslab = 0;
+    bool big = false;      // 256 < M <= 1024: column passes + A ring (predict_tf32_big.cuh)
+    int pass_cols = 0;
     uint32_t off_bar = 0, off_tmem = 0, off_a = 0, off_b = 0, off_x = 0, off_out = 0, off_vred = 0, bstage_bytes = 0, smem = 0;
 };
 
@@ -572,24 +574,30 @@ uint32_t host_tf32_rna(float x) {   // round-to-nearest (ties away) to 10 mantis
 int ensure_tf32(gpe_model* m) {
     if (m->tf.valid) return GPE_OK;
     const int M = m->M, D = m->D;
-    if (M > 256) return fail(GPE_ERR_UNSUPPORTED, "the single-precision tensor-core path supports M <= 256 (got %d)", M);
+    if (M > 1024) return fail(GPE_ERR_UNSUPPORTED, "the single-precision tensor-core path supports M <= 1024 (got %d)", M);
     Tf32Plan t;
     t.DP = -1;
     for (int dp : kTfDpList) if (dp >= D) { t.DP = dp; break; }
     if (t.DP < 0) return fail(GPE_ERR_UNSUPPORTED, "D = %d not supported by the single-precision path", D);
     t.Mp = (M + 63) / 64 * 64;
     t.nslab = (M + 31) / 32;
-    t.bstage_bytes = (uint32_t)t.Mp * 128u;
-    uint32_t off = 0;
-    t.off_bar = off; off += 128;
-    t.off_tmem = off; off += 16;
-    off = align_up(off, 1024);
-    t.off_a = off; off += (uint32_t)t.nslab * kTfTN * 128u;
-    t.off_b = off; off += 2 * t.bstage_bytes;
-    t.off_x = off; off += align_up((uint32_t)t.Mp * (t.DP + 1) * 4u, 16);
-    t.off_out = off; off += align_up((uint32_t)kTfTN * (D + 1) * 4u, 16);
-    t.off_vred = off; off += 2u * kTfTN * 4u;
-    t.smem = off;
+    t.big = t.Mp > 256;
+    auto layout = [&](int pass_cols) {
+        t.pass_cols = pass_cols;
+        t.bstage_bytes = (uint32_t)(t.big ? pass_cols : t.Mp) * 128u;
+        uint32_t off = 0;
+        t.off_bar = off; off += 128;
+        t.off_tmem = off; off += 16;
+        off = align_up(off, 1024);
+        t.off_a = off; off += (uint32_t)(t.big ? 2 : t.nslab) * kTfTN * 128u;   // A ring (big) or the whole K* tile
+        t.off_b = off; off += 2 * t.bstage_bytes;
+        t.off_x = off; off += align_up((uint32_t)t.Mp * (t.DP + 1) * 4u, 16);
+        t.off_out = off; off += align_up((uint32_t)kTfTN * (D + 1) * 4u, 16);
+        t.off_vred = off; off += 2u * kTfTN * 4u;
+        t.smem = off;
+    };
+    layout(512);
+    if (t.big && t.smem > kSmemMax) layout(256);
     if (t.smem > kSmemMax) return fail(GPE_ERR_UNSUPPORTED, "single-precision path needs %u bytes of shared memory", t.smem);
     const float b = (float)m->b;
     std::vector<float> xa((size_t)t.Mp * (t.DP + 1), 0.f);
@@ -615,6 +623,7 @@ int ensure_tf32(gpe_model* m) {
     }
     t.valid = true;
     m->tf = t;
+    std::vector<double>().swap(m->h_invQ);   // the FP64 host copy was only needed for this packing
     return GPE_OK;
 }
 
@@ -625,6 +634,22 @@ int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu,
     if (rc) return rc;
     if (var && !m->d_bslabs) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
     const Tf32Plan& t = m->tf;
+    const int64_t ntiles = (N + kTfTN - 1) / kTfTN;
+    const int grid = (int)std::min<int64_t>(ntiles, m->sms);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (t.big) {
+        Tf32BigParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
+        p.ld_mu = 1; p.ld_var = 1; p.ld_deriv = m->D;
+        p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs;
+        p.M = m->M; p.D = m->D; p.Mp = t.Mp; p.nslab = t.nslab; p.pass_cols = t.pass_cols; p.b = (float)m->b;
+        p.off_bar = t.off_bar; p.off_a = t.off_a; p.off_b = t.off_b; p.off_x = t.off_x; p.off_out = t.off_out;
+        p.off_vred = t.off_vred; p.off_tmem = t.off_tmem; p.bstage_bytes = t.bstage_bytes;
+        for (int d = 0; d < 32; ++d) p.sqrt_w[d] = (float)m->sqrt_w[d];
+        CUDA_TRY(launch_tf32_big(t.DP, p, grid, t.smem, st));
+        return GPE_OK;
+    }
     Tf32Params p;
     memset(&p, 0, sizeof(p));
     p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
@@ -634,9 +659,6 @@ int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu,
     p.off_bar = t.off_bar; p.off_a = t.off_a; p.off_b = t.off_b; p.off_x = t.off_x; p.off_out = t.off_out;
     p.off_vred = t.off_vred; p.off_tmem = t.off_tmem; p.bstage_bytes = t.bstage_bytes;
     for (int d = 0; d < 32; ++d) p.sqrt_w[d] = (float)m->sqrt_w[d];
-    const int64_t ntiles = (N + kTfTN - 1) / kTfTN;
-    const int grid = (int)std::min<int64_t>(ntiles, m->sms);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(launch_tf32(t.DP, p, grid, t.smem, st));
     return GPE_OK;
 }
@@ -697,7 +719,7 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
     m->symmetric = (options & GPE_OPT_SYMMETRIC_VARIANCE) != 0;
     m->h_inputs.assign(inputs, inputs + (size_t)M * D);
     m->h_invQt.assign(invQt, invQt + M);
-    if (invQ && M <= 256) m->h_invQ.assign(invQ, invQ + (size_t)M * M);
+    if (invQ && M <= 1024) m->h_invQ.assign(invQ, invQ + (size_t)M * M);
     for (int d = 0; d <= D; ++d) m->h_expx[d] = expX[d];
     m->mean = plan_mean(M, D, m->DP);
     {

@@ -4,6 +4,7 @@
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
 #include "predict_tf32.cuh"
+#include "predict_tf32_big.cuh"
 
 namespace gpe {
 
@@ -23,6 +24,7 @@ GPE_DECL_DP(32)
 #undef GPE_DECL_DP
 
 cudaError_t launch_tf32(int DP, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_tf32_big(int DP, const Tf32BigParams& p, int grid, size_t smem, cudaStream_t st);
 static const int kTfDpList[] = {4, 8, 12, 16, 32};
 
 // padded input dimensions that have compiled kernels, ascending

@@ -150,7 +150,7 @@ class GaussianProcess:
         Returns ``(mu, var, deriv)``; ``(mu, deriv)`` if ``do_unc`` is False (as the reference's CPU branch,
         :248-251); ``(mu, var)`` / ``mu`` when ``do_deriv`` is False (the upstream-style signature).
         ``deriv`` is (N, D).  Computation is FP64 on the GPU unless ``precision=np.float32`` (or a float32 CUDA
-        tensor) is given and M <= 256: then the single-precision tensor-core path runs (for larger M the FP64
+        tensor) is given and M <= 1024: then the single-precision tensor-core path runs (for larger M the FP64
         results are cast).
         ``testing`` may also be a float64 torch CUDA tensor, in which case torch tensors are returned.
         ``out`` (dict with any of "mu", "var", "deriv") supplies preallocated result buffers, ``pinned=True``
@@ -163,7 +163,7 @@ class GaussianProcess:
         dm = self._device_model()
         is_t = hasattr(testing, "dim")
         f32_in = (is_t and str(testing.dtype) == "torch.float32") or (not is_t and precision is np.float32)
-        if f32_in and dm.M <= 256 and out is None:
+        if f32_in and dm.M <= 1024 and out is None:
             # the reference's FP32 GPU build (precision=np.float32, GaussianProcess.py:289-316): single precision
             # end to end, variance contraction on the tensor cores (tcgen05, TF32 inputs)
             o = dm.predict_f32(testing, want_var=do_unc, want_deriv=do_deriv)

@@ -88,8 +88,9 @@ int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, doub
 /* Single-precision variant on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in TMEM):
  * what the reference's FP32 build of gpuPredict computes (`real` = float, gp_emulator/gpu/gpu_predict.h:20-34;
  * Python side precision=np.float32, gp_emulator/GaussianProcess.py:289-316).  Same handle, float32 I/O
- * (testing (N, D), mu (N), var (N), deriv (N, D)), M <= 256, no Hessian.  K*, mean and gradient are FP32; the
- * variance contraction uses TF32 inputs with FP32 accumulation (relative error ~1e-4 of max|var|). */
+ * (testing (N, D), mu (N), var (N), deriv (N, D)), M <= 1024, no Hessian.  K*, mean and gradient are FP32; the
+ * variance contraction uses TF32 inputs with FP32 accumulation (relative error ~1e-4 of max|var|).
+ * M <= 256 keeps the whole K* tile on chip; 256 < M <= 1024 runs column passes over the 512 TMEM columns. */
 int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, float* var, float* deriv,
                     unsigned flags, void* stream);
 

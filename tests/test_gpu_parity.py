@@ -200,11 +200,27 @@ def test_single_precision_tensor_core_path(gpemu, M, D, N):
         assert np.array_equal(od[k].cpu().numpy(), o[k])
 
 
+@pytest.mark.parametrize("M,D,N", [(300, 5, 200), (512, 10, 129), (513, 4, 64), (1000, 10, 300), (1024, 12, 100),
+                                   (700, 16, 50)])
+def test_single_precision_large_m(gpemu, M, D, N):
+    """256 < M <= 1024: column passes over 512 TMEM columns, K* slabs through a 2-deep A ring, epilogue with K*
+    recomputed (predict_tf32_big.cuh).  Same bars as the small-M kernel."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    t32 = testing.astype(np.float32)
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, t32.astype(np.float64))
+    o = m.predict_f32(t32)
+    assert orc.ref_err(o["mu"], mu) < 1e-5 and orc.ref_err(o["deriv"], deriv) < 1e-5
+    assert orc.ref_err(o["var"], var) < 5e-4
+    o2 = m.predict_f32(t32, want_var=False)
+    assert np.array_equal(o2["mu"], o["mu"]) and np.array_equal(o2["deriv"], o["deriv"])
+
+
 def test_single_precision_limits_and_dropin_routing(gpemu):
-    inputs, theta, invQ, invQt, testing = orc.make_S_model(300, 5, 50, seed=2)
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(1100, 5, 50, seed=2)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     with pytest.raises(gpemu.GpemuError):
-        m.predict_f32(testing.astype(np.float32))          # M > 256: not served by the tensor-core path
+        m.predict_f32(testing.astype(np.float32))          # M > 1024: not served by the tensor-core path
     inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 5000, seed=0)
     gp = gpemu.GaussianProcess(inputs, [])
     gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt

@@ -38,8 +38,16 @@ s, _ = timeit(lambda: m.predict(t))
 out.append({"config": "3: M=1000 D=10 FP64 mu+var+grad", "N": N, "points_per_s": N / s,
             "alg_tflops": N * F(M, D) / s / 1e12, "frac_of_dmma_peak": N * F(M, D) / s / 1e12 / P64,
             "parity": {"mu": orc.ref_err(o["mu"], mu), "var": orc.ref_err(o["var"], var), "deriv": orc.ref_err(o["deriv"], deriv)},
-            "note": "single-precision tensor-core variant serves M <= 256 only (see config 1T below)"})
-del t
+            })
+t32d = torch.rand(N, D, dtype=torch.float32, device="cuda")
+o32 = m.predict_f32(testing.astype(np.float32))
+mu32, var32, deriv32 = orc.predict(inputs, theta, invQ, invQt, testing.astype(np.float32).astype(np.float64))
+s32, _ = timeit(lambda: m.predict_f32(t32d))
+out.append({"config": "3T: M=1000 D=10 FP32/TF32 (tcgen05 + TMEM, column passes) mu+var+grad", "N": N,
+            "points_per_s": N / s32, "tf32_tflops": N * 2 * 1024 * 1024 / s32 / 1e12,
+            "parity_vs_fp64_oracle": {"mu": orc.ref_err(o32["mu"], mu32), "var": orc.ref_err(o32["var"], var32),
+                                      "deriv": orc.ref_err(o32["deriv"], deriv32)}})
+del t, t32d
 
 # ---- config 1T: headline shape in single precision on tcgen05 -----------------------------------------------
 M, D, N = 250, 10, 40_000_000
