@@ -98,9 +98,10 @@ struct gpe_model {
     double* d_xchunks_full = nullptr;
     double* d_stiled = nullptr;
     double* d_xchunks_mean = nullptr;
-    Tf32Plan tf;                 // single-precision tcgen05 path (M <= 256), built lazily by gpe_predict_f32
+    Tf32Plan tf, tfx;            // single-precision tcgen05 paths: fast (1 x TF32) and precise (3 x TF32); lazy
     float* d_xa_f32 = nullptr;
     uint32_t* d_bslabs = nullptr;
+    uint32_t* d_bslabs_lo = nullptr;
     std::vector<double> h_inputs, h_invQt, h_invQ;  // host copy of the model for the lazy FP32 packing
     double h_expx[33];
     Slot slots[2];
@@ -575,65 +576,77 @@ int ensure_tf32(gpe_model* m) {
     if (m->tf.valid) return GPE_OK;
     const int M = m->M, D = m->D;
     if (M > 1024) return fail(GPE_ERR_UNSUPPORTED, "the single-precision tensor-core path supports M <= 1024 (got %d)", M);
-    Tf32Plan t;
-    t.DP = -1;
-    for (int dp : kTfDpList) if (dp >= D) { t.DP = dp; break; }
-    if (t.DP < 0) return fail(GPE_ERR_UNSUPPORTED, "D = %d not supported by the single-precision path", D);
-    t.Mp = (M + 63) / 64 * 64;
-    t.nslab = (M + 31) / 32;
-    t.big = t.Mp > 256;
-    auto layout = [&](int pass_cols) {
-        t.pass_cols = pass_cols;
-        t.bstage_bytes = (uint32_t)(t.big ? pass_cols : t.Mp) * 128u;
+    int DP = -1;
+    for (int dp : kTfDpList) if (dp >= D) { DP = dp; break; }
+    if (DP < 0) return fail(GPE_ERR_UNSUPPORTED, "D = %d not supported by the single-precision path", D);
+    const int Mp = (M + 63) / 64 * 64, nslab = (M + 31) / 32;
+    // ring = true: K* slabs through a 2-deep A ring, column passes (predict_tf32_big.cuh); x3: hi + lo operands
+    auto make_plan = [&](bool ring, bool x3, int pass_cols) {
+        Tf32Plan t;
+        t.DP = DP; t.Mp = Mp; t.nslab = nslab; t.big = ring; t.pass_cols = std::min(pass_cols, Mp);
+        t.bstage_bytes = (uint32_t)(ring ? t.pass_cols : Mp) * 128u;
         uint32_t off = 0;
         t.off_bar = off; off += 128;
         t.off_tmem = off; off += 16;
         off = align_up(off, 1024);
-        t.off_a = off; off += (uint32_t)(t.big ? 2 : t.nslab) * kTfTN * 128u;   // A ring (big) or the whole K* tile
+        t.off_a = off; off += (uint32_t)(ring ? (x3 ? 4 : 2) : nslab) * kTfTN * 128u;   // A ring or the whole K* tile
         t.off_b = off; off += 2 * t.bstage_bytes;
-        t.off_x = off; off += align_up((uint32_t)t.Mp * (t.DP + 1) * 4u, 16);
+        t.off_x = off; off += align_up((uint32_t)Mp * (DP + 1) * 4u, 16);
         t.off_out = off; off += align_up((uint32_t)kTfTN * (D + 1) * 4u, 16);
         t.off_vred = off; off += 2u * kTfTN * 4u;
         t.smem = off;
+        t.valid = t.smem <= kSmemMax;
+        return t;
     };
-    layout(512);
-    if (t.big && t.smem > kSmemMax) layout(256);
-    if (t.smem > kSmemMax) return fail(GPE_ERR_UNSUPPORTED, "single-precision path needs %u bytes of shared memory", t.smem);
-    const float b = (float)m->b;
-    std::vector<float> xa((size_t)t.Mp * (t.DP + 1), 0.f);
+    Tf32Plan fast = (Mp <= 256) ? make_plan(false, false, Mp) : make_plan(true, false, 512);
+    if (!fast.valid && Mp > 256) fast = make_plan(true, false, 256);
+    Tf32Plan prec = make_plan(true, true, 512);
+    for (int pc : {256, 128, 64}) if (!prec.valid) prec = make_plan(true, true, pc);
+    if (!fast.valid || !prec.valid)
+        return fail(GPE_ERR_UNSUPPORTED, "single-precision path does not fit shared memory for M = %d, D = %d", M, D);
+
+    std::vector<float> xa((size_t)Mp * (DP + 1), 0.f);
     for (int j = 0; j < M; ++j) {
-        for (int d = 0; d < D; ++d) xa[(size_t)j * t.DP + d] = (float)(m->sqrt_w[d] * m->h_inputs[(size_t)j * D + d]);
-        xa[(size_t)t.Mp * t.DP + j] = (float)(m->b * m->h_invQt[j]);
+        for (int d = 0; d < D; ++d) xa[(size_t)j * DP + d] = (float)(m->sqrt_w[d] * m->h_inputs[(size_t)j * D + d]);
+        xa[(size_t)Mp * DP + j] = (float)(m->b * m->h_invQt[j]);
     }
-    (void)b;
     CUDA_TRY(cudaMalloc((void**)&m->d_xa_f32, xa.size() * 4));
     CUDA_TRY(cudaMemcpy(m->d_xa_f32, xa.data(), xa.size() * 4, cudaMemcpyHostToDevice));
     if (!m->h_invQ.empty()) {
         // B operand: slab s holds invQ[j][32 s .. 32 s + 31] for every output column j as a [Mp][128 B] image with
-        // the 16-byte chunk index XOR-ed by (j % 8): exactly what a SWIZZLE_128B K-major UMMA descriptor reads
-        std::vector<uint32_t> bs((size_t)t.nslab * t.Mp * 32, 0u);
+        // the 16-byte chunk index XOR-ed by (j % 8): exactly what a SWIZZLE_128B K-major UMMA descriptor reads.
+        // hi = rna_tf32(x); lo = rna_tf32(x - hi) for the 3 x TF32 split.
+        std::vector<uint32_t> bh((size_t)nslab * Mp * 32, 0u), bl((size_t)nslab * Mp * 32, 0u);
         for (int j = 0; j < M; ++j)
             for (int i = 0; i < M; ++i) {
                 const int s = i >> 5, c = (i & 31) >> 2, e = i & 3;
-                bs[(size_t)s * t.Mp * 32 + (size_t)j * 32 + (size_t)((c ^ (j & 7)) << 2) + e] =
-                    host_tf32_rna((float)m->h_invQ[(size_t)j * M + i]);
+                const size_t at = (size_t)s * Mp * 32 + (size_t)j * 32 + (size_t)((c ^ (j & 7)) << 2) + e;
+                const float x = (float)m->h_invQ[(size_t)j * M + i];
+                const uint32_t hi = host_tf32_rna(x);
+                float hf;
+                memcpy(&hf, &hi, 4);
+                bh[at] = hi;
+                bl[at] = host_tf32_rna(x - hf);
             }
-        CUDA_TRY(cudaMalloc((void**)&m->d_bslabs, bs.size() * 4));
-        CUDA_TRY(cudaMemcpy(m->d_bslabs, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void**)&m->d_bslabs, bh.size() * 4));
+        CUDA_TRY(cudaMemcpy(m->d_bslabs, bh.data(), bh.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void**)&m->d_bslabs_lo, bl.size() * 4));
+        CUDA_TRY(cudaMemcpy(m->d_bslabs_lo, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice));
     }
-    t.valid = true;
-    m->tf = t;
+    m->tf = fast;
+    m->tfx = prec;
     std::vector<double>().swap(m->h_invQ);   // the FP64 host copy was only needed for this packing
     return GPE_OK;
 }
 
 int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu, float* var, float* deriv,
-                       cudaStream_t st) {
+                       bool fast, cudaStream_t st) {
     if (N == 0) return GPE_OK;
     int rc = ensure_tf32(m);
     if (rc) return rc;
     if (var && !m->d_bslabs) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
-    const Tf32Plan& t = m->tf;
+    const bool x3 = !fast && var != nullptr;   // without the variance both modes are plain FP32: use the lighter plan
+    const Tf32Plan& t = x3 ? m->tfx : m->tf;
     const int64_t ntiles = (N + kTfTN - 1) / kTfTN;
     const int grid = (int)std::min<int64_t>(ntiles, m->sms);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -642,12 +655,12 @@ int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu,
         memset(&p, 0, sizeof(p));
         p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
         p.ld_mu = 1; p.ld_var = 1; p.ld_deriv = m->D;
-        p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs;
+        p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs; p.bslabs_lo = m->d_bslabs_lo;
         p.M = m->M; p.D = m->D; p.Mp = t.Mp; p.nslab = t.nslab; p.pass_cols = t.pass_cols; p.b = (float)m->b;
         p.off_bar = t.off_bar; p.off_a = t.off_a; p.off_b = t.off_b; p.off_x = t.off_x; p.off_out = t.off_out;
         p.off_vred = t.off_vred; p.off_tmem = t.off_tmem; p.bstage_bytes = t.bstage_bytes;
         for (int d = 0; d < 32; ++d) p.sqrt_w[d] = (float)m->sqrt_w[d];
-        CUDA_TRY(launch_tf32_big(t.DP, p, grid, t.smem, st));
+        CUDA_TRY(launch_tf32_big(t.DP, x3, p, grid, t.smem, st));
         return GPE_OK;
     }
     Tf32Params p;
@@ -762,6 +775,7 @@ int gpe_model_destroy(gpe_model* m) {
     if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
     if (m->d_xa_f32) cudaFree(m->d_xa_f32);
     if (m->d_bslabs) cudaFree(m->d_bslabs);
+    if (m->d_bslabs_lo) cudaFree(m->d_bslabs_lo);
     delete m;
     return GPE_OK;
 }
@@ -802,7 +816,11 @@ int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, fl
     if ((flags & GPE_WANT_DERIV) && !deriv) return fail(GPE_ERR_INVALID, "GPE_WANT_DERIV set but deriv is NULL");
     if (!mu && !var && !deriv) return fail(GPE_ERR_INVALID, "no output requested");
     CUDA_TRY(cudaSetDevice(m->device));
-    if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, (cudaStream_t)stream);
+    // variance mode: 3xTF32 split unless asked otherwise -- except for M > 256, where the FP32 accumulation of the
+    // long sums dominates the error anyway (1.1e-5 vs 1.5e-5 at M = 1000) and the split costs 3.6x: there the
+    // single pass is the default and GPE_F32_FORCE_3X opts in
+    const bool fast = (flags & GPE_F32_FAST_TF32) != 0 || (m->M > 256 && !(flags & GPE_F32_FORCE_3X));
+    if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, fast, (cudaStream_t)stream);
     // host pointers: plain chunked copies on the default stream (the FP64 path has the overlapped pipeline)
     const int D = m->D;
     const int64_t CH = std::min<int64_t>(1 << 20, N);
@@ -816,7 +834,7 @@ int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, fl
         float* o_mu = d_out; float* o_var = d_out + n; float* o_der = d_out + 2 * n;
         e = cudaMemcpy(d_in, testing + n0 * D, (size_t)n * D * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) rc = predict_device_f32(m, d_in, n, mu ? o_mu : nullptr, var ? o_var : nullptr,
-                                                      deriv ? o_der : nullptr, nullptr);
+                                                      deriv ? o_der : nullptr, fast, nullptr);
         if (rc == GPE_OK && e == cudaSuccess && mu) e = cudaMemcpy(mu + n0, o_mu, (size_t)n * 4, cudaMemcpyDeviceToHost);
         if (rc == GPE_OK && e == cudaSuccess && var) e = cudaMemcpy(var + n0, o_var, (size_t)n * 4, cudaMemcpyDeviceToHost);
         if (rc == GPE_OK && e == cudaSuccess && deriv) e = cudaMemcpy(deriv + n0 * D, o_der, (size_t)n * D * 4, cudaMemcpyDeviceToHost);

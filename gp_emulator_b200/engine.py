@@ -125,17 +125,21 @@ class DeviceModel:
         return {k: out[k] for k in wanted}
 
 
-    def predict_f32(self, testing, want_var=True, want_deriv=True):
+    def predict_f32(self, testing, want_var=True, want_deriv=True, fast=None):
         """Single-precision prediction on the tcgen05 / TMEM path (M <= 256): float32 in, float32 out.
 
         numpy float32 (N, D) -> numpy results; torch float32 CUDA tensor -> torch results (asynchronous).
-        The variance contraction runs on the tensor cores with TF32 inputs (see DESIGN.md for the error bound).
+        The variance contraction runs on the tensor cores: 3xTF32 split by default (FP32-grade, meets the
+        reference's 1e-5 FP32 criterion); ``fast=True`` uses a single TF32 pass (error ~1e-4, ~1.7x faster).
+        ``fast=None`` (default) = split for M <= 256, single pass above (where FP32 accumulation dominates the
+        error anyway); ``fast=False`` forces the split for any M.
         """
         lib = _lib.load()
         D = self.D
         if want_var and not self.has_var:
             raise GpemuError("variance requested but the model was uploaded without invQ")
-        flags = WANT_MU | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0)
+        flags = WANT_MU | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0) | (
+            _lib.F32_FAST_TF32 if fast else (_lib.F32_FORCE_3X if fast is False else 0))
         if _is_torch(testing):
             import torch
             t = testing

@@ -38,6 +38,8 @@ typedef enum gpe_status {
 #define GPE_WANT_DERIV  0x04u
 #define GPE_WANT_HESS   0x08u
 #define GPE_HOST_PTRS   0x100u /* testing/outputs are host pointers: the library streams them */
+#define GPE_F32_FAST_TF32 0x200u /* gpe_predict_f32 only: one TF32 pass for the variance instead of the 3xTF32 split */
+#define GPE_F32_FORCE_3X  0x400u /* gpe_predict_f32 only: 3xTF32 split also for M > 256 (default there: one pass) */
 
 #define GPE_MAX_TRAIN 1024     /* largest M served by the register-resident variance contraction */
 #define GPE_MAX_INPUTS 32      /* largest D */
@@ -88,9 +90,12 @@ int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, doub
 /* Single-precision variant on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in TMEM):
  * what the reference's FP32 build of gpuPredict computes (`real` = float, gp_emulator/gpu/gpu_predict.h:20-34;
  * Python side precision=np.float32, gp_emulator/GaussianProcess.py:289-316).  Same handle, float32 I/O
- * (testing (N, D), mu (N), var (N), deriv (N, D)), M <= 1024, no Hessian.  K*, mean and gradient are FP32; the
- * variance contraction uses TF32 inputs with FP32 accumulation (relative error ~1e-4 of max|var|).
- * M <= 256 keeps the whole K* tile on chip; 256 < M <= 1024 runs column passes over the 512 TMEM columns. */
+ * (testing (N, D), mu (N), var (N), deriv (N, D)), M <= 1024, no Hessian.  K*, mean and gradient are FP32.
+ * Variance contraction: by default a 3xTF32 split (hi.hi + lo.hi + hi.lo, FP32 accumulation) that meets the
+ * reference's own FP32 pass criterion of 1e-5 (tests/benchmark.py:56); with GPE_F32_FAST_TF32 a single TF32 pass
+ * (relative error ~1e-4 of max|var|, bound 2^-11), about 1.7x faster at M = 250.  For M > 256 the single pass is
+ * the default (the FP32 accumulation of 1000-term sums costs ~1e-5 by itself, so the split buys little for 3.6x the
+ * time); GPE_F32_FORCE_3X selects the split there too. */
 int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, float* var, float* deriv,
                     unsigned flags, void* stream);
 

@@ -181,8 +181,9 @@ def test_preallocated_and_pinned_outputs(gpemu):
 @pytest.mark.parametrize("M,D,N", [(250, 10, 3000), (256, 10, 129), (64, 4, 500), (37, 3, 1), (100, 7, 257),
                                    (200, 16, 300), (130, 12, 128), (10, 1, 40)])
 def test_single_precision_tensor_core_path(gpemu, M, D, N):
-    """tcgen05 / TMEM kernel.  Bars: mean and gradient at the reference's own FP32 pass criterion 1e-5
-    (tests/benchmark.py:56); variance 5e-4 = 2^-11, the TF32 input rounding (measured ~6e-5 at M = 250)."""
+    """tcgen05 / TMEM kernels.  Bars: mean and gradient at the reference's own FP32 pass criterion 1e-5
+    (tests/benchmark.py:56); variance 1e-5 as well in the default 3xTF32 mode, 5e-4 = 2^-11 (the TF32 input
+    rounding; measured ~6e-5 at M = 250) in the single-pass `fast` mode."""
     import torch
     inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
@@ -191,9 +192,12 @@ def test_single_precision_tensor_core_path(gpemu, M, D, N):
     o = m.predict_f32(t32)
     assert o["mu"].dtype == np.float32 and o["deriv"].shape == (N, D)
     assert orc.ref_err(o["mu"], mu) < 1e-5 and orc.ref_err(o["deriv"], deriv) < 1e-5
-    assert orc.ref_err(o["var"], var) < 5e-4
+    assert orc.ref_err(o["var"], var) < 1e-5
+    of = m.predict_f32(t32, fast=True)
+    assert orc.ref_err(of["mu"], mu) < 1e-5 and orc.ref_err(of["deriv"], deriv) < 1e-5
+    assert orc.ref_err(of["var"], var) < 5e-4
     o2 = m.predict_f32(t32, want_var=False)
-    assert np.array_equal(o2["mu"], o["mu"]) and np.array_equal(o2["deriv"], o["deriv"])
+    assert orc.ref_err(o2["mu"], mu) < 1e-5 and orc.ref_err(o2["deriv"], deriv) < 1e-5
     od = m.predict_f32(torch.from_numpy(t32).cuda())
     torch.cuda.synchronize()
     for k in ("mu", "var", "deriv"):
@@ -203,17 +207,19 @@ def test_single_precision_tensor_core_path(gpemu, M, D, N):
 @pytest.mark.parametrize("M,D,N", [(300, 5, 200), (512, 10, 129), (513, 4, 64), (1000, 10, 300), (1024, 12, 100),
                                    (700, 16, 50)])
 def test_single_precision_large_m(gpemu, M, D, N):
-    """256 < M <= 1024: column passes over 512 TMEM columns, K* slabs through a 2-deep A ring, epilogue with K*
-    recomputed (predict_tf32_big.cuh).  Same bars as the small-M kernel."""
+    """256 < M <= 1024: column passes over the TMEM columns, K* slabs through a 2-deep A ring, epilogue with K*
+    recomputed (predict_tf32_big.cuh).  At M ~ 1000 the FP32 accumulation of 1000-term sums itself costs ~1e-5, so
+    the variance bar of the 3xTF32 mode is 3e-5 here (measured 1.1e-5 at M = 1000); fast mode as for small M."""
     inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     t32 = testing.astype(np.float32)
     mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, t32.astype(np.float64))
-    o = m.predict_f32(t32)
-    assert orc.ref_err(o["mu"], mu) < 1e-5 and orc.ref_err(o["deriv"], deriv) < 1e-5
-    assert orc.ref_err(o["var"], var) < 5e-4
+    for fast, bar in ((False, 3e-5), (True, 5e-4)):
+        o = m.predict_f32(t32, fast=fast)
+        assert orc.ref_err(o["mu"], mu) < 1e-5 and orc.ref_err(o["deriv"], deriv) < 1e-5
+        assert orc.ref_err(o["var"], var) < bar, (fast, orc.ref_err(o["var"], var))
     o2 = m.predict_f32(t32, want_var=False)
-    assert np.array_equal(o2["mu"], o["mu"]) and np.array_equal(o2["deriv"], o["deriv"])
+    assert orc.ref_err(o2["mu"], mu) < 1e-5 and orc.ref_err(o2["deriv"], deriv) < 1e-5
 
 
 def test_single_precision_limits_and_dropin_routing(gpemu):
@@ -227,7 +233,8 @@ def test_single_precision_limits_and_dropin_routing(gpemu):
     mu_c, var_c, deriv_c = orc.predict(inputs, theta, invQ, invQt, testing)
     mu, var, deriv = gp.predict(testing, precision=np.float32)    # the reference benchmark's GPU call
     assert mu.dtype == np.float32
-    assert orc.ref_err(mu, mu_c) < 1e-5 and orc.ref_err(deriv, deriv_c) < 1e-5 and orc.ref_err(var, var_c) < 5e-4
+    # all three outputs at the reference's FP32 criterion (tests/benchmark.py:56)
+    assert orc.ref_err(mu, mu_c) < 1e-5 and orc.ref_err(deriv, deriv_c) < 1e-5 and orc.ref_err(var, var_c) < 1e-5
 
 
 def test_dropin_class_matches_reference_semantics(gpemu):
