@@ -4,10 +4,10 @@ Same public names as the reference package for the prediction path (reference gp
 ``GaussianProcess``, ``k_fold_cross_validation``, ``MultivariateEmulator``; plus the device handles
 ``DeviceModel`` / ``DeviceBank`` for callers that keep data on the GPU.
 """
-from .engine import DeviceBank, DeviceModel
+from .engine import DeviceBank, DeviceModel, MultiDeviceModel
 from .gaussian_process import GaussianProcess, k_fold_cross_validation
 from .multivariate import MultivariateEmulator
 from ._lib import GpemuError, measure_fp64_peaks
 
-__all__ = ["GaussianProcess", "k_fold_cross_validation", "MultivariateEmulator", "DeviceModel", "DeviceBank",
+__all__ = ["GaussianProcess", "k_fold_cross_validation", "MultivariateEmulator", "DeviceModel", "DeviceBank", "MultiDeviceModel",
            "GpemuError", "measure_fp64_peaks"]

@@ -23,7 +23,7 @@ MAX_TRAIN, MAX_INPUTS = 1024, 32
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
-    "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
+    "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_destroy", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
     "gpe_bank_project", "gpe_measure_fp64_peaks", "gpe_launch_count",
 )
 
@@ -61,6 +61,13 @@ def load():
     lib.gpe_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint, C.c_void_p]
     lib.gpe_predict_f32.restype = C.c_int
     lib.gpe_predict_f32.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, C.c_uint, C.c_void_p]
+    lib.gpe_multi_create.restype = C.c_int
+    lib.gpe_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, dp, dp, dp, dp, C.c_uint,
+                                     C.POINTER(C.c_void_p)]
+    lib.gpe_multi_predict.restype = C.c_int
+    lib.gpe_multi_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint]
+    lib.gpe_multi_destroy.restype = C.c_int
+    lib.gpe_multi_destroy.argtypes = [C.c_void_p]
     lib.gpe_predict_wrap.restype = C.c_int
     lib.gpe_predict_wrap.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.gpe_bank_create.restype = C.c_int

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cmath>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -105,6 +106,10 @@ struct gpe_model {
     std::vector<double> h_inputs, h_invQt, h_invQ;  // host copy of the model for the lazy FP32 packing
     double h_expx[33];
     Slot slots[2];
+};
+
+struct gpe_multi {
+    std::vector<gpe_model*> models;   // one resident copy of the GP per device
 };
 
 struct gpe_bank {
@@ -872,6 +877,58 @@ int gpe_predict_wrap(const double* expX, const double* inputs, const double* inv
     // the legacy extension hands deriv back as (Ninputs, Npredict); its caller transposes (GaussianProcess.py:321)
     for (int n = 0; n < Npredict; ++n)
         for (int d = 0; d < Ninputs; ++d) deriv[(size_t)d * Npredict + n] = nd[(size_t)n * Ninputs + d];
+    return GPE_OK;
+}
+
+// ---- one call, G devices: host-resident test points are split into contiguous ranges, one host thread per
+// device drives that device's streaming pipeline (no steady-state exchange) ------------
+int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
+                     const double* invQt, const double* invQ, unsigned options, gpe_multi** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
+    gpe_multi* mm = new gpe_multi();
+    for (int i = 0; i < n_devices; ++i) {
+        gpe_model* m = nullptr;
+        int rc = gpe_model_create_ex(devices[i], M, D, inputs, expX, invQt, invQ, options, &m);
+        if (rc) { gpe_multi_destroy(mm); return rc; }
+        mm->models.push_back(m);
+    }
+    *out = mm;
+    return GPE_OK;
+}
+
+int gpe_multi_destroy(gpe_multi* mm) {
+    if (!mm) return GPE_OK;
+    for (gpe_model* m : mm->models) gpe_model_destroy(m);
+    delete mm;
+    return GPE_OK;
+}
+
+int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                      double* hess, unsigned flags) {
+    if (!mm) return fail(GPE_ERR_INVALID, "handle is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    const int G = (int)mm->models.size();
+    const int64_t D = mm->models[0]->D;
+    std::vector<int> rcs(G, GPE_OK);
+    std::vector<std::string> msgs(G);
+    std::vector<std::thread> th;
+    const int64_t base = N / G, rem = N % G;
+    for (int g = 0; g < G; ++g) {
+        const int64_t lo = g * base + std::min<int64_t>(g, rem), n = base + (g < rem ? 1 : 0);
+        if (n == 0) continue;
+        th.emplace_back([=, &rcs, &msgs] {
+            rcs[g] = gpe_predict(mm->models[g], testing + lo * D, n, mu ? mu + lo : nullptr, var ? var + lo : nullptr,
+                                 deriv ? deriv + lo * D : nullptr, hess ? hess + lo * D * D : nullptr,
+                                 flags | GPE_HOST_PTRS, nullptr);
+            if (rcs[g]) msgs[g] = gpe_last_error();   // thread-local in the worker: carry it out
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", mm->models[g]->device, msgs[g].c_str());
     return GPE_OK;
 }
 

@@ -167,6 +167,55 @@ class DeviceModel:
         return out
 
 
+class MultiDeviceModel:
+    """One GP resident on several GPUs of the box; ``predict`` splits a host batch into contiguous ranges, one
+    per device, driven by one host thread each inside the library (no Python threads, no collective)."""
+
+    def __init__(self, inputs, theta, invQt, invQ=None, devices=None, symmetric_variance=False):
+        inputs = f64c(inputs)
+        self.M, self.D = inputs.shape
+        theta = f64c(theta).ravel()
+        expx = np.exp(theta[: self.D + 1])
+        invQt = f64c(invQt).ravel()
+        invQ = None if invQ is None else f64c(invQ)
+        lib = _lib.load()
+        if devices is None:
+            devices = list(range(lib.gpe_device_count()))
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise GpemuError("no CUDA device available; gp_emulator_b200 has no CPU fallback")
+        self.has_var = invQ is not None
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        check(lib.gpe_multi_create(len(self.devices), arr, self.M, self.D, addr(inputs), addr(expx), addr(invQt),
+                                   addr(invQ), _lib.OPT_SYMMETRIC_VARIANCE if symmetric_variance else 0, C.byref(h)))
+        self._h = h
+        self._fin = weakref.finalize(self, lib.gpe_multi_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def predict(self, testing, want_var=True, want_deriv=True, want_hess=False, out=None, pinned=False):
+        t = f64c(testing)
+        if t.ndim != 2 or t.shape[1] != self.D:
+            raise ValueError(f"testing must be (N, {self.D})")
+        if want_var and not self.has_var:
+            raise GpemuError("variance requested but the model was uploaded without invQ")
+        N, D = t.shape
+        shapes = {"mu": (N,), "var": (N,), "deriv": (N, D), "hess": (N, D, D)}
+        wanted = ["mu"] + [k for k, w in (("var", want_var), ("deriv", want_deriv), ("hess", want_hess)) if w]
+        out = dict(out) if out else {}
+        mk = _pinned_empty if pinned else np.empty
+        for k in wanted:
+            if k not in out:
+                out[k] = mk(shapes[k])
+        flags = WANT_MU | (WANT_VAR if want_var else 0) | (WANT_DERIV if want_deriv else 0) | (
+            WANT_HESS if want_hess else 0)
+        check(_lib.load().gpe_multi_predict(self._h, addr(t), N, addr(out.get("mu")), addr(out.get("var")),
+                                            addr(out.get("deriv")), addr(out.get("hess")), flags))
+        return {k: out[k] for k in wanted}
+
+
 class DeviceBank:
     """E GPs sharing training inputs and test points; optional PCA basis (E, W) for back-projection."""
 

@@ -110,6 +110,17 @@ int gpe_predict_wrap(const double* expX, const double* inputs, const double* inv
                      const double* testing, double* result, double* error, double* deriv,
                      int Npredict, int Ntrain, int Ninputs, int theta_size);
 
+/* One call, several devices: the GP is uploaded to every listed device and a host-resident batch is split into
+ * contiguous row ranges, one per device, each streamed by its own host thread (test points are independent:
+ * gp_emulator/GaussianProcess.py:228-249; the reference has no multi-device code, doc/report.md:48,95 lists it as
+ * future work).  Host pointers only; results are bit-identical to the single-device call. */
+typedef struct gpe_multi gpe_multi;
+int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
+                     const double* invQt, const double* invQ, unsigned options, gpe_multi** out);
+int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                      double* hess, unsigned flags);
+int gpe_multi_destroy(gpe_multi* mm);
+
 /* Bank of E GPs that share the training inputs (M, D) and the test points, each with its own
  * hyper-parameters: the per-PC emulators of MultivariateEmulator (gp_emulator/multivariate_gp.py:176-188)
  * and the per-band banks of tests/test_perband_emulator.py:22-37.

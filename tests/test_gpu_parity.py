@@ -380,3 +380,18 @@ def test_inplace_edit_needs_invalidate(gpemu):
     _, v1, _ = gp.predict(testing)
     _, var, _ = orc.predict(inputs, theta, gp.invQ, invQt, testing)
     assert orc.ref_err(v1, var) < TOL and not np.array_equal(v0, v1)
+
+
+def test_one_call_multi_device_fanout(lib, gpemu):
+    """gpe_multi_*: with G visible GPUs the batch is split over them; with one GPU the same code path runs two
+    copies of the model on device 0 from two host threads.  Bit-identical to the single-device result."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 100001, seed=12)
+    ndev = lib.gpe_device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    mm = gpemu.MultiDeviceModel(inputs, theta, invQt, invQ, devices=devices)
+    a = mm.predict(testing)
+    b = gpemu.DeviceModel(inputs, theta, invQt, invQ).predict(testing)
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(a[k], b[k]), k
+    h = mm.predict(testing[:300], want_var=False, want_deriv=False, want_hess=True)["hess"]
+    assert orc.ref_err(h, orc.hessian(inputs, theta, invQt, testing[:300])) < TOL
