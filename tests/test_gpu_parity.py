@@ -395,3 +395,25 @@ def test_one_call_multi_device_fanout(lib, gpemu):
         assert np.array_equal(a[k], b[k]), k
     h = mm.predict(testing[:300], want_var=False, want_deriv=False, want_hess=True)["hess"]
     assert orc.ref_err(h, orc.hessian(inputs, theta, invQt, testing[:300])) < TOL
+
+
+def test_random_shape_sweep(gpemu):
+    """Seeded fuzz over (M, D, N): every kernel configuration, chunked / resident training sets, ragged tiles."""
+    rs = np.random.RandomState(2026)
+    for _ in range(24):
+        M = int(rs.choice([rs.randint(1, 64), rs.randint(64, 257), rs.randint(257, 513), rs.randint(513, 1025)]))
+        D = int(rs.randint(1, 33))
+        N = int(rs.choice([1, rs.randint(2, 200), rs.randint(200, 700)]))
+        inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=int(rs.randint(1 << 30)))
+        invQ = invQ - 0.5                       # mixed signs: exercises cancellation in the contraction
+        theta = theta - 1.0
+        m = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=bool(rs.randint(2)))
+        out = m.predict(testing)
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+        tag = (M, D, N)
+        assert orc.ref_err(out["mu"], mu) < TOL, tag
+        assert orc.ref_err(out["deriv"], deriv) < TOL, tag
+        assert orc.var_cond_err(out["var"], var, inputs, theta, invQ, testing) < TOL, tag
+        if D <= 16:
+            o32 = m.predict_f32(testing.astype(np.float32), fast=bool(rs.randint(2)))
+            assert orc.ref_err(o32["mu"], mu) < 2e-5, tag
