@@ -247,7 +247,8 @@ MeanPlan plan_mean(int M, int D, int DP) {
     m.off_ts = off; off += align_up((uint32_t)kMeanTN * (D + 1) * 8u, 16);
     m.off_out = off;
     m.smem = off;
-    m.smem_hess = off + (uint32_t)kMeanTN * D * D * 8u;
+    // Hessian staging: [TN][D][D] for the triangular kernel (D <= 12), [TN][HR][D] for the row-block kernel
+    m.smem_hess = off + (uint32_t)kMeanTN * D * 8u * (uint32_t)(DP <= 12 ? D : (DP <= 16 ? 4 : 2));
     return m;
 }
 
@@ -323,8 +324,6 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     const bool need_mean = !mean_done && (mu != nullptr || deriv != nullptr);
     if (need_mean || hess != nullptr) {
         const bool do_hess = hess != nullptr;
-        if (do_hess && m->DP > 12)
-            return fail(GPE_ERR_UNSUPPORTED, "Hessian output supports D <= 12 (got D = %d)", m->D);
         MeanParams p;
         memset(&p, 0, sizeof(p));
         p.testing = testing; p.N = N;
@@ -1007,7 +1006,6 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
         // mean / gradient / Hessian of ALL emulators in one launch (blockIdx.y = emulator)
         gpe_model* m0 = b->models[0];
         const bool do_hess = hess != nullptr;
-        if (do_hess && m0->DP > 12) return fail(GPE_ERR_UNSUPPORTED, "Hessian output supports D <= 12 (got D = %d)", m0->D);
         if (E > 65535) return fail(GPE_ERR_UNSUPPORTED, "bank size %d exceeds the grid limit", (int)E);
         MeanParams p;
         memset(&p, 0, sizeof(p));

@@ -46,7 +46,22 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
         kern<<<grid, kMeanThreads, smem, st>>>(p);
         return cudaGetLastError();
 #else
-        return cudaErrorNotSupported;
+        // D > 12: row-block Hessian kernel (predict_mean.cuh::k_hessian_rows); mean / gradient, if also requested,
+        // come from the plain mean kernel first
+        if (p.mu != nullptr || p.deriv != nullptr) {
+            MeanParams q = p;
+            q.hess = nullptr;
+            auto k0 = k_predict_mean<GPE_DP, false>;
+            cudaError_t e0 = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e0 != cudaSuccess) return e0;
+            k0<<<grid, kMeanThreads, smem, st>>>(q);
+        }
+        constexpr int HR = (GPE_DP <= 16) ? 4 : 2;
+        auto kern = k_hessian_rows<GPE_DP, HR>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kMeanThreads, smem, st>>>(p);
+        return cudaGetLastError();
 #endif
     }
     auto kern = k_predict_mean<GPE_DP, false>;

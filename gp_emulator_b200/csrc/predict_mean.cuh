@@ -199,4 +199,111 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     }
 }
 
+// Hessian for input dimensions beyond the register budget of the triangular kernel (D > 12): HR rows of the
+// (symmetric) Hessian at a time, all DP columns, K* recomputed for every row block.  Same thread mapping and
+// formulas as k_predict_mean; costs ~(DP / HR) x the K* work, which is acceptable for this completeness path.
+template <int DP, int HR>
+__global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams p) {
+    constexpr int TN = kMeanTN;
+    extern __shared__ __align__(128) unsigned char smem_h[];
+    double* Xc = reinterpret_cast<double*>(smem_h + p.off_xc);
+    double* ts_s = reinterpret_cast<double*>(smem_h + p.off_ts);
+    double* out_s = reinterpret_cast<double*>(smem_h + p.off_out);   // [TN][HR][D]
+    __shared__ double sqw_s[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
+    const int D = p.D, M = p.M;
+    const int em = blockIdx.y;
+    const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
+    if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
+    double* const o_hess = p.hess + em * p.eo_hess;
+    const int64_t ntiles = (p.N + TN - 1) / TN;
+    const int chunk_doubles = p.JC * (DP + 1);
+    bool x_resident = false;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = tile * TN;
+        const int npts = (int)min((int64_t)TN, p.N - n0);
+        __syncthreads();
+        for (int e = tid; e < TN * D; e += kMeanThreads) {
+            const int r = e / D;
+            const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
+            ts_s[e] = __ldg(p.testing + src);
+        }
+        __syncthreads();
+        double ts[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) ts[d] = (d < D) ? ts_s[n_loc * D + d] * sqw_s[d] : 0.0;
+        for (int r0 = 0; r0 < D; r0 += HR) {
+            double T[HR][DP];
+            double mu = 0.0;
+#pragma unroll
+            for (int i = 0; i < HR; ++i)
+#pragma unroll
+                for (int e = 0; e < DP; ++e) T[i][e] = 0.0;
+            for (int c = 0; c < p.nchunks; ++c) {
+                if (!x_resident) {
+                    __syncthreads();
+                    const double2* src = reinterpret_cast<const double2*>(xchunks + (size_t)c * chunk_doubles);
+                    double2* dst = reinterpret_cast<double2*>(Xc);
+                    for (int e = tid; e < chunk_doubles / 2; e += kMeanThreads) dst[e] = __ldg(src + e);
+                    __syncthreads();
+                    if (p.nchunks == 1) x_resident = true;
+                }
+                const int jn = min(p.JC, M - c * p.JC);
+                const double* al = Xc + p.JC * DP;
+                for (int jl = g_low; jl < jn; jl += 4) {
+                    const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
+                    double u[DP];
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DP; d += 2) {
+                        const double2 a = x1[d >> 1];
+                        u[d] = a.x - ts[d];
+                        u[d + 1] = a.y - ts[d + 1];
+                        r2 = fma(u[d], u[d], r2);
+                        r2 = fma(u[d + 1], u[d + 1], r2);
+                    }
+                    const double cj = exp_neg(-0.5 * r2) * al[jl];
+                    mu += cj;
+#pragma unroll
+                    for (int i = 0; i < HR; ++i) {
+                        // u[r0 + i] with a runtime r0: select from registers without dynamic indexing
+                        double ur = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) ur = (d == r0 + i) ? u[d] : ur;
+                        const double cu = cj * ur;
+#pragma unroll
+                        for (int e = 0; e < DP; ++e) T[i][e] = fma(cu, u[e], T[i][e]);
+                    }
+                }
+            }
+            mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+            mu += __shfl_xor_sync(0xffffffffu, mu, 2);
+            __syncthreads();   // out_s of the previous row block has been written out
+#pragma unroll
+            for (int i = 0; i < HR; ++i) {
+#pragma unroll
+                for (int e = 0; e < DP; ++e) {
+                    double v = T[i][e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int d = r0 + i;
+                    if (g_low == 0 && d < D && e < D) {
+                        double h = sqw_s[d] * sqw_s[e] * v;
+                        if (d == e) h -= sqw_s[d] * sqw_s[d] * mu;
+                        out_s[(n_loc * HR + i) * D + e] = h;
+                    }
+                }
+            }
+            __syncthreads();
+            const int nr = min(HR, D - r0);
+            for (int e = tid; e < npts * nr * D; e += kMeanThreads) {
+                const int r = e / (nr * D), q = e - r * (nr * D);
+                const int i = q / D, col = q - i * D;
+                o_hess[(n0 + r) * p.ld_hess + (int64_t)(r0 + i) * D + col] = out_s[(r * HR + i) * D + col];
+            }
+        }
+    }
+}
+
 }  // namespace gpe
