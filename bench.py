@@ -190,11 +190,22 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     model = synthetic_model() if rank == 0 else None
     if world > 1:
-        model = sharding.broadcast_model(model, src=0, device=dev)   # the only collective on the path
+        # NCCL initialises lazily and may print (version banner, NCCL_DEBUG output) on fd 1: point fd 1 at stderr
+        # until the communicator exists, so that stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            model = sharding.broadcast_model(model, src=0, device=dev)   # the only collective on the path
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     gp = gpe.GaussianProcess(model["inputs"], [], device=local_rank)
     gp.theta, gp.invQ, gp.invQt = model["theta"], model["invQ"], model["invQt"]   # tests/benchmark.py:11-15
