@@ -387,8 +387,11 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
 
 // Host-resident caller: stream chunks through two slots so the H2D copy of chunk i+1, the kernels of chunk i
 // and the D2H copy of chunk i-1 overlap.  Pinned caller buffers are DMA'd directly; pageable ones are staged.
-int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
-                 double* hess) {
+// T = double (FP64 path) or float (single-precision path); `launch(d_in, n, d_mu, d_var, d_deriv, d_hess, stream)`
+// enqueues the kernels for one chunk.
+template <typename T, typename Launch>
+int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* deriv, T* hess, Launch launch) {
+    constexpr size_t ES = sizeof(T);
     const int D = m->D;
     const int64_t per_out = (mu ? 1 : 0) + (var ? 1 : 0) + (deriv ? D : 0) + (hess ? (int64_t)D * D : 0);
     const bool direct = is_pinned_or_null(testing) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
@@ -397,14 +400,14 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
     for (auto& s : m->slots) {
         if (!s.st) CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        int rc = ensure(&s.d_in, &s.d_in_cap, (size_t)CH * D * 8, false);
+        int rc = ensure(&s.d_in, &s.d_in_cap, (size_t)CH * D * ES, false);
         if (rc) return rc;
-        rc = ensure(&s.d_out, &s.d_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * 8, false);
+        rc = ensure(&s.d_out, &s.d_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, false);
         if (rc) return rc;
         if (!direct) {
-            rc = ensure(&s.h_in, &s.h_in_cap, (size_t)CH * D * 8, true);
+            rc = ensure(&s.h_in, &s.h_in_cap, (size_t)CH * D * ES, true);
             if (rc) return rc;
-            rc = ensure(&s.h_out, &s.h_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * 8, true);
+            rc = ensure(&s.h_out, &s.h_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, true);
             if (rc) return rc;
         }
         s.pending = false;
@@ -413,11 +416,11 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
         if (!s.pending) return GPE_OK;
         CUDA_TRY(cudaEventSynchronize(s.done));
         const int64_t n0 = s.pend_n0, n = s.pend_n;
-        const double* src = s.h_out;
-        if (mu) { par_memcpy(mu + n0, src, (size_t)n * 8); src += n; }
-        if (var) { par_memcpy(var + n0, src, (size_t)n * 8); src += n; }
-        if (deriv) { par_memcpy(deriv + n0 * D, src, (size_t)n * D * 8); src += n * D; }
-        if (hess) { par_memcpy(hess + n0 * D * D, src, (size_t)n * D * D * 8); }
+        const T* src = reinterpret_cast<const T*>(s.h_out);
+        if (mu) { par_memcpy(mu + n0, src, (size_t)n * ES); src += n; }
+        if (var) { par_memcpy(var + n0, src, (size_t)n * ES); src += n; }
+        if (deriv) { par_memcpy(deriv + n0 * D, src, (size_t)n * D * ES); src += n * D; }
+        if (hess) { par_memcpy(hess + n0 * D * D, src, (size_t)n * D * D * ES); }
         s.pending = false;
         return GPE_OK;
     };
@@ -425,28 +428,29 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
     for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
         Slot& s = m->slots[which];
         const int64_t n = std::min(CH, N - n0);
-        double* o = s.d_out;
-        double* d_mu = mu ? o : nullptr;   if (mu) o += n;
-        double* d_var = var ? o : nullptr; if (var) o += n;
-        double* d_der = deriv ? o : nullptr; if (deriv) o += n * D;
-        double* d_hes = hess ? o : nullptr;
+        T* const d_in = reinterpret_cast<T*>(s.d_in);
+        T* o = reinterpret_cast<T*>(s.d_out);
+        T* d_mu = mu ? o : nullptr;   if (mu) o += n;
+        T* d_var = var ? o : nullptr; if (var) o += n;
+        T* d_der = deriv ? o : nullptr; if (deriv) o += n * D;
+        T* d_hes = hess ? o : nullptr;
         if (direct) {
-            CUDA_TRY(cudaMemcpyAsync(s.d_in, testing + n0 * D, (size_t)n * D * 8, cudaMemcpyHostToDevice, s.st));
+            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
         } else {
             int rc = drain(s);  // the slot's previous results must leave the staging buffer first
             if (rc) return rc;
-            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * 8);
-            CUDA_TRY(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)n * D * 8, cudaMemcpyHostToDevice, s.st));
+            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
+            CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
         }
-        int rc = predict_device(m, s.d_in, n, d_mu, d_var, d_der, d_hes, 1, 1, D, (int64_t)D * D, s.st);
+        int rc = launch(d_in, n, d_mu, d_var, d_der, d_hes, s.st);
         if (rc) return rc;
         if (direct) {
-            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, d_mu, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st));
-            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, d_var, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st));
-            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, d_der, (size_t)n * D * 8, cudaMemcpyDeviceToHost, s.st));
-            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, d_hes, (size_t)n * D * D * 8, cudaMemcpyDeviceToHost, s.st));
+            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, d_mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, d_var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, d_der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
+            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, d_hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
         } else {
-            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * 8, cudaMemcpyDeviceToHost, s.st));
+            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
             CUDA_TRY(cudaEventRecord(s.done, s.st));
             s.pending = true; s.pend_n0 = n0; s.pend_n = n;
         }
@@ -456,6 +460,15 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
         else { int rc = drain(s); if (rc) return rc; }
     }
     return GPE_OK;
+}
+
+int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                 double* hess) {
+    const int64_t D = m->D;
+    return predict_host_t<double>(m, testing, N, mu, var, deriv, hess,
+                                  [&](double* d_in, int64_t n, double* a, double* b, double* c, double* h, cudaStream_t st) {
+                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st);
+                                  });
 }
 
 // ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
@@ -825,28 +838,11 @@ int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, fl
     // single pass is the default and GPE_F32_FORCE_3X opts in
     const bool fast = (flags & GPE_F32_FAST_TF32) != 0 || (m->M > 256 && !(flags & GPE_F32_FORCE_3X));
     if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, fast, (cudaStream_t)stream);
-    // host pointers: plain chunked copies on the default stream (the FP64 path has the overlapped pipeline)
-    const int D = m->D;
-    const int64_t CH = std::min<int64_t>(1 << 20, N);
-    float *d_in = nullptr, *d_out = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d_in, (size_t)CH * D * 4));
-    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)CH * (D + 2) * 4);
-    if (e != cudaSuccess) { cudaFree(d_in); return fail(GPE_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
-    int rc = GPE_OK;
-    for (int64_t n0 = 0; n0 < N && rc == GPE_OK; n0 += CH) {
-        const int64_t n = std::min(CH, N - n0);
-        float* o_mu = d_out; float* o_var = d_out + n; float* o_der = d_out + 2 * n;
-        e = cudaMemcpy(d_in, testing + n0 * D, (size_t)n * D * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) rc = predict_device_f32(m, d_in, n, mu ? o_mu : nullptr, var ? o_var : nullptr,
-                                                      deriv ? o_der : nullptr, fast, nullptr);
-        if (rc == GPE_OK && e == cudaSuccess && mu) e = cudaMemcpy(mu + n0, o_mu, (size_t)n * 4, cudaMemcpyDeviceToHost);
-        if (rc == GPE_OK && e == cudaSuccess && var) e = cudaMemcpy(var + n0, o_var, (size_t)n * 4, cudaMemcpyDeviceToHost);
-        if (rc == GPE_OK && e == cudaSuccess && deriv) e = cudaMemcpy(deriv + n0 * D, o_der, (size_t)n * D * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(GPE_ERR_CUDA, "single-precision host path failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d_in);
-    cudaFree(d_out);
-    return rc;
+    // host pointers: the same two-slot overlapped pipeline as the FP64 path
+    return predict_host_t<float>(m, testing, N, mu, var, deriv, (float*)nullptr,
+                                 [&](float* d_in, int64_t n, float* a, float* b, float* c, float*, cudaStream_t st) {
+                                     return predict_device_f32(m, d_in, n, a, b, c, fast, st);
+                                 });
 }
 
 int gpe_predict_wrap(const double* expX, const double* inputs, const double* invQt, const double* invQ,

@@ -425,3 +425,17 @@ def test_random_shape_sweep(gpemu):
         if D <= 16:
             o32 = m.predict_f32(testing.astype(np.float32), fast=bool(rs.randint(2)))
             assert orc.ref_err(o32["mu"], mu) < 2e-5, tag
+
+
+def test_single_precision_host_streaming_multi_chunk(gpemu):
+    """float32 host arrays go through the same two-slot pipeline as FP64: chunk seams must be invisible."""
+    import torch
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(96, 5, 1, seed=3)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    N = (1 << 18) + 4321
+    t32 = np.random.RandomState(1).random_sample((N, 5)).astype(np.float32)
+    a = m.predict_f32(t32)
+    b = m.predict_f32(torch.from_numpy(t32).cuda())
+    torch.cuda.synchronize()
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(a[k], b[k].cpu().numpy()), k
