@@ -40,12 +40,12 @@ out.append({"config": "3: M=1000 D=10 FP64 mu+var+grad", "N": N, "points_per_s":
             "parity": {"mu": orc.ref_err(o["mu"], mu), "var": orc.ref_err(o["var"], var), "deriv": orc.ref_err(o["deriv"], deriv)},
             })
 t32d = torch.rand(N, D, dtype=torch.float32, device="cuda")
-o32 = m.predict_f32(testing.astype(np.float32))
+o32 = m.predict_f32(testing.astype(np.float32), fast=False)
 mu32, var32, deriv32 = orc.predict(inputs, theta, invQ, invQt, testing.astype(np.float32).astype(np.float64))
-s32, _ = timeit(lambda: m.predict_f32(t32d))
+s32, _ = timeit(lambda: m.predict_f32(t32d, fast=False))
 s32f, _ = timeit(lambda: m.predict_f32(t32d, fast=True))
 o32f = m.predict_f32(testing.astype(np.float32), fast=True)
-out.append({"config": "3T: M=1000 D=10 FP32 on tcgen05 + TMEM (column passes), 3xTF32 default / 1xTF32 fast", "N": N,
+out.append({"config": "3T: M=1000 D=10 FP32 on tcgen05 + TMEM (column passes): points_per_s = 3xTF32 (opt-in at this M), fast_points_per_s = 1xTF32 (default for M > 256)", "N": N,
             "points_per_s": N / s32, "fast_points_per_s": N / s32f, "fast_var_err": orc.ref_err(o32f["var"], var32), "tf32_tflops": N * 2 * 1024 * 1024 / s32 / 1e12,
             "parity_vs_fp64_oracle": {"mu": orc.ref_err(o32["mu"], mu32), "var": orc.ref_err(o32["var"], var32),
                                       "deriv": orc.ref_err(o32["deriv"], deriv32)}})
@@ -62,7 +62,7 @@ t = torch.rand(N, D, dtype=torch.float32, device="cuda")
 s, _ = timeit(lambda: m.predict_f32(t))
 sf, _ = timeit(lambda: m.predict_f32(t, fast=True))
 of = m.predict_f32(t32, fast=True)
-out.append({"config": "1T: M=250 D=10 FP32 on tcgen05 + TMEM, 3xTF32 default / 1xTF32 fast", "N": N, "points_per_s": N / s,
+out.append({"config": "1T: M=250 D=10 FP32 on tcgen05 + TMEM: points_per_s = 3xTF32 (default for M <= 256), fast_points_per_s = 1xTF32", "N": N, "points_per_s": N / s,
             "fast_points_per_s": N / sf, "fast_var_err": orc.ref_err(of["var"], var),
             "tf32_tflops": N * 2 * 256 * 256 / s / 1e12,
             "parity_vs_fp64_oracle": {"mu": orc.ref_err(o["mu"], mu), "var": orc.ref_err(o["var"], var), "deriv": orc.ref_err(o["deriv"], deriv)}})
