@@ -617,8 +617,9 @@ int ensure_tf32(gpe_model* m) {
     };
     Tf32Plan fast = (Mp <= 256) ? make_plan(false, false, Mp) : make_plan(true, false, 512);
     if (!fast.valid && Mp > 256) fast = make_plan(true, false, 256);
-    Tf32Plan prec = make_plan(true, true, 512);
-    for (int pc : {256, 128, 64}) if (!prec.valid) prec = make_plan(true, true, pc);
+    // 3xTF32: M <= 256 keeps the resident-K* kernel (K*_lo lives in tensor memory), larger M the ring kernel
+    Tf32Plan prec = (Mp <= 256) ? make_plan(false, false, Mp) : make_plan(true, true, 512);
+    for (int pc : {256, 128, 64}) if (!prec.valid && Mp > 256) prec = make_plan(true, true, pc);
     if (!fast.valid || !prec.valid)
         return fail(GPE_ERR_UNSUPPORTED, "single-precision path does not fit shared memory for M = %d, D = %d", M, D);
 
@@ -684,12 +685,12 @@ int predict_device_f32(gpe_model* m, const float* testing, int64_t N, float* mu,
     memset(&p, 0, sizeof(p));
     p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
     p.ld_mu = 1; p.ld_var = 1; p.ld_deriv = m->D;
-    p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs;
+    p.xa = m->d_xa_f32; p.bslabs = m->d_bslabs; p.bslabs_lo = m->d_bslabs_lo;
     p.M = m->M; p.D = m->D; p.Mp = t.Mp; p.nslab = t.nslab; p.b = (float)m->b;
     p.off_bar = t.off_bar; p.off_a = t.off_a; p.off_b = t.off_b; p.off_x = t.off_x; p.off_out = t.off_out;
     p.off_vred = t.off_vred; p.off_tmem = t.off_tmem; p.bstage_bytes = t.bstage_bytes;
     for (int d = 0; d < 32; ++d) p.sqrt_w[d] = (float)m->sqrt_w[d];
-    CUDA_TRY(launch_tf32(t.DP, p, grid, t.smem, st));
+    CUDA_TRY(launch_tf32(t.DP, x3, p, grid, t.smem, st));
     return GPE_OK;
 }
 

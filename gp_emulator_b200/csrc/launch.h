@@ -23,7 +23,7 @@ GPE_DECL_DP(24)
 GPE_DECL_DP(32)
 #undef GPE_DECL_DP
 
-cudaError_t launch_tf32(int DP, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_tf32(int DP, bool x3, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_tf32_big(int DP, bool x3, const Tf32BigParams& p, int grid, size_t smem, cudaStream_t st);
 static const int kTfDpList[] = {4, 8, 12, 16, 32};
 

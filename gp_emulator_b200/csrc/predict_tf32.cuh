@@ -34,6 +34,7 @@ struct Tf32Params {
     int64_t ld_mu, ld_var, ld_deriv;
     const float* xa;        // [Mp][DP] sqrt(w)-scaled inputs (FP32), then [Mp] b*alpha
     const uint32_t* bslabs; // [nslab][Mp rows (j)][32 (i)] TF32 bit patterns, 128B-swizzled smem image per slab
+    const uint32_t* bslabs_lo;  // X3: rna_tf32(invQ - hi), same layout
     int M, D, Mp, nslab;   // Mp = ceil64(M) output columns (UMMA N); nslab = ceil(M / 32) K slabs
     float b;
     uint32_t off_bar, off_a, off_b, off_x, off_out, off_vred, off_tmem;
@@ -91,6 +92,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+// A operand from TENSOR MEMORY (lane = row, 32-bit column = k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+
+// this thread's TMEM lane (lane base in taddr + lane id), 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(a), "r"(b), "r"(c),
+                 "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                  : "memory");
@@ -121,8 +142,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // DP: input dimension padded to a multiple of 4 (float4 training rows)
-template <int DP>
+// X3: 3xTF32 split.  K*_hi lives in the shared-memory A tile, K*_lo in the upper 256 columns of TENSOR MEMORY (the
+// A operand of tcgen05.mma may come from TMEM), invQ_hi / invQ_lo alternate through the B ring:
+//   D += K*_hi . B_hi + K*_lo . B_hi + K*_hi . B_lo.
+template <int DP, bool X3>
 __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params p) {
+    constexpr uint32_t kTmemCols = X3 ? 512 : 256;   // accumulator [0, 256) (+ K*_lo [256, 512))
     constexpr int TN = kTfTN;
     constexpr int NC = kTfComputeWarps * 32;
     extern __shared__ __align__(1024) unsigned char smem_tf[];
@@ -157,7 +182,8 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
         fence_mbar_init();
     }
     if (warp == kTfComputeWarps) {  // control warp owns the TMEM allocation (256 columns: Mp <= 256 FP32 accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     tc_fence_before();
@@ -181,41 +207,66 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
             uint32_t full_par = 0, empty_par = 0;   // bit st = parity of the next completion of b_full / b_empty[st]
             uint32_t a_par = 0, accE_par = 0;
             int64_t loads = 0;  // B slabs issued so far (global count); slab g -> stage g & 1
-            auto load_b = [&](int slab) {
+            // B ring uses: one per slab (X3: two per slab, hi then lo); use u -> stage (global count) & 1
+            const int uses_per_tile = nslab * (X3 ? 2 : 1);
+            auto load_b = [&](int use) {
+                const int slab = X3 ? (use >> 1) : use;
+                const uint32_t* src = (X3 && (use & 1)) ? p.bslabs_lo : p.bslabs;
                 const int st = (int)(loads & 1);
-                if (loads >= 2) {  // the MMAs that read this stage two slabs ago must have completed
+                if (loads >= 2) {  // the MMAs that read this stage two uses ago must have completed
                     mbar_wait(&b_empty[st], (empty_par >> st) & 1u);
                     empty_par ^= 1u << st;
                 }
                 mbar_arrive_expect_tx(&b_full[st], p.bstage_bytes);
-                tma_bulk_g2s(Bt + (size_t)st * p.bstage_bytes, p.bslabs + (size_t)slab * Mp * 32, p.bstage_bytes,
-                             &b_full[st]);
+                tma_bulk_g2s(Bt + (size_t)st * p.bstage_bytes, src + (size_t)slab * Mp * 32, p.bstage_bytes, &b_full[st]);
                 ++loads;
             };
-            int64_t used = 0;  // B slabs consumed so far
+            int64_t used = 0;  // B ring uses consumed so far
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const bool first_tile = (tile == (int64_t)blockIdx.x);
                 load_b(0);
-                if (nslab > 1) load_b(1);
-                if (!first_tile) {  // previous tile's epilogue must have drained the accumulator
+                if (uses_per_tile > 1) load_b(1);
+                if (!first_tile) {  // previous tile's epilogue must have drained the accumulator (and K*_lo)
                     mbar_wait(acc_empty, accE_par);
                     accE_par ^= 1;
                 }
+                int use = 0;
                 for (int s = 0; s < nslab; ++s) {
                     mbar_wait(&a_ready[s], a_par);
-                    const int st = (int)(used & 1);
-                    mbar_wait(&b_full[st], (full_par >> st) & 1u);
-                    full_par ^= 1u << st;
-                    tc_fence_after();
                     const uint32_t a_addr = smem_u32(At + (size_t)s * (TN * 128));
-                    const uint32_t b_addr = smem_u32(Bt + (size_t)st * p.bstage_bytes);
+                    {
+                        const int st = (int)(used & 1);
+                        mbar_wait(&b_full[st], (full_par >> st) & 1u);
+                        full_par ^= 1u << st;
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(Bt + (size_t)st * p.bstage_bytes);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 4 k-steps of 8 TF32 (32 bytes) inside the 128-byte swizzle atom
-                        umma_tf32(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                  (s | k) != 0);
-                    umma_commit(&b_empty[st]);   // arrives when these MMAs have finished reading the stage
-                    ++used;
-                    if (s + 2 < nslab) load_b(s + 2);
+                        for (int k = 0; k < 4; ++k)   // 4 k-steps of 8 TF32 (32 bytes) inside the 128-byte swizzle atom
+                            umma_tf32(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (s | k) != 0);
+                        if (X3) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)   // K*_lo from tensor memory: columns 256 + 32 s + 8 k ..
+                                umma_tf32_ts(tmem_d, tmem_d + 256u + (uint32_t)(32 * s + 8 * k),
+                                             umma_desc_sw128(b_addr + k * 32), idesc, true);
+                        }
+                        umma_commit(&b_empty[st]);   // arrives when these MMAs have finished reading the stage
+                        ++used; ++use;
+                        if (use + 1 < uses_per_tile) load_b(use + 1);
+                    }
+                    if (X3) {
+                        const int st = (int)(used & 1);
+                        mbar_wait(&b_full[st], (full_par >> st) & 1u);
+                        full_par ^= 1u << st;
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(Bt + (size_t)st * p.bstage_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_tf32(tmem_d, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, true);
+                        umma_commit(&b_empty[st]);
+                        ++used; ++use;
+                        if (use + 1 < uses_per_tile) load_b(use + 1);
+                    }
                 }
                 umma_commit(acc_ready);
                 a_par ^= 1;
@@ -282,7 +333,16 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
                     uint4 v;
                     v.x = tf32_rna(k4[0]); v.y = tf32_rna(k4[1]); v.z = tf32_rna(k4[2]); v.w = tf32_rna(k4[3]);
                     *reinterpret_cast<uint4*>(At + (size_t)slab * (TN * 128) + row * 128 + ((cc ^ sw) << 4)) = v;
+                    if (X3) {   // lo = rna(k - hi) -> this row's TMEM lane, columns 256 + 4 c .. + 3
+                        tmem_st4(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + 256u + (uint32_t)(4 * c),
+                                 tf32_rna(k4[0] - __uint_as_float(v.x)), tf32_rna(k4[1] - __uint_as_float(v.y)),
+                                 tf32_rna(k4[2] - __uint_as_float(v.z)), tf32_rna(k4[3] - __uint_as_float(v.w)));
+                    }
                     if (cc >= 6) {   // this thread's last chunk of the slab (cc == 6 for h == 0, 7 for h == 1)
+                        if (X3) {
+                            tmem_st_wait();
+                            tc_fence_before();
+                        }
                         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
                         mbar_arrive(&a_ready[slab]);
                     }
@@ -332,9 +392,14 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
                     float gv[32];
                     tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, gv);
                     const unsigned char* arow = At + (size_t)(c0 >> 5) * (TN * 128) + erow * 128;
+                    float lo[32];
+                    if (X3) tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + 256u + (uint32_t)c0, lo);
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
-                        const float4 kv = *reinterpret_cast<const float4*>(arow + ((cc ^ (erow & 7)) << 4));
+                        float4 kv = *reinterpret_cast<const float4*>(arow + ((cc ^ (erow & 7)) << 4));
+                        if (X3) {   // K* = hi + lo, exact to 2^-22
+                            kv.x += lo[4 * cc + 0]; kv.y += lo[4 * cc + 1]; kv.z += lo[4 * cc + 2]; kv.w += lo[4 * cc + 3];
+                        }
                         vsum = fmaf(gv[4 * cc + 0], kv.x, vsum);
                         vsum = fmaf(gv[4 * cc + 1], kv.y, vsum);
                         vsum = fmaf(gv[4 * cc + 2], kv.z, vsum);
@@ -354,7 +419,7 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32(const Tf32Params
     tc_fence_before();
     __syncthreads();
     if (warp == kTfComputeWarps) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem_d));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols));
     }
 }
 

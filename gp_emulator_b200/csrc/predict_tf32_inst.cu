@@ -5,24 +5,27 @@
 
 namespace gpe {
 
-template <int DP>
+template <int DP, bool X3>
 static cudaError_t launch_dp(const Tf32Params& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = k_predict_tf32<DP>;
+    auto kern = k_predict_tf32<DP, X3>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kTfThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_tf32(int DP, const Tf32Params& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_tf32(int DP, bool x3, const Tf32Params& p, int grid, size_t smem, cudaStream_t st) {
+#define GPE_TF_CASE(DPV) \
+    case DPV: return x3 ? launch_dp<DPV, true>(p, grid, smem, st) : launch_dp<DPV, false>(p, grid, smem, st);
     switch (DP) {
-        case 4: return launch_dp<4>(p, grid, smem, st);
-        case 8: return launch_dp<8>(p, grid, smem, st);
-        case 12: return launch_dp<12>(p, grid, smem, st);
-        case 16: return launch_dp<16>(p, grid, smem, st);
-        case 32: return launch_dp<32>(p, grid, smem, st);
+        GPE_TF_CASE(4)
+        GPE_TF_CASE(8)
+        GPE_TF_CASE(12)
+        GPE_TF_CASE(16)
+        GPE_TF_CASE(32)
         default: return cudaErrorInvalidValue;
     }
+#undef GPE_TF_CASE
 }
 
 template <int DP, bool X3>
