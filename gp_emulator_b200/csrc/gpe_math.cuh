@@ -44,4 +44,42 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// Sum `NV` per-point values held by the 8 training-point lanes (lane bits 0..2) of two points a / b with a
+// shuffle reduce-scatter: 8-lane butterflies would need 3 * 2 * NV shuffles, this needs NV + NV/2 + NV/4.
+// On return lane (b2 b1 b0) holds the complete sums of point (b2 ? b : a) for value indices
+//   base + i,  i < H3,  base = (b1 ? H2 : 0) + (b0 ? H3 : 0)   (indices >= the half / NV are padding).
+template <int NV>
+struct RS {
+    static constexpr int H2 = (NV + 1) / 2;
+    static constexpr int H3 = (H2 + 1) / 2;
+    double r3[H3];
+    __device__ __forceinline__ void run(const double (&va)[NV], const double (&vb)[NV], int lane) {
+        const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+        double r1[2 * H2];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double send = b2 ? va[i] : vb[i];
+            const double keep = b2 ? vb[i] : va[i];
+            r1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int i = NV; i < 2 * H2; ++i) r1[i] = 0.0;
+        double r2[2 * H3];
+#pragma unroll
+        for (int i = 0; i < H2; ++i) {
+            const double send = b1 ? r1[i] : r1[H2 + i];
+            const double keep = b1 ? r1[H2 + i] : r1[i];
+            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int i = H2; i < 2 * H3; ++i) r2[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < H3; ++i) {
+            const double send = b0 ? r2[i] : r2[H3 + i];
+            const double keep = b0 ? r2[H3 + i] : r2[i];
+            r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+};
+
 }  // namespace gpe

@@ -335,7 +335,10 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.off_xc = m->mean.off_xc; p.off_ts = m->mean.off_ts; p.off_out = m->mean.off_out;
         memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
         const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * 8);
+        // CTAs per SM: a multiple of what is resident (3 for the mean + gradient kernel, 2 / 4 for the Hessian ones)
+        static const int env_mult = getenv("GPE_MEAN_GRID") ? atoi(getenv("GPE_MEAN_GRID")) : 0;
+        const int mult = env_mult > 0 ? env_mult : (do_hess ? 8 : 12);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * mult);
         const size_t smem = do_hess ? m->mean.smem_hess : m->mean.smem;
         CUDA_TRY(launch_mean(m->DP, do_hess, p, dim3(grid), smem, st));
     }

@@ -3,6 +3,7 @@
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
 #include "launch.h"
+#include <stdlib.h>
 
 #ifndef GPE_DP
 #error "compile with -DGPE_DP=<padded input dimension>"
@@ -64,7 +65,9 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
         return cudaGetLastError();
 #endif
     }
-    auto kern = k_predict_mean<GPE_DP, false>;
+    // mean + gradient: two-rows-per-thread kernel (k_predict_mean2); GPE_MEAN_V1=1 selects the first version
+    static const bool v1 = getenv("GPE_MEAN_V1") != nullptr;
+    auto kern = v1 ? k_predict_mean<GPE_DP, false> : k_predict_mean2<GPE_DP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kMeanThreads, smem, st>>>(p);

@@ -199,6 +199,133 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     }
 }
 
+// Mean + gradient only, with the phase-A design of the fused kernel: a warp owns 8 test rows, 8 lanes sweep the
+// training points, every thread carries TWO test rows (each training row pulled from shared memory feeds two
+// pairs), training-row loads are software-pipelined one step ahead, and the 8 lanes are combined by a shuffle
+// reduce-scatter.  32 points per 128-thread CTA.
+template <int DP>
+__global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams p) {
+    constexpr int TN = kMeanTN;
+    constexpr int NV = DP + 1;
+    extern __shared__ __align__(128) unsigned char smem_m2[];
+    double* Xc = reinterpret_cast<double*>(smem_m2 + p.off_xc);
+    double* ts_s = reinterpret_cast<double*>(smem_m2 + p.off_ts);   // [TN][D]; reused as [TN][D+1] outs
+    __shared__ double sqw_s[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g_low = lane & 7, n_a = warp * 8 + (lane >> 3), n_b = n_a + 4;
+    const int D = p.D, M = p.M, DV = D + 1;
+    const int em = blockIdx.y;
+    const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
+    if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
+    double* const o_mu = p.mu ? p.mu + em * p.eo_mu : nullptr;
+    double* const o_deriv = p.deriv ? p.deriv + em * p.eo_deriv : nullptr;
+    const int64_t ntiles = (p.N + TN - 1) / TN;
+    bool x_resident = false;
+    const int chunk_doubles = p.JC * (DP + 1);
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = tile * TN;
+        const int npts = (int)min((int64_t)TN, p.N - n0);
+        __syncthreads();
+        for (int e = tid; e < TN * D; e += kMeanThreads) {
+            const int r = e / D;
+            const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
+            ts_s[e] = __ldg(p.testing + src);
+        }
+        __syncthreads();
+        double tsa[DP], tsb[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
+            tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
+        }
+        double va[NV], vb[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) va[i] = vb[i] = 0.0;
+        for (int c = 0; c < p.nchunks; ++c) {
+            if (!x_resident) {
+                __syncthreads();
+                const double2* src = reinterpret_cast<const double2*>(xchunks + (size_t)c * chunk_doubles);
+                double2* dst = reinterpret_cast<double2*>(Xc);
+                for (int e = tid; e < chunk_doubles / 2; e += kMeanThreads) dst[e] = __ldg(src + e);
+                __syncthreads();
+                if (p.nchunks == 1) x_resident = true;
+            }
+            const int jn = min(p.JC, M - c * p.JC);
+            const double* al = Xc + p.JC * DP;
+            int jl = g_low;
+            if (jl < jn) {
+                double2 xn[DP / 2];
+                double aln;
+                {
+                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * DP);
+#pragma unroll
+                    for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
+                    aln = al[jl];
+                }
+                for (; jl < jn; jl += 8) {
+                    double2 x[DP / 2];
+#pragma unroll
+                    for (int q = 0; q < DP / 2; ++q) x[q] = xn[q];
+                    const double alj = aln;
+                    {
+                        const int jnx = min(jl + 8, jn - 1);
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * DP);
+#pragma unroll
+                        for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
+                        aln = al[jnx];
+                    }
+                    double ua[DP], ub[DP];
+                    double ra = 0.0, rb = 0.0;
+#pragma unroll
+                    for (int q = 0; q < DP / 2; ++q) {
+                        const int d = 2 * q;
+                        ua[d] = x[q].x - tsa[d];
+                        ub[d] = x[q].x - tsb[d];
+                        ua[d + 1] = x[q].y - tsa[d + 1];
+                        ub[d + 1] = x[q].y - tsb[d + 1];
+                        ra = fma(ua[d], ua[d], ra);
+                        rb = fma(ub[d], ub[d], rb);
+                        ra = fma(ua[d + 1], ua[d + 1], ra);
+                        rb = fma(ub[d + 1], ub[d + 1], rb);
+                    }
+                    const double ca = exp_neg(-0.5 * ra) * alj;
+                    const double cb = exp_neg(-0.5 * rb) * alj;
+                    va[0] += ca;
+                    vb[0] += cb;
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) {
+                        va[1 + d] = fma(ca, ua[d], va[1 + d]);
+                        vb[1 + d] = fma(cb, ub[d], vb[1 + d]);
+                    }
+                }
+            }
+        }
+        __syncthreads();   // everyone has read ts_s
+        double* outs = ts_s;
+        {
+            RS<NV> rs;
+            rs.run(va, vb, lane);
+            double* dst = outs + ((lane & 4) ? n_b : n_a) * DV;
+            const int half_base = (lane & 2) ? RS<NV>::H2 : 0;
+            const int base3 = (lane & 1) ? RS<NV>::H3 : 0;
+#pragma unroll
+            for (int i = 0; i < RS<NV>::H3; ++i) {
+                const int i2 = base3 + i, idx = half_base + i2;
+                if (i2 < RS<NV>::H2 && idx < DV) dst[idx] = rs.r3[i];
+            }
+        }
+        __syncthreads();
+        if (o_mu != nullptr && tid < npts) o_mu[(n0 + tid) * p.ld_mu] = outs[tid * DV];
+        if (o_deriv != nullptr) {
+            for (int e = tid; e < npts * D; e += kMeanThreads) {
+                const int r = e / D, d = e - r * D;
+                o_deriv[(n0 + r) * p.ld_deriv + d] = sqw_s[d] * outs[r * DV + 1 + d];
+            }
+        }
+    }
+}
+
 // Hessian for input dimensions beyond the register budget of the triangular kernel (D > 12): HR rows of the
 // (symmetric) Hessian at a time, all DP columns, K* recomputed for every row block.  Same thread mapping and
 // formulas as k_predict_mean; costs ~(DP / HR) x the K* work, which is acceptable for this completeness path.
