@@ -52,12 +52,17 @@ constexpr int64_t kPipeChunk = 1 << 18;  // points per host-streaming chunk
 
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+constexpr int kHessFusedMaxDp = 16;   // predict_full_inst.cu instantiates the HESS variants up to this DP
+
 struct FullPlan {
     bool valid = false;
     int cfg = 0, TN = 0, WC = 0, GH = 1, alias_x = 0, ctas_per_sm = 1;
     int Mp = 0, nt_act = 0, kblk = 0, kbps = 0, nit = 0, nstage = 0, JC = 0, nchunks = 0;
     uint32_t off_bar = 0, off_sqw = 0, off_ks = 0, off_bst = 0, off_xc = 0, off_ts = 0, off_pa = 0, off_vred = 0;
     uint32_t stage_bytes = 0, smem = 0, ts_bytes = 0;
+    // fused Hessian (phase C of the fused kernel): P operand width, k-blocks per ring stage, iterations
+    uint32_t off_hts = 0;
+    int NC = 0, kbh = 0, nit_h = 0;
 };
 
 struct Tf32Plan {
@@ -98,6 +103,9 @@ struct gpe_model {
     MeanPlan mean;
     double* d_xchunks_full = nullptr;
     double* d_stiled = nullptr;
+    double* d_ptiled = nullptr;  // Hessian operand of the fused kernel (null: direct Hessian kernel only)
+    double centre[32];
+    bool hess_fused_ok = false;
     double* d_xchunks_mean = nullptr;
     Tf32Plan tf, tfx;            // single-precision tcgen05 paths: fast (1 x TF32) and precise (3 x TF32); lazy
     float* d_xa_f32 = nullptr;
@@ -198,6 +206,12 @@ FullPlan plan_full(int M, int D, int DP) {
     f.off_ts = off; off += 2 * f.ts_bytes;
     f.off_pa = off; off += (f.GH > 1) ? align_up((uint32_t)f.GH * f.TN * (D + 1) * 8u, 16) : 0;
     f.off_vred = off; off += (uint32_t)f.WC * f.TN * 8u;
+    if (DP <= kHessFusedMaxDp && f.cfg <= 2) {   // room for the centred test rows of the fused Hessian
+        f.off_hts = off; off += align_up((uint32_t)f.TN * D * 8u, 16);
+        f.NC = (DP * (DP + 1) / 2 + 7) / 8 * 8;
+        f.kbh = (int)(f.stage_bytes / ((uint32_t)f.NC * 32u));
+        f.nit_h = f.kbh > 0 ? (f.kblk + f.kbh - 1) / f.kbh : 0;
+    }
     off = align_up(off, 128);
     const uint32_t fixed = off;
     const int m4 = (M + 3) / 4 * 4;
@@ -291,6 +305,46 @@ void free_slot(Slot& s) {
     s = Slot();
 }
 
+// Operand of the fused Hessian (predict_full.cuh, phase C): p_tiled[kb][col][c] = b alpha_j x'_jd x'_je for
+// j = 4 kb + c, col = index of (d <= e) in the row-major upper triangle, x' = sqrt(w) x - centre (mid-range).
+// The expansion sum k a (x'_d - t'_d)(x'_e - t'_e) = S2 - t'_d g_e - t'_e g_d - t'_d t'_e S0 loses about
+// log10(max |x'|^2) digits to cancellation, so it is only enabled while max |x'|^2 <= kHessFusedMaxR2
+// (training inputs within ~45 length scales of the centre: error amplification <= 2e3 * 2^-53 ~ 2e-13);
+// beyond that, and for the shapes the fused kernel does not cover, the direct kernel runs.
+constexpr double kHessFusedMaxR2 = 2000.0;
+
+int build_hessian_operand(gpe_model* m, const double* inputs, const double* invQt) {
+    const FullPlan& f = m->full;
+    const int M = m->M, D = m->D;
+    memset(m->centre, 0, sizeof(m->centre));
+    m->hess_fused_ok = false;
+    if (getenv("GPE_HESS_DIRECT") != nullptr) return GPE_OK;   // dev aid: always use the direct Hessian kernels
+    if (!f.valid || f.kbh < 1 || m->symmetric || f.NC > M || f.NC > f.Mp) return GPE_OK;
+    double r2max = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double lo = inputs[d], hi = inputs[d];
+        for (int j = 1; j < M; ++j) { lo = std::min(lo, inputs[(size_t)j * D + d]); hi = std::max(hi, inputs[(size_t)j * D + d]); }
+        m->centre[d] = m->sqrt_w[d] * 0.5 * (lo + hi);
+        const double r = m->sqrt_w[d] * 0.5 * (hi - lo);
+        r2max = std::max(r2max, r * r);
+    }
+    if (!(r2max <= kHessFusedMaxR2)) return GPE_OK;
+    std::vector<double> pt((size_t)f.kblk * f.NC * 4, 0.0);
+    std::vector<double> xp(D);
+    for (int j = 0; j < M; ++j) {
+        for (int d = 0; d < D; ++d) xp[d] = m->sqrt_w[d] * inputs[(size_t)j * D + d] - m->centre[d];
+        const double ba = m->b * invQt[j];
+        int col = 0;
+        for (int d = 0; d < D; ++d)
+            for (int e = d; e < D; ++e, ++col) pt[((size_t)(j >> 2) * f.NC + col) * 4 + (j & 3)] = ba * xp[d] * xp[e];
+    }
+    cudaError_t e = cudaMalloc((void**)&m->d_ptiled, pt.size() * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_ptiled, pt.data(), pt.size() * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e));
+    m->hess_fused_ok = true;
+    return GPE_OK;
+}
+
 // Launch the kernels for device-resident data on `st`.  Output strides allow bank (point-major) layouts.
 int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                    double* hess, int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess,
@@ -298,7 +352,11 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     if (N == 0) return GPE_OK;
     bool mean_done = false;
     static const bool force_full = getenv("GPE_FORCE_FULL") != nullptr;  // dev aid: time phase A alone
-    if (var != nullptr || (force_full && m->full.valid)) {
+    // the Hessian rides on the fused kernel when the model qualifies (build_hessian_operand); without a variance
+    // request that only pays for the 64-point tiles of cfg 0 (measured: 4.6e8 vs 3.6e8 points/s at M = 250, but
+    // 0.98e8 vs 1.10e8 at M = 1000), so larger M keeps the direct kernel for Hessian-only calls
+    const bool fuse_hess = hess != nullptr && m->hess_fused_ok && (var != nullptr || m->full.cfg == 0);
+    if (var != nullptr || fuse_hess || (force_full && m->full.valid)) {
         if (var != nullptr && !m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
         if (!m->full.valid)
             return fail(GPE_ERR_UNSUPPORTED, "variance contraction supports M <= %d (got M = %d)", GPE_MAX_TRAIN, m->M);
@@ -316,6 +374,11 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.stage_bytes = f.stage_bytes; p.ts_bytes = f.ts_bytes;
         memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
         p.trace = g_trace;
+        if (fuse_hess) {
+            p.hess = hess; p.ld_hess = ld_hess; p.p_tiled = m->d_ptiled; p.kbh = f.kbh; p.nit_h = f.nit_h; p.off_hts = f.off_hts;
+            memcpy(p.centre, m->centre, sizeof(p.centre));
+            hess = nullptr;   // done by this launch
+        }
         const int64_t ntiles = (N + f.TN - 1) / f.TN;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * f.ctas_per_sm);
         CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem, st));
@@ -781,6 +844,8 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
             if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_stiled, st.size() * 8);
             if (e == cudaSuccess) e = cudaMemcpy(m->d_stiled, st.data(), st.size() * 8, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
+            rc = build_hessian_operand(m, inputs, invQt);
+            if (rc) { gpe_model_destroy(m); return rc; }
         }
     }
     *out = m;
@@ -793,6 +858,7 @@ int gpe_model_destroy(gpe_model* m) {
     for (auto& s : m->slots) free_slot(s);
     if (m->d_xchunks_full) cudaFree(m->d_xchunks_full);
     if (m->d_stiled) cudaFree(m->d_stiled);
+    if (m->d_ptiled) cudaFree(m->d_ptiled);
     if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
     if (m->d_xa_f32) cudaFree(m->d_xa_f32);
     if (m->d_bslabs) cudaFree(m->d_bslabs);
@@ -995,12 +1061,16 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
     CUDA_TRY(cudaSetDevice(b->device));
     const int64_t E = b->E, D = b->D;
     const bool with_var = var != nullptr;
-    if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient)
+    if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient,
+                      // and the Hessian when every emulator qualifies for the fused Hessian)
+        bool fuse_hess = hess != nullptr;
+        for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok;
         for (int64_t e = 0; e < E; ++e) {
             int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var + e, deriv ? deriv + e * D : nullptr,
-                                    nullptr, E, E, E * D, E * D * D, (cudaStream_t)stream);
+                                    fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, (cudaStream_t)stream);
             if (rc) return rc;
         }
+        if (fuse_hess) hess = nullptr;
     }
     if (hess != nullptr || (!with_var && (mu != nullptr || deriv != nullptr))) {
         // mean / gradient / Hessian of ALL emulators in one launch (blockIdx.y = emulator)

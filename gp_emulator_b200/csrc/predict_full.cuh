@@ -8,12 +8,22 @@
 //   phase B  contracts  G = K* (TN x M) . invQ^T (M x M)  on the FP64 tensor path (DMMA.8x8x4) with the whole
 //            TN x Mp accumulator tile resident in registers, invQ streamed L2 -> smem by TMA bulk copies through
 //            an mbarrier ring, then var_n = b - b^2 sum_j G_nj K*_nj  -- reference GaussianProcess.py:240.
+//   phase C  (HESS variants) Hessian of the mean on the same tensor path.  With centred scaled coordinates
+//            x' = sqrt(w) x - c, t' = sqrt(w) t - c:
+//              sum_j k_j a_j (x'_jd - t'_d)(x'_je - t'_e) = S2_de - t'_d g_e - t'_e g_d - t'_d t'_e S0,
+//            where S0 / g are the mean / gradient sums phase A already has and
+//              S2 = K* (TN x M) . P (M x NC),  P[j][(d,e)] = b alpha_j x'_jd x'_je  (d <= e, NC = 8 ceil(D(D+1)/16))
+//            is one more GEMM against the K* tile that is already in shared memory; P streams through the same ring
+//            after invQ.  Reference GaussianProcess.py:345-366.  The expansion cancels digits when the training
+//            inputs span many length scales, so the host only selects these variants when max |x'| is small
+//            (gpemu.cu: hess_fused_ok); otherwise the direct kernel in predict_mean.cuh runs.
 // The next tile's test rows are prefetched by a TMA bulk copy while the current tile computes.
 //
 // Layouts chosen for the hardware (built once at model upload, see gpemu.cu):
 //   xchunks : per chunk of JC training points  [JC][DP] sqrt(w)-scaled inputs | [JC] b*alpha  (one bulk copy)
 //   s_tiled : [ceil(M/4)][Mp][4]  s_tiled[kb][j][c] = invQ[j][4 kb + c], zero padded: a k-block of the B operand
 //             is one contiguous 32*Mp-byte run whose smem image is bank-conflict-free for DMMA B fragments.
+//   p_tiled : [ceil(M/4)][NC][4]  p_tiled[kb][col][c] = P[4 kb + c][col], same idea for the Hessian operand.
 //   K* smem : [TN][Mp + 4] doubles; pitch = 4 (mod 16) doubles keeps the DMMA A-fragment loads conflict-free.
 #pragma once
 #include <cuda_runtime.h>
@@ -50,11 +60,19 @@ struct FullParams {
     uint32_t off_bar, off_sqw, off_ks, off_bst, off_xc, off_ts, off_pa, off_vred;
     uint32_t ts_bytes;     // size of ONE of the two test-row / output staging buffers at off_ts
     uint32_t stage_bytes;
+    // fused Hessian (HESS variants; hess == null skips phase C)
+    double* hess;          // (N, D, D) or null
+    int64_t ld_hess;       // element stride between consecutive points (D * D for a single GP)
+    const double* p_tiled;
+    int kbh;               // Hessian k-blocks per ring stage
+    int nit_h;             // ceil(kblk / kbh)
+    uint32_t off_hts;      // [TN][D] centred scaled test rows
     long long* trace;      // dev aid (normally null): CTA 0 stores clock64() at phase boundaries of its first 64 tiles
     double sqrt_w[kMaxD];
+    double centre[kMaxD];  // c_d of the centred coordinates (HESS variants)
 };
 
-template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT, bool SYM>
+template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT, bool SYM, bool HESS>
 __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullParams p) {
     constexpr int NW = WR * WC;           // warps per CTA (power of two)
     constexpr int NTHR = NW * 32;
@@ -67,6 +85,16 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     static_assert(NHI * GH == NW && NHI >= 1 && GH >= 1, "TN must be 8 * (a divisor of the warp count)");
     static_assert(TPR >= 1 && TPR * TN == NTHR, "TN must divide the thread count");
     static_assert(DP % 2 == 0, "DP even (16-byte rows)");
+    // phase C: the TN / 8 row tiles go to warp % NMT, the NCT column tiles are dealt cyclically to the CG = NW / NMT
+    // warps that share a row tile (8 warps, TN = 64: one row tile and all column tiles per warp -- balanced across
+    // the four SM sub-partitions, which warp % 4 maps onto)
+    constexpr int NMT = TN / 8;
+    constexpr int CG = (NW >= NMT) ? NW / NMT : 1;
+    constexpr int NCT = (DP * (DP + 1) / 2 + 7) / 8;
+    constexpr int NC = NCT * 8;
+    constexpr int NTH = (NCT + CG - 1) / CG;
+    static_assert(!HESS || (NW % NMT == 0 && NW >= NMT), "phase C needs the row tiles to divide the warps");
+    static_assert(!(HESS && SYM), "the fused Hessian is built for the plain variance operand only");
 
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -79,6 +107,9 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     double* Xc = reinterpret_cast<double*>(smem + p.off_xc);
     double* pa_s = reinterpret_cast<double*>(smem + p.off_pa);   // [GH][TN][D+1] (GH > 1 only)
     double* vred = reinterpret_cast<double*>(smem + p.off_vred); // [WC][TN]
+    double* hts = reinterpret_cast<double*>(smem + p.off_hts);   // HESS: [TN][D] centred scaled test rows
+    __shared__ int htab[HESS ? 256 : 1];                         // HESS: (d, e) -> d | e << 8 | column << 16
+    __shared__ double cen_s[HESS ? kMaxD : 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = p.D, M = p.M, Mp = p.Mp;
@@ -89,6 +120,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
 
     const int64_t ntiles = (p.N + TN - 1) / TN;
     const bool want_var = (p.var != nullptr);
+    const bool want_hess = HESS && (p.hess != nullptr);
+    // ring iterations per tile: [0, nit_b) stream invQ for phase B, [nit_b, nit_tot) stream P for phase C
+    const int nit_b = want_var ? p.nit : 0;
+    const int nit_tot = nit_b + (want_hess ? p.nit_h : 0);
     const bool alias_x = p.alias_x != 0;
     // bulk copies need 16-byte aligned sources; row blocks of full tiles are multiples of 64 bytes
     const bool ts_tma_ok = (reinterpret_cast<uintptr_t>(p.testing) & 15) == 0;
@@ -106,6 +141,14 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         fence_mbar_init();
     }
     if (tid < kMaxD) sqw_s[tid] = p.sqrt_w[tid];
+    if (HESS) {
+        if (tid < kMaxD) cen_s[tid] = p.centre[tid];
+        for (int e = tid; e < p.D * p.D; e += NTHR) {
+            const int d1 = e / p.D, d2 = e - d1 * p.D;
+            const int lo = min(d1, d2), hi = max(d1, d2);
+            htab[e] = d1 | (d2 << 8) | ((lo * p.D - lo * (lo - 1) / 2 + hi - lo) << 16);
+        }
+    }
     // zero the K* columns [M, Mp + 4): phase A never writes them, phase B multiplies them by zero rows of invQ
     for (int r = warp; r < TN; r += NW)
         for (int c = M + lane; c < pitch; c += 32) Ks[r * pitch + c] = 0.0;
@@ -121,6 +164,13 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     int cs = 0;
     uint32_t cpar = 0;
     auto issue = [&](int stage, int it_local) {  // k-blocks [KB * it_local, +KB) -> ring stage
+        if (HESS && it_local >= nit_b) {             // phase C operand: k-blocks [kbh * (it_local - nit_b), +kbh) of P
+            const int kb0 = (it_local - nit_b) * p.kbh;
+            const uint32_t bytes = (uint32_t)min(p.kbh, p.kblk - kb0) * (uint32_t)NC * 32u;
+            mbar_arrive_expect_tx(&bar_full[stage], bytes);
+            tma_bulk_g2s(Bst + (size_t)stage * p.stage_bytes, p.p_tiled + (size_t)kb0 * NC * 4, bytes, &bar_full[stage]);
+            return;
+        }
         const int kb0 = it_local * KB;
         const int nkb = min(KB, p.kblk - kb0);
         unsigned char* dst = Bst + (size_t)stage * p.stage_bytes;
@@ -142,10 +192,18 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     };
     auto issue_burst = [&]() {
         int s = cs;
-        const int burst = min(nstage, p.nit);
+        const int burst = min(nstage, nit_tot);
         for (int i = 0; i < burst; ++i) {
             issue(s, i);
             if (++s == nstage) s = 0;
+        }
+    };
+    auto refill = [&](int it) {   // called by every thread at the top of ring iteration `it` of the tile
+        if (it >= lag && lane == 0 && warp == (it & (NW - 1)) && it - lag + nstage < nit_tot) {
+            const int ps = (cs >= lag) ? cs - lag : cs - lag + nstage;   // stage of iteration it - lag
+            const uint32_t ppar = (cs >= lag) ? cpar : (cpar ^ 1);      // parity of that use
+            mbar_wait(&bar_empty[ps], ppar);
+            issue(ps, it - lag + nstage);
         }
     };
     uint32_t xpar = 0;
@@ -186,7 +244,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
         GPE_TRACE(0);
         // B-operand prefetch for this tile's contraction lands while phase A runs (unless the buffers are shared)
-        if (want_var && !alias_x && tid == 0) issue_burst();
+        if (nit_tot > 0 && !alias_x && tid == 0) issue_burst();
 
         // ---- this tile's test rows: prefetched by TMA during the previous tile, or loaded in-line ------------
         if (rows_prefetched(tile)) {
@@ -205,6 +263,14 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         for (int d = 0; d < DP; ++d) {
             tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
             tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
+        }
+        if (HESS && want_hess && g_hi == 0) {   // the 8 training-point lanes of a row share its D stores
+#pragma unroll
+            for (int d = 0; d < DP; ++d)
+                if ((d & 7) == g_low && d < D) {
+                    hts[n_a * D + d] = tsa[d] - cen_s[d];
+                    hts[n_b * D + d] = tsb[d] - cen_s[d];
+                }
         }
         // phase-A chunk 0 (unless resident) is requested before the barrier so its latency overlaps the barrier
         if (!x_resident && tid == 0) {
@@ -330,6 +396,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         }
 
         GPE_TRACE(3);
+        if (alias_x && nit_tot > 0 && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
         // ---- phase B: variance contraction on the FP64 tensor path --------------------------------------
         if (want_var) {
             double acc[MT][NT][2];
@@ -343,16 +410,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             // (keeps the warps balanced when SYM skips the tiles below the diagonal)
             const int b_off = (wcol * 8 + (lane >> 2)) * 4 + (lane & 3);
 
-            if (alias_x && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
             // KB k-blocks (4 values of the contraction index each) per ring stage, fully unrolled.  The A fragments
             // come from the K* tile, not from the ring, so they are fetched before waiting on the stage barrier.
-            for (int it = 0; it < p.nit; ++it) {
-                if (it >= lag && lane == 0 && warp == (it & (NW - 1)) && it - lag + nstage < p.nit) {
-                    const int ps = (cs >= lag) ? cs - lag : cs - lag + nstage;   // stage of iteration it - lag
-                    const uint32_t ppar = (cs >= lag) ? cpar : (cpar ^ 1);      // parity of that use
-                    mbar_wait(&bar_empty[ps], ppar);
-                    issue(ps, it - lag + nstage);
-                }
+            for (int it = 0; it < nit_b; ++it) {
+                refill(it);
                 const int kb0 = it * KB;
                 double a[KB][MT];
 #pragma unroll
@@ -427,8 +488,82 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 p.var[(n0 + tid) * p.ld_var] = p.b - p.b * p.b * v;
             }
         }
+        // ---- phase C: Hessian of the mean, S2 = K* . P on the tensor path -------------------------------
+        if (HESS && want_hess) {
+            GPE_TRACE(5);
+            const int mt = warp % NMT, cg = warp / NMT;
+            double hacc[NTH][2];
+#pragma unroll
+            for (int j = 0; j < NTH; ++j) hacc[j][0] = hacc[j][1] = 0.0;
+            const double* a_base = Ks + (mt * 8 + (lane >> 2)) * pitch + (lane & 3);
+            const int b_off = (cg * 8 + (lane >> 2)) * 4 + (lane & 3);
+            for (int it = nit_b; it < nit_tot; ++it) {
+                refill(it);
+                const int kb0 = (it - nit_b) * p.kbh;
+                const int nkb = min(p.kbh, p.kblk - kb0);
+                mbar_wait(&bar_full[cs], cpar);
+                const double* bs = reinterpret_cast<const double*>(Bst + (size_t)cs * p.stage_bytes) + b_off;
+                const double* ap = a_base + kb0 * 4;
+#pragma unroll 3
+                for (int kk = 0; kk < nkb; ++kk) {
+                    const double a = ap[kk * 4];
+                    const double* bk = bs + kk * (NC * 4);
+#pragma unroll
+                    for (int j = 0; j < NTH; ++j) {
+                        if (NCT % CG != 0 && cg + CG * j >= NCT) break;
+                        dmma_m8n8k4(hacc[j][0], hacc[j][1], a, bk[j * (CG * 32)]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[cs]);
+                if (++cs == nstage) { cs = 0; cpar ^= 1; }
+            }
+            GPE_TRACE(6);
+            __syncthreads();  // every warp is done with the K* tile: its rows now stage S2 ([TN][NC], pitch as K*)
+#pragma unroll
+            for (int j = 0; j < NTH; ++j) {
+                if (cg + CG * j < NCT)
+                    *reinterpret_cast<double2*>(Ks + (mt * 8 + (lane >> 2)) * pitch + (cg + CG * j) * 8 + 2 * (lane & 3)) =
+                        make_double2(hacc[j][0], hacc[j][1]);
+            }
+            __syncthreads();
+            // H_de = sqrt(w_d w_e) (S2_de - t'_d g_e - t'_e g_d - t'_d t'_e S0) - [d == e] w_d S0; a warp writes whole
+            // (D x D) blocks, consecutive lanes consecutive addresses
+            // A lane owns the same (d, e) elements in every row, so their indices and weights are fetched once per
+            // tile; the row loop then has NE independent load / FMA chains in flight.
+            constexpr int NE = (DP * DP + 31) / 32;
+            const int DD = D * D;
+            int o1[NE], o2[NE], oc[NE];
+            double ow[NE], od[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                const int e = min(lane + 32 * i, DD - 1);
+                const int t = htab[e];
+                o1[i] = t & 255; o2[i] = (t >> 8) & 255; oc[i] = t >> 16;
+                ow[i] = sqw_s[o1[i]] * sqw_s[o2[i]];
+                od[i] = (o1[i] == o2[i]) ? ow[i] : 0.0;
+            }
+#pragma unroll 2
+            for (int r = warp; r < npts; r += NW) {
+                const double* s2 = Ks + r * pitch;
+                const double* tp = hts + r * D;
+                const double* g = outs + r * DV + 1;
+                const double s0 = outs[r * DV];
+                double* dst = p.hess + (n0 + r) * p.ld_hess;
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const double t1 = tp[o1[i]], t2 = tp[o2[i]];
+                    double v = s2[oc[i]];
+                    v = fma(-t1, g[o2[i]], v);
+                    v = fma(-t2, fma(t1, s0, g[o1[i]]), v);
+                    v = fma(v, ow[i], -od[i] * s0);
+                    if (lane + 32 * i < DD) dst[lane + 32 * i] = v;
+                }
+            }
+            GPE_TRACE(7);
+        }
         __syncthreads();  // K*, outs, vred (and the ring, if it doubles as chunk buffer) are free for the next tile
-        GPE_TRACE(5);
+        if (!(HESS && want_hess)) GPE_TRACE(5);
         ++trace_tile;
     }
 }

@@ -16,10 +16,21 @@ namespace gpe {
 
 template <int MT, int NT, int WR, int WC, int MINB, int KB>
 static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = p.symmetric ? ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, true>
-                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, true>)
-                            : ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false>
-                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false>);
+    auto kern = p.symmetric ? ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, true, false>
+                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, true, false>)
+                            : ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, false>
+                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, false>);
+#if GPE_DP <= 16
+    // fused Hessian variants (gpemu.cu only asks for them when cfg <= 2 and the model is not symmetric-folded)
+    if (p.hess != nullptr) {
+        if (p.symmetric || MINB != 1 || WR * WC != 8) return cudaErrorInvalidValue;
+        if constexpr (MINB == 1 && WR * WC == 8)
+            kern = (p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, true>
+                                    : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, true>;
+    }
+#else
+    if (p.hess != nullptr) return cudaErrorInvalidValue;
+#endif
     // per function AND per device: set on every launch (microseconds) so multi-device processes stay correct
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -378,6 +378,80 @@ def test_hessian_large_d(gpemu, M, D, N):
     assert orc.ref_err(out["hess"], orc.hessian(inputs, theta, invQt, testing)) < TOL
 
 
+@pytest.mark.parametrize("M,D,N", [(250, 10, 333), (96, 4, 65), (60, 2, 64), (400, 7, 100), (1000, 10, 50), (200, 16, 77),
+                                   (180, 12, 130), (57, 10, 40)])
+def test_fused_hessian(gpemu, M, D, N):
+    """mean + variance + gradient + Hessian in one launch: the Hessian is a second tensor-path contraction against
+    the K* tile (predict_full.cuh phase C).  Reference GaussianProcess.py:345-366 for the values."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    before = gpemu._lib.load().gpe_launch_count()
+    out = m.predict(testing, want_hess=True)
+    assert gpemu._lib.load().gpe_launch_count() - before == 1
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    assert orc.ref_err(out["mu"], mu) < TOL and orc.ref_err(out["var"], var) < TOL
+    assert orc.ref_err(out["deriv"], deriv) < TOL
+    ho = orc.hessian(inputs, theta, invQt, testing)
+    assert orc.ref_err(out["hess"], ho) < TOL
+    h = m.predict(testing, want_mu=False, want_var=False, want_deriv=False, want_hess=True)["hess"]
+    assert orc.ref_err(h, ho) < TOL
+
+
+def test_fused_hessian_fallbacks(gpemu):
+    """Shapes / data the fused Hessian does not take fall back to the direct kernel (two launches), same values:
+    fewer training points than Hessian columns, symmetric-folded variance operand, inputs spanning so many length
+    scales that the centred expansion would cancel digits."""
+    lib = gpemu._lib.load()
+    cases = []
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(40, 10, 50, seed=1)          # NC = 56 > M
+    cases.append((gpemu.DeviceModel(inputs, theta, invQt, invQ), inputs, theta, invQ, invQt, testing))
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 50, seed=2)
+    cases.append((gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=True), inputs, theta, invQ, invQt, testing))
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 50, seed=3)
+    theta = theta.copy(); theta[0] += np.log(1.0e6)                                      # 1000x shorter length scale in d = 0
+    invQ, invQt = orc.prepare_likelihood(inputs, np.sin(inputs.sum(1)), theta)
+    testing = inputs[:50] + 1e-4
+    cases.append((gpemu.DeviceModel(inputs, theta, invQt, invQ), inputs, theta, invQ, invQt, testing))
+    for m, inputs, theta, invQ, invQt, testing in cases:
+        before = lib.gpe_launch_count()
+        out = m.predict(testing, want_hess=True)
+        assert lib.gpe_launch_count() - before == 2
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+        assert orc.ref_err(out["mu"], mu) < TOL and orc.ref_err(out["var"], var) < 1e-9
+        assert orc.ref_err(out["hess"], orc.hessian(inputs, theta, invQt, testing)) < TOL
+
+
+def test_fused_hessian_short_length_scales(gpemu):
+    """Training inputs spanning +-30 length scales in every dimension: still inside the fused path's guard
+    (max |x'|^2 = 900 <= 2000); the cancellation of the centred expansion must stay far below the bar."""
+    lib = gpemu._lib.load()
+    rs = np.random.RandomState(11)
+    M, D = 250, 6
+    inputs = rs.random_sample((M, D))
+    theta = np.concatenate([np.full(D, np.log(3600.0)), [0.3, -6.0]])
+    invQ, invQt = orc.prepare_likelihood(inputs, np.sin(4 * inputs.sum(1)), theta)
+    testing = inputs[:200] + 0.01 * rs.standard_normal((200, D))
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    before = lib.gpe_launch_count()
+    out = m.predict(testing, want_hess=True)
+    assert lib.gpe_launch_count() - before == 1
+    ho = orc.hessian(inputs, theta, invQt, testing)
+    assert np.abs(ho).max() > 1.0
+    assert orc.ref_err(out["hess"], ho) < TOL
+
+
+def test_fused_hessian_offset_inputs(gpemu):
+    """Inputs far from the origin: the centring of the fused expansion must keep the error at the level of the
+    direct formula (which itself is limited by the conditioning of x - t at |x| ~ 1e3)."""
+    inputs, theta, _, _, testing = orc.make_S_model(250, 10, 200, seed=5)
+    inputs = inputs + 1000.0
+    testing = testing + 1000.0
+    invQ, invQt = orc.prepare_likelihood(inputs, np.sin(inputs.sum(1)), theta)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    out = m.predict(testing, want_hess=True)
+    assert orc.ref_err(out["hess"], orc.hessian(inputs, theta, invQt, testing)) < 1e-10
+
+
 def test_inplace_edit_needs_invalidate(gpemu):
     inputs, theta, invQ, invQt, testing = orc.make_S_model(64, 4, 50, seed=2)
     gp = gpemu.GaussianProcess(inputs, [])
