@@ -1071,6 +1071,19 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
             if (rc) return rc;
         }
         if (fuse_hess) hess = nullptr;
+    } else if (hess != nullptr && N >= 16384) {
+        // Hessian without variance on a large batch: per-emulator fused launches (phase A + phase C) beat the
+        // one-launch direct kernel when every emulator qualifies and tiles are 64 points (cfg 0)
+        bool fuse_hess = true;
+        for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok && b->models[e]->full.cfg == 0;
+        if (fuse_hess) {
+            for (int64_t e = 0; e < E; ++e) {
+                int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, nullptr, deriv ? deriv + e * D : nullptr,
+                                        hess + e * D * D, E, E, E * D, E * D * D, (cudaStream_t)stream);
+                if (rc) return rc;
+            }
+            return GPE_OK;
+        }
     }
     if (hess != nullptr || (!with_var && (mu != nullptr || deriv != nullptr))) {
         // mean / gradient / Hessian of ALL emulators in one launch (blockIdx.y = emulator)
