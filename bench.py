@@ -288,17 +288,20 @@ def main():
         sym = gpe.DeviceModel(model["inputs"], model["theta"], model["invQt"], model["invQ"], device=local_rank,
                               symmetric_variance=True)
         t32 = tv.to(torch.float32)
+        nh = min(nv, 4_000_000)   # the (N, D, D) Hessian output is 800 B per point
+        hout = {"hess": torch.empty(nh, D, D, dtype=torch.float64, device=tv.device)}
         variants = {
             "points": nv,
             "fp64_symmetric_variance_points_per_s": _rate(lambda: sym.predict(tv), nv),
             "fp32_3xtf32_tcgen05_points_per_s": _rate(lambda: dm.predict_f32(t32), nv),
             "fp32_1xtf32_tcgen05_points_per_s": _rate(lambda: dm.predict_f32(t32, fast=True), nv),
             "fp64_mean_gradient_only_points_per_s": _rate(lambda: dm.predict(tv, want_var=False), nv),
+            "fp64_with_hessian_points_per_s": _rate(lambda: dm.predict(tv[:nh], want_hess=True, out=hout), nh),
             "note": "same model and test points; symmetric = opt-in upper-triangular fold of invQ (exact identity, "
-                    "half the DMMAs); tf32 = single precision with the variance contraction on tcgen05/TMEM (3x split: var error "
+                    "half the DMMAs); with_hessian = mean + variance + gradient + (N, D, D) Hessian in one fused launch; tf32 = single precision with the variance contraction on tcgen05/TMEM (3x split: var error "
                     "~3e-6, meets the reference FP32 bar 1e-5; 1x: ~6e-5)",
         }
-        del sym, t32, tv
+        del sym, t32, tv, hout
     if rank == 0:
         from oracle import gp_oracle as orc
         mu_o, var_o, _ = orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], t_head)
