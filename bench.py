@@ -58,8 +58,14 @@ def workload_config(n_points):
 
 
 def synthetic_model():
-    from oracle.gp_oracle import make_S_model   # input generator only (tests/benchmark.py:11-15 recipe)
-    inputs, theta, invQ, invQt, _ = make_S_model(M, D, 1, seed=0)
+    # the reference benchmark's recipe (tests/benchmark.py:11-15, 28-29): everything U(0, 1), drawn in the order
+    # inputs, testing, theta, invQ, invQt; legacy RandomState so the stream is the same on every numpy
+    rs = np.random.RandomState(0)
+    inputs = rs.random_sample((M, D))
+    rs.random_sample((1, D))
+    theta = rs.random_sample(D + 2)
+    invQ = rs.random_sample((M, M))
+    invQt = rs.random_sample(M)
     return {"inputs": inputs, "theta": theta, "invQ": invQ, "invQt": invQt}
 
 
@@ -188,6 +194,8 @@ def main():
     # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) off it
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    # one process per GPU: keep each rank (and the page-locked buffers it touches first) on its GPU's NUMA node
+    numa_cpus = sharding.bind_host_to_gpu(local_rank) if (world > 1 and not os.environ.get("GPE_NO_NUMA_BIND")) else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     model = synthetic_model() if rank == 0 else None
@@ -334,6 +342,7 @@ def main():
             "e2e": {"value": Ne * world * args.steps / e2e_s, "unit": "points/s",
                     "h2d_bytes_per_step": Ne * D * 8, "d2h_bytes_per_step": Ne * (2 + D) * 8,
                     "points_per_gpu_per_step": Ne,
+                    "host_numa_binding": ("rank pinned to the %d CPUs local to its GPU" % len(numa_cpus)) if numa_cpus else None,
                     "api": "GaussianProcess.predict(numpy pinned in, preallocated pinned out) -> libgpemu two-slot stream pipeline"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

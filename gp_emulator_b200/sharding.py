@@ -20,6 +20,35 @@ def shard_range(N, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPUs that are NUMA-local to GPU ``device_index`` (NVML's CPU affinity mask).
+
+    With one process per GPU every rank streams its own test points host -> device and results back; page-locked
+    buffers are placed by first touch, so a rank that runs on the far socket pushes all of its PCIe traffic across
+    the inter-socket link.  Call this before allocating host buffers.  Returns the CPU list, or None when NVML or
+    the affinity call is unavailable (nothing is changed then).
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in cpus if c in allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def broadcast_model(model, src=0, device=None):
     """Broadcast a dict of float64 numpy arrays (the trained model) from ``src`` to every rank.
 

@@ -92,3 +92,13 @@ def test_shard_range_partitions(N, world):
     assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
     sizes = [b - a for a, b in ranges]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_bind_host_to_gpu_is_a_noop_without_nvml_device():
+    """No GPU here: the NUMA helper must report None and leave the affinity mask alone."""
+    import os
+    from gp_emulator_b200 import sharding
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_host_to_gpu(0) is None or os.sched_getaffinity(0) <= before
+    if sharding.bind_host_to_gpu(0) is None:
+        assert os.sched_getaffinity(0) == before
