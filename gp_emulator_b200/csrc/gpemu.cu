@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cmath>
 #include <mutex>
 #include <string>
@@ -113,7 +116,7 @@ struct gpe_model {
     uint32_t* d_bslabs_lo = nullptr;
     std::vector<double> h_inputs, h_invQt, h_invQ;  // host copy of the model for the lazy FP32 packing
     double h_expx[33];
-    Slot slots[2];
+    Slot slots[3];               // host-streaming pipeline: the direct (pinned caller) path uses two, the staged path three
 };
 
 struct gpe_multi {
@@ -430,29 +433,90 @@ int ensure(double** ptr, size_t* cap, size_t need, bool host) {
     return GPE_OK;
 }
 
-// Staging copies for pageable callers: one core moves ~10 GB/s, the PCIe link 55 GB/s each way, so large copies
-// are split over a few threads (spawned per chunk: tens of microseconds against milliseconds of copy).
-void par_memcpy(void* dst, const void* src, size_t bytes) {
-    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), bytes / (2u << 20));
-    if (nt <= 1) {
-        memcpy(dst, src, bytes);
-        return;
+// Staging copies for pageable callers.  One core moves ~14 GB/s on the GPU boxes, eight ~50 GB/s, and the PCIe link
+// 55 GB/s each way, so copies of 1 MB and more are split into >= 256 KB pieces over a small persistent pool (created on first use;
+// the submitting thread takes a share of the pieces itself).  Several threads may submit at once: the staged pipeline
+// copies results out on its own thread while the caller's thread stages the next inputs.
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool pool;
+        return pool;
     }
-    std::vector<std::thread> th;
-    const size_t part = (bytes / nt + 63) & ~(size_t)63;
-    for (unsigned i = 1; i < nt; ++i) {
-        const size_t off = (size_t)i * part;
-        if (off >= bytes) break;
-        const size_t len = std::min(part, bytes - off);
-        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    void copy(void* dst, const void* src, size_t bytes) {
+        constexpr size_t kPiece = 256u << 10;   // waking a worker costs tens of microseconds: not worth it below 1 MB
+        const size_t want = bytes >= 4 * kPiece ? bytes / kPiece : 1;
+        const unsigned np = (unsigned)std::min<size_t>(workers_.size() + 1, std::max<size_t>(want, 1));
+        if (np <= 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t part = (bytes / np + 63) & ~(size_t)63;
+        Batch batch;
+        unsigned queued = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (unsigned i = 1; i < np; ++i) {
+                const size_t off = (size_t)i * part;
+                if (off >= bytes) break;
+                q_.push_back(Task{(char*)dst + off, (const char*)src + off, std::min(part, bytes - off), &batch});
+                ++queued;
+            }
+            batch.remaining = (int)queued;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(part, bytes));
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return batch.remaining == 0; });
     }
-    memcpy(dst, src, std::min(part, bytes));
-    for (auto& t : th) t.join();
-}
 
-// Host-resident caller: stream chunks through two slots so the H2D copy of chunk i+1, the kernels of chunk i
-// and the D2H copy of chunk i-1 overlap.  Pinned caller buffers are DMA'd directly; pageable ones are staged.
+private:
+    struct Batch { int remaining = 0; };
+    struct Task { char* dst; const char* src; size_t len; Batch* batch; };
+    CopyPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n = std::min(7u, std::max(1u, hw / 2) - (hw >= 4 ? 1u : 0u));
+        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run() {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+            if (stop_) return;
+            Task t = q_.front();
+            q_.pop_front();
+            lk.unlock();
+            memcpy(t.dst, t.src, t.len);
+            lk.lock();
+            if (--t.batch->remaining == 0) done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::deque<Task> q_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    bool stop_ = false;
+};
+
+void par_memcpy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
+
+// Host-resident caller: stream chunks through a few slots so the H2D copy of chunk i+1, the kernels of chunk i and
+// the D2H copy of chunk i-1 overlap.
+//   pinned caller buffers   : DMA'd directly, two slots, 2^18-point chunks;
+//   pageable caller buffers : staged through page-locked slot buffers.  The caller's thread stages inputs and
+//                             enqueues (copy-in -> H2D -> kernels -> D2H -> event), a second thread waits for each
+//                             chunk's event and copies its results out, both copying through the CopyPool; three
+//                             slots keep the GPU busy while either side is late.  Chunks are about a quarter of the
+//                             call (whole waves of 64-point tiles, at most 2^18 points) so that mid-sized calls
+//                             (1e5 points) overlap too.
 // T = double (FP64 path) or float (single-precision path); `launch(d_in, n, d_mu, d_var, d_deriv, d_hess, stream)`
 // enqueues the kernels for one chunk.
 template <typename T, typename Launch>
@@ -462,8 +526,15 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
     const int64_t per_out = (mu ? 1 : 0) + (var ? 1 : 0) + (deriv ? D : 0) + (hess ? (int64_t)D * D : 0);
     const bool direct = is_pinned_or_null(testing) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
                         is_pinned_or_null(deriv) && is_pinned_or_null(hess);
-    const int64_t CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(N, 1));
-    for (auto& s : m->slots) {
+    int64_t CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(N, 1));
+    if (!direct) {
+        const int64_t wave = 64 * (int64_t)m->sms;
+        CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(2 * wave, ((N + 3) / 4 + wave - 1) / wave * wave));
+        if (N <= 3 * wave) CH = std::max<int64_t>(N, 1);   // too small to be worth a second thread
+    }
+    const int ns = direct ? 2 : 3;
+    for (int i = 0; i < ns; ++i) {
+        Slot& s = m->slots[i];
         if (!s.st) CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         int rc = ensure(&s.d_in, &s.d_in_cap, (size_t)CH * D * ES, false);
@@ -478,53 +549,121 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         }
         s.pending = false;
     }
-    auto drain = [&](Slot& s) -> int {
-        if (!s.pending) return GPE_OK;
-        CUDA_TRY(cudaEventSynchronize(s.done));
+    struct Outs { T *mu, *var, *der, *hes; };
+    auto carve = [&](Slot& s, int64_t n) {
+        T* o = reinterpret_cast<T*>(s.d_out);
+        Outs r;
+        r.mu = mu ? o : nullptr;    if (mu) o += n;
+        r.var = var ? o : nullptr;  if (var) o += n;
+        r.der = deriv ? o : nullptr; if (deriv) o += n * D;
+        r.hes = hess ? o : nullptr;
+        return r;
+    };
+    if (direct) {
+        int which = 0;
+        for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
+            Slot& s = m->slots[which];
+            const int64_t n = std::min(CH, N - n0);
+            T* const d_in = reinterpret_cast<T*>(s.d_in);
+            const Outs o = carve(s, n);
+            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
+            int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
+            if (rc) return rc;
+            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, o.mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, o.var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, o.der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
+            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, o.hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
+        }
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(m->slots[i].st));
+        return GPE_OK;
+    }
+
+    // ---- staged path ---------------------------------------------------------------------------------------
+    static const bool pipe_trace = getenv("GPE_PIPE_TRACE") != nullptr;   // dev aid: host-side time split of a call
+    double t_wait = 0, t_out = 0, t_in = 0, t_block = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    auto copy_out = [&](Slot& s) -> cudaError_t {   // wait for the slot's chunk, then scatter its results to the caller
+        double t0 = now();
+        cudaError_t e = cudaEventSynchronize(s.done);
+        if (e != cudaSuccess) return e;
+        t_wait += now() - t0; t0 = now();
         const int64_t n0 = s.pend_n0, n = s.pend_n;
         const T* src = reinterpret_cast<const T*>(s.h_out);
         if (mu) { par_memcpy(mu + n0, src, (size_t)n * ES); src += n; }
         if (var) { par_memcpy(var + n0, src, (size_t)n * ES); src += n; }
         if (deriv) { par_memcpy(deriv + n0 * D, src, (size_t)n * D * ES); src += n * D; }
         if (hess) { par_memcpy(hess + n0 * D * D, src, (size_t)n * D * D * ES); }
-        s.pending = false;
+        t_out += now() - t0;
+        return cudaSuccess;
+    };
+    auto stage_in = [&](Slot& s, int64_t n0, int64_t n) -> int {   // copy-in + enqueue of one chunk on the slot
+        double t0 = now();
+        par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
+        t_in += now() - t0;
+        T* const d_in = reinterpret_cast<T*>(s.d_in);
+        const Outs o = carve(s, n);
+        CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
+        int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
+        CUDA_TRY(cudaEventRecord(s.done, s.st));
+        s.pend_n0 = n0; s.pend_n = n;
         return GPE_OK;
     };
-    int which = 0;
-    for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
-        Slot& s = m->slots[which];
-        const int64_t n = std::min(CH, N - n0);
-        T* const d_in = reinterpret_cast<T*>(s.d_in);
-        T* o = reinterpret_cast<T*>(s.d_out);
-        T* d_mu = mu ? o : nullptr;   if (mu) o += n;
-        T* d_var = var ? o : nullptr; if (var) o += n;
-        T* d_der = deriv ? o : nullptr; if (deriv) o += n * D;
-        T* d_hes = hess ? o : nullptr;
-        if (direct) {
-            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
-        } else {
-            int rc = drain(s);  // the slot's previous results must leave the staging buffer first
-            if (rc) return rc;
-            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
-            CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
-        }
-        int rc = launch(d_in, n, d_mu, d_var, d_der, d_hes, s.st);
+    const int64_t nchunks = (N + CH - 1) / CH;
+    int rc = GPE_OK;
+    if (nchunks == 1) {
+        rc = stage_in(m->slots[0], 0, N);
         if (rc) return rc;
-        if (direct) {
-            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, d_mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, d_var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, d_der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
-            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, d_hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
-            CUDA_TRY(cudaEventRecord(s.done, s.st));
-            s.pending = true; s.pend_n0 = n0; s.pend_n = n;
+        CUDA_TRY(copy_out(m->slots[0]));
+    } else {
+        // chunk c lives in slot c % 3.  `staged` / `drained` count chunks handed to / finished by the output thread.
+        std::mutex mx;
+        std::condition_variable cv;
+        int64_t staged = 0, drained = 0;
+        bool abort = false;
+        cudaError_t out_err = cudaSuccess;
+        const int device = m->device;
+        std::thread out_thread([&] {
+            cudaSetDevice(device);
+            for (int64_t c = 0; c < nchunks; ++c) {
+                {
+                    std::unique_lock<std::mutex> lk(mx);
+                    cv.wait(lk, [&] { return staged > c || abort; });
+                    if (staged <= c) return;
+                }
+                const cudaError_t e = copy_out(m->slots[c % 3]);
+                std::lock_guard<std::mutex> lk(mx);
+                if (e != cudaSuccess) { out_err = e; abort = true; cv.notify_all(); return; }
+                drained = c + 1;
+                cv.notify_all();
+            }
+        });
+        for (int64_t c = 0; c < nchunks && rc == GPE_OK; ++c) {
+            {
+                const double t0 = now();
+                std::unique_lock<std::mutex> lk(mx);
+                cv.wait(lk, [&] { return drained + 3 > c || abort; });   // the slot's previous chunk has left it
+                if (abort) break;
+                t_block += now() - t0;
+            }
+            const int64_t n0 = c * CH;
+            rc = stage_in(m->slots[c % 3], n0, std::min(CH, N - n0));
+            std::lock_guard<std::mutex> lk(mx);
+            if (rc == GPE_OK) staged = c + 1; else abort = true;
+            cv.notify_all();
         }
+        out_thread.join();
+        if (rc) {                     // stage_in failed: the error text is already set on this thread
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        if (out_err != cudaSuccess) return fail(GPE_ERR_CUDA, "result copy-out failed: %s", cudaGetErrorString(out_err));
     }
-    for (auto& s : m->slots) {
-        if (direct) CUDA_TRY(cudaStreamSynchronize(s.st));
-        else { int rc = drain(s); if (rc) return rc; }
-    }
+    if (pipe_trace)
+        fprintf(stderr, "[gpemu pipe] N=%lld in %lld chunks of %lld: out-thread wait %.3f ms, copy-out %.3f ms | copy-in %.3f ms, "
+                        "caller blocked on a slot %.3f ms\n",
+                (long long)N, (long long)nchunks, (long long)CH, t_wait * 1e3, t_out * 1e3, t_in * 1e3, t_block * 1e3);
     return GPE_OK;
 }
 

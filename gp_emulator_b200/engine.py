@@ -3,7 +3,7 @@
 ``DeviceModel`` is one trained GP on one GPU, ``DeviceBank`` is E GPs that share training inputs and test
 points (the per-PC emulators of a MultivariateEmulator, or a per-band bank).  Test points may be
 
-* numpy arrays (host): the library streams them through its pinned two-slot pipeline and the results
+* numpy arrays (host): the library streams them through its chunked host pipeline and the results
   come back as numpy arrays; or
 * torch CUDA tensors (device): the call is asynchronous on torch's current stream and the results are
   torch CUDA tensors -- PyTorch is used only to own the device buffers.

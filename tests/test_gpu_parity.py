@@ -157,6 +157,46 @@ def test_pageable_and_pinned_host_paths_multi_chunk(gpemu):
     assert orc.ref_err(a["deriv"][idx], deriv) < TOL
 
 
+def test_staged_pipeline_chunk_seams(gpemu):
+    """Pageable callers go through the three-slot staged pipeline (copy-in thread / GPU / copy-out thread).  Sizes
+    around its chunking decisions must give bit-identical results to the device-resident call, repeatedly (slot
+    reuse across calls), for every output combination."""
+    import torch
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(64, 5, 1, seed=9)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    lib = gpemu._lib.load()
+    wave = 64 * torch.cuda.get_device_properties(0).multi_processor_count
+    rs = np.random.RandomState(2)
+    for N in (1, 3 * wave, 3 * wave + 1, 8 * wave - 1, 8 * wave, 12 * wave + 7, 4 * (1 << 18) + 1, 777_777):
+        testing = rs.random_sample((N, 5))
+        dev = m.predict(torch.from_numpy(testing).cuda(), want_hess=True)
+        torch.cuda.synchronize()
+        for rep in range(2):
+            host = m.predict(testing, want_hess=True)
+            for k in ("mu", "var", "deriv", "hess"):
+                assert np.array_equal(host[k], dev[k].cpu().numpy()), (N, rep, k)
+        h2 = m.predict(testing, want_mu=False, want_var=True, want_deriv=False)
+        assert set(h2) == {"var"} and np.array_equal(h2["var"], dev["var"].cpu().numpy())
+
+
+def test_staged_pipeline_concurrent_models(gpemu):
+    """Two models streaming pageable batches from two Python threads share the copy pool."""
+    import threading
+    res = {}
+    def work(seed):
+        inputs, theta, invQ, invQt, _ = orc.make_S_model(80, 4, 1, seed=seed)
+        testing = np.random.RandomState(seed).random_sample((400_000, 4))
+        m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+        out = m.predict(testing)
+        idx = np.r_[0:40, 200_000:200_040, 399_960:400_000]
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing[idx])
+        res[seed] = max(orc.ref_err(out["mu"][idx], mu), orc.ref_err(out["var"][idx], var), orc.ref_err(out["deriv"][idx], deriv))
+    th = [threading.Thread(target=work, args=(s,)) for s in (21, 22, 23)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert len(res) == 3 and max(res.values()) < TOL, res
+
+
 def test_preallocated_and_pinned_outputs(gpemu):
     import torch
     inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 7, 70000, seed=6)
@@ -502,7 +542,7 @@ def test_random_shape_sweep(gpemu):
 
 
 def test_single_precision_host_streaming_multi_chunk(gpemu):
-    """float32 host arrays go through the same two-slot pipeline as FP64: chunk seams must be invisible."""
+    """float32 host arrays go through the same host pipeline as FP64: chunk seams must be invisible."""
     import torch
     inputs, theta, invQ, invQt, _ = orc.make_S_model(96, 5, 1, seed=3)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
