@@ -264,11 +264,42 @@ class DeviceBank:
         as_numpy = not _is_torch(testing)
         dev = torch.device("cuda", self.device)
         if as_numpy:
-            t = torch.from_numpy(f64c(testing)).to(dev)
-        else:
-            t = testing.contiguous()
+            th = f64c(testing)
+            if th.ndim != 2 or th.shape[1] != D:
+                raise ValueError(f"testing must be float64 (N, {D})")
+            # host caller: bound the device footprint (fwd / deriv_full are W and D*W doubles per point) by walking
+            # the batch in chunks; results land directly in the numpy arrays that are returned
+            N = th.shape[0]
+            per_point = 8 * (E * (1 + (1 if want_var else 0) + (D if (want_deriv or project_deriv) else 0)
+                                  + (D * D if want_hess else 0))
+                             + (self.W if project else 0) + (D * self.W if project_deriv else 0))
+            chunk = max(1, min(N, self.host_chunk_bytes // max(per_point, 1)))
+            if N > chunk:
+                res = None
+                for s0 in range(0, N, chunk):
+                    part = self._predict_device(torch.from_numpy(th[s0:s0 + chunk]).to(dev), want_var, want_deriv,
+                                                want_hess, project, project_deriv)
+                    if res is None:
+                        res = {k: np.empty((N,) + tuple(v.shape[1:])) for k, v in part.items()}
+                    for k, v in part.items():
+                        torch.from_numpy(res[k][s0:s0 + chunk]).copy_(v)
+                    del part
+                return res
+            out = self._predict_device(torch.from_numpy(th).to(dev), want_var, want_deriv, want_hess, project,
+                                       project_deriv)
+            return {k: v.cpu().numpy() for k, v in out.items()}
+        t = testing.contiguous()
         if t.dim() != 2 or t.shape[1] != D or t.dtype != torch.float64:
             raise ValueError(f"testing must be float64 (N, {D})")
+        return self._predict_device(t, want_var, want_deriv, want_hess, project, project_deriv)
+
+    host_chunk_bytes = 1 << 30   # device bytes of results per chunk when the caller passes numpy arrays
+
+    def _predict_device(self, t, want_var, want_deriv, want_hess, project, project_deriv):
+        import torch
+        lib = _lib.load()
+        D, E = self.D, self.E
+        dev = t.device
         N = t.shape[0]
         mk = lambda *s: torch.empty(*s, dtype=torch.float64, device=dev)
         out = {"mu": mk(N, E)}
@@ -286,6 +317,4 @@ class DeviceBank:
             if project_deriv: out["deriv_full"] = mk(N, D, self.W)
             check(lib.gpe_bank_project(self._h, addr(out["mu"]), addr(out.get("deriv")), N, addr(out.get("fwd")),
                                        addr(out.get("deriv_full")), st))
-        if as_numpy:
-            out = {k: v.cpu().numpy() for k, v in out.items()}
         return out

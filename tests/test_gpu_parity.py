@@ -157,6 +157,27 @@ def test_pageable_and_pinned_host_paths_multi_chunk(gpemu):
     assert orc.ref_err(a["deriv"][idx], deriv) < TOL
 
 
+def test_bank_host_batches_are_chunked(gpemu):
+    """numpy callers of a bank get their batch walked in device-memory-bounded chunks (fwd / deriv_full are W and
+    D*W doubles per point): same values as the one-shot call, every output key, ragged last chunk."""
+    rs = np.random.RandomState(12)
+    M, D, E, W, N = 60, 4, 5, 300, 1037
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    basis = rs.standard_normal((E, W))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
+    t = rs.random_sample((N, D))
+    kw = dict(want_var=True, want_deriv=True, want_hess=True, project=True, project_deriv=True)
+    ref = bank.predict(t, **kw)
+    bank.host_chunk_bytes = 8 * 100 * (E * (2 + D + D * D) + W + D * W)     # 100 points per chunk
+    got = bank.predict(t, **kw)
+    assert set(got) == set(ref)
+    for k in ref:
+        assert got[k].shape == ref[k].shape and np.array_equal(got[k], ref[k]), k
+    fwd = bank.predict(t, want_var=False, want_deriv=False, project=True)["fwd"]
+    assert np.array_equal(fwd, ref["fwd"])
+
+
 def test_staged_pipeline_chunk_seams(gpemu):
     """Pageable callers go through the three-slot staged pipeline (copy-in thread / GPU / copy-out thread).  Sizes
     around its chunking decisions must give bit-identical results to the device-resident call, repeatedly (slot
