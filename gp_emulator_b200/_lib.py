@@ -18,7 +18,7 @@ WANT_MU, WANT_VAR, WANT_DERIV, WANT_HESS, HOST_PTRS = 0x01, 0x02, 0x04, 0x08, 0x
 OPT_SYMMETRIC_VARIANCE = 0x1
 F32_FAST_TF32 = 0x200
 F32_FORCE_3X = 0x400
-MAX_TRAIN, MAX_INPUTS = 1024, 32
+MAX_TRAIN, MAX_INPUTS = 4096, 32
 
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (

@@ -107,6 +107,12 @@ struct gpe_model {
     double* d_xchunks_full = nullptr;
     double* d_stiled = nullptr;
     double* d_ptiled = nullptr;  // Hessian operand of the fused kernel (null: direct Hessian kernel only)
+    // 1024 < M <= GPE_MAX_TRAIN: two-launch variance path (predict_var_large.cuh); d_stiled then has Mp / 4 k-blocks
+    bool large_valid = false;
+    int large_Mp = 0, large_kblk = 0, large_nstage = 0;
+    int64_t large_chunk = 0;             // points per sub-batch = capacity of the K* scratch
+    double* d_kscratch = nullptr;        // [large_chunk / 16][large_kblk][16][4], pads stay zero
+    cudaEvent_t scratch_free = nullptr;  // the scratch is shared by every stream that predicts with this model
     double centre[32];
     bool hess_fused_ok = false;
     double* d_xchunks_mean = nullptr;
@@ -359,6 +365,38 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     // request that only pays for the 64-point tiles of cfg 0 (measured: 4.6e8 vs 3.6e8 points/s at M = 250, but
     // 0.98e8 vs 1.10e8 at M = 1000), so larger M keeps the direct kernel for Hessian-only calls
     const bool fuse_hess = hess != nullptr && m->hess_fused_ok && (var != nullptr || m->full.cfg == 0);
+    if (var != nullptr && m->has_invQ && !m->full.valid && m->large_valid) {
+        // 1024 < M <= GPE_MAX_TRAIN: per sub-batch, K* + mean + gradient (k_predict_mean2<DP, true>) into the scratch,
+        // then the column-pass contraction (k_var_large).  The scratch is per model: streams take turns.
+        CUDA_TRY(cudaStreamWaitEvent(st, m->scratch_free, 0));
+        for (int64_t n0 = 0; n0 < N; n0 += m->large_chunk) {
+            const int64_t n = std::min(m->large_chunk, N - n0);
+            MeanParams p;
+            memset(&p, 0, sizeof(p));
+            p.testing = testing + n0 * m->D; p.N = n;
+            p.mu = mu ? mu + n0 * ld_mu : nullptr;
+            p.deriv = deriv ? deriv + n0 * ld_deriv : nullptr;
+            p.ld_mu = ld_mu; p.ld_deriv = ld_deriv;
+            p.xchunks = m->d_xchunks_mean; p.M = m->M; p.D = m->D; p.JC = m->mean.JC; p.nchunks = m->mean.nchunks;
+            p.off_xc = m->mean.off_xc; p.off_ts = m->mean.off_ts; p.off_out = m->mean.off_out;
+            p.kstar = m->d_kscratch; p.kblk = m->large_kblk;
+            memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
+            const int64_t mtiles = (n + kMeanTN - 1) / kMeanTN;
+            CUDA_TRY(launch_mean(m->DP, false, p, dim3((unsigned)std::min<int64_t>(mtiles, (int64_t)m->sms * 12)), m->mean.smem, st));
+            VarLargeParams v;
+            memset(&v, 0, sizeof(v));
+            v.kstar = m->d_kscratch; v.s_tiled = m->d_stiled; v.var = var + n0 * ld_var; v.ld_var = ld_var; v.N = n;
+            v.Mp = m->large_Mp; v.kblk = m->large_kblk; v.npass = (m->large_Mp + kVlPass - 1) / kVlPass;
+            v.nstage = m->large_nstage; v.b = m->b;
+            const size_t smem = 128 + kVlWarps * kVlTN * 8 + (size_t)v.nstage * kVlStageBytes;
+            const int64_t vtiles = (n + kVlTN - 1) / kVlTN;
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(launch_var_large(v, (int)std::min<int64_t>(vtiles, m->sms), smem, st));
+        }
+        CUDA_TRY(cudaEventRecord(m->scratch_free, st));
+        mean_done = true;
+        var = nullptr;
+    }
     if (var != nullptr || fuse_hess || (force_full && m->full.valid)) {
         if (var != nullptr && !m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
         if (!m->full.valid)
@@ -985,6 +1023,24 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
             if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
             rc = build_hessian_operand(m, inputs, invQt);
             if (rc) { gpe_model_destroy(m); return rc; }
+        } else if (M <= GPE_MAX_TRAIN) {
+            // beyond the fused kernel: s_tiled with the contraction padded to Mp (the K* scratch pads are zero)
+            m->large_Mp = (M + 63) / 64 * 64;
+            m->large_kblk = m->large_Mp / 4;
+            m->large_nstage = 6;
+            m->large_chunk = 16 * (int64_t)m->sms * 4;
+            const size_t Mp = (size_t)m->large_Mp;
+            std::vector<double> st((size_t)m->large_kblk * Mp * 4, 0.0);
+            for (int j = 0; j < M; ++j)
+                for (int i = 0; i < M; ++i) st[((size_t)(i >> 2) * Mp + j) * 4 + (i & 3)] = invQ[(size_t)j * M + i];
+            const size_t scratch = (size_t)(m->large_chunk / 16) * m->large_kblk * 64 * 8;
+            cudaError_t e = cudaMalloc((void**)&m->d_stiled, st.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_stiled, st.data(), st.size() * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_kscratch, scratch);
+            if (e == cudaSuccess) e = cudaMemset(m->d_kscratch, 0, scratch);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->scratch_free, cudaEventDisableTiming);
+            if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
+            m->large_valid = true;
         }
     }
     *out = m;
@@ -998,6 +1054,8 @@ int gpe_model_destroy(gpe_model* m) {
     if (m->d_xchunks_full) cudaFree(m->d_xchunks_full);
     if (m->d_stiled) cudaFree(m->d_stiled);
     if (m->d_ptiled) cudaFree(m->d_ptiled);
+    if (m->d_kscratch) cudaFree(m->d_kscratch);
+    if (m->scratch_free) cudaEventDestroy(m->scratch_free);
     if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
     if (m->d_xa_f32) cudaFree(m->d_xa_f32);
     if (m->d_bslabs) cudaFree(m->d_bslabs);

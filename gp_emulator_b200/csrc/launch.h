@@ -5,6 +5,7 @@
 #include "predict_mean.cuh"
 #include "predict_tf32.cuh"
 #include "predict_tf32_big.cuh"
+#include "predict_var_large.cuh"
 
 namespace gpe {
 
@@ -25,6 +26,7 @@ GPE_DECL_DP(32)
 
 cudaError_t launch_tf32(int DP, bool x3, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_tf32_big(int DP, bool x3, const Tf32BigParams& p, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_var_large(const VarLargeParams& p, int grid, size_t smem, cudaStream_t st);
 static const int kTfDpList[] = {4, 8, 12, 16, 32};
 
 // padded input dimensions that have compiled kernels, ascending

@@ -78,7 +78,8 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
     }
     // mean + gradient: two-rows-per-thread kernel (k_predict_mean2); GPE_MEAN_V1=1 selects the first version
     static const bool v1 = getenv("GPE_MEAN_V1") != nullptr;
-    auto kern = v1 ? k_predict_mean<GPE_DP, false> : k_predict_mean2<GPE_DP>;
+    auto kern = p.kstar != nullptr ? k_predict_mean2<GPE_DP, true>
+                                   : (v1 ? k_predict_mean<GPE_DP, false> : k_predict_mean2<GPE_DP, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kMeanThreads, smem, st>>>(p);

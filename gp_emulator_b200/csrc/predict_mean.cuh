@@ -37,6 +37,8 @@ struct MeanParams {
     double sqrt_w[32];
     const MeanBankEntry* bank;          // null: single GP.  Else gridDim.y emulators, outputs offset by e * eo_*
     int64_t eo_mu, eo_deriv, eo_hess;   // element offsets per emulator into the point-major bank outputs
+    double* kstar;                      // k_predict_mean2<DP, true>: K* scratch [ceil(N/16)][kblk][16][4] (predict_var_large.cuh)
+    int kblk;
 };
 
 template <int DP, bool HESS>
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
 // training points, every thread carries TWO test rows (each training row pulled from shared memory feeds two
 // pairs), training-row loads are software-pipelined one step ahead, and the 8 lanes are combined by a shuffle
 // reduce-scatter.  32 points per 128-thread CTA.
-template <int DP>
+// KSTAR: also store K* (without alpha) into the scratch consumed by k_var_large (M > 1024 variance path).
+template <int DP, bool KSTAR>
 __global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams p) {
     constexpr int TN = kMeanTN;
     constexpr int NV = DP + 1;
@@ -289,8 +292,15 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams
                         ra = fma(ua[d + 1], ua[d + 1], ra);
                         rb = fma(ub[d + 1], ub[d + 1], rb);
                     }
-                    const double ca = exp_neg(-0.5 * ra) * alj;
-                    const double cb = exp_neg(-0.5 * rb) * alj;
+                    const double ka = exp_neg(-0.5 * ra), kb = exp_neg(-0.5 * rb);
+                    if (KSTAR) {
+                        const int jg = c * p.JC + jl;
+                        const size_t col = ((size_t)(jg >> 2) * 16) * 4 + (jg & 3);
+                        const int64_t na = n0 + n_a, nb = n0 + n_b;
+                        p.kstar[((size_t)(na >> 4) * p.kblk * 16 + (na & 15)) * 4 + col] = ka;
+                        p.kstar[((size_t)(nb >> 4) * p.kblk * 16 + (nb & 15)) * 4 + col] = kb;
+                    }
+                    const double ca = ka * alj, cb = kb * alj;
                     va[0] += ca;
                     vb[0] += cb;
 #pragma unroll

@@ -417,14 +417,51 @@ def test_symmetric_variance_on_trained_model(gpemu):
 
 
 def test_documented_limits_raise_cleanly(gpemu):
-    """M > 1024 (variance) is reported as GPE_ERR_UNSUPPORTED, never a wrong answer."""
-    inputs, theta, invQ, invQt, testing = orc.make_S_model(1100, 3, 20, seed=1)
+    """M > GPE_MAX_TRAIN (variance) is reported as GPE_ERR_UNSUPPORTED, never a wrong answer."""
+    rs = np.random.RandomState(1)
+    M = 4100
+    inputs = rs.random_sample((M, 3)); theta = rs.random_sample(5); invQt = rs.random_sample(M)
+    invQ = rs.random_sample((M, M))
+    testing = rs.random_sample((20, 3))
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
-    with pytest.raises(gpemu.GpemuError, match="M <= 1024"):
+    with pytest.raises(gpemu.GpemuError, match="M <= 4096"):
         m.predict(testing)
     o = m.predict(testing, want_var=False)               # mean + gradient have no M limit
     mu, _, deriv = orc.predict(inputs, theta, invQ, invQt, testing, do_unc=False)
     assert orc.ref_err(o["mu"], mu) < TOL and orc.ref_err(o["deriv"], deriv) < TOL
+
+
+@pytest.mark.parametrize("M,D,N", [(1025, 4, 300), (1100, 3, 20), (1500, 10, 2500), (2048, 6, 777), (2500, 10, 100),
+                                   (4096, 2, 50)])
+def test_large_m_variance(gpemu, M, D, N):
+    """1024 < M <= 4096: K* goes through a scratch buffer and the contraction runs in column passes
+    (predict_var_large.cuh).  Same formula as GaussianProcess.py:232-247, same tolerance."""
+    import torch
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M % 97)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    out = m.predict(testing, want_hess=(D <= 6))
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    assert orc.ref_err(out["mu"], mu) < TOL and orc.ref_err(out["var"], var) < TOL
+    assert orc.ref_err(out["deriv"], deriv) < TOL
+    if D <= 6:
+        assert orc.ref_err(out["hess"], orc.hessian(inputs, theta, invQt, testing)) < TOL
+    v_only = m.predict(torch.from_numpy(testing).cuda(), want_mu=False, want_deriv=False)["var"]
+    assert np.array_equal(v_only.cpu().numpy(), out["var"])
+
+
+def test_large_m_variance_many_points_and_streams(gpemu):
+    """More points than the K* scratch holds (sub-batches) and the host pipeline's three streams sharing it."""
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(1300, 5, 1, seed=4)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    N = 60_001
+    testing = np.random.RandomState(5).random_sample((N, 5))
+    out = m.predict(testing)                                  # pageable: staged pipeline, several chunks
+    idx = np.r_[0:30, 9460:9490, 30_000:30_030, N - 30:N]
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing[idx])
+    assert orc.ref_err(out["mu"][idx], mu) < TOL and orc.ref_err(out["var"][idx], var) < TOL
+    assert orc.ref_err(out["deriv"][idx], deriv) < TOL
+    again = m.predict(testing)
+    assert np.array_equal(again["var"], out["var"])
 
 
 @pytest.mark.parametrize("M,D,N", [(50, 13, 70), (120, 16, 33), (300, 20, 40), (64, 32, 65)])
