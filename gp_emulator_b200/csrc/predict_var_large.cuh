@@ -11,8 +11,9 @@
 //                              of predict_full.cuh) -- through an mbarrier ring; the pass epilogue multiplies by the
 //                              K* columns of the pass (read back from the scratch, C-fragment layout).
 // Reference: GaussianProcess.py:240 (the same formula; the reference has no limit on M).
-// Cost model: invQ is re-streamed once per 16-point tile (8 M^2 bytes from L2 / HBM), so the kernel is bound by the
-// L2 -> SM stream (2 * 16 M^2 flop per 8 M^2 bytes = 4 flop/B), not by the FP64 tensor pipe.
+// Cost model: invQ is re-streamed once per 16-point tile (8 M^2 bytes, L2-resident: ncu shows a 95 % L2 hit rate and
+// 22 % of the L2 throughput at M = 2048), the FP64 tensor sub-pipe is 80 % active -- the kernel is tensor-bound
+// like the fused one; the K* scratch adds 8 M bytes per point of HBM write + read (profiles/r01_ncu_var_large_summary.md).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
