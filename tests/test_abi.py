@@ -24,6 +24,19 @@ def test_header_symbols_all_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_header_constants_match_python_binding():
+    """Flag bits and limits are declared twice (C header, ctypes layer): they must agree."""
+    from gp_emulator_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "gpemu.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(GPE_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)", text)}
+    assert defs["GPE_MAX_TRAIN"] == _lib.MAX_TRAIN and defs["GPE_MAX_INPUTS"] == _lib.MAX_INPUTS
+    for cname, pyname in [("GPE_WANT_MU", "WANT_MU"), ("GPE_WANT_VAR", "WANT_VAR"), ("GPE_WANT_DERIV", "WANT_DERIV"),
+                          ("GPE_WANT_HESS", "WANT_HESS"), ("GPE_HOST_PTRS", "HOST_PTRS"),
+                          ("GPE_F32_FAST_TF32", "F32_FAST_TF32"), ("GPE_F32_FORCE_3X", "F32_FORCE_3X"),
+                          ("GPE_OPT_SYMMETRIC_VARIANCE", "OPT_SYMMETRIC_VARIANCE")]:
+        assert defs[cname] == getattr(_lib, pyname), cname
+
+
 def test_header_cites_reference_interfaces():
     text = open(os.path.join(ROOT, "include", "gpemu.h")).read()
     for cite in ("_gpu_predict.cpp:115-159", "GaussianProcess.py:211-251", "predict.cu:168-176",
