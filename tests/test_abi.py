@@ -82,3 +82,26 @@ def test_product_code_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src, f"{fn} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/gpemu.h is the drop-in boundary for any host language: it must compile as C99 (no C++, no torch types)
+    and a C program must link against libgpemu.so and call through it."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "gpemu.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    gpe_model* m = 0;\n'
+                   '    double x[8] = {0}, e[3] = {1, 1, 1}, a[4] = {0};\n'
+                   '    int rc = gpe_model_create(0, 0, 2, x, e, a, 0, &m);   /* M = 0: invalid on any box */\n'
+                   '    printf("%d %d %s\\n", gpe_version(), rc, gpe_last_error());\n'
+                   '    return rc == GPE_ERR_INVALID ? 0 : 1;\n}\n')
+    libdir = os.path.join(ROOT, "gp_emulator_b200")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lgpemu", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("100 -1 ")
