@@ -122,6 +122,7 @@ struct gpe_model {
     uint32_t* d_bslabs_lo = nullptr;
     std::vector<double> h_inputs, h_invQt, h_invQ;  // host copy of the model for the lazy FP32 packing
     double h_expx[33];
+    std::mutex host_mu;          // host-pointer calls on one model share its slots (and the lazy FP32 packing): one at a time
     Slot slots[3];               // host-streaming pipeline: the direct (pinned caller) path uses two, the staged path three
 };
 
@@ -1080,7 +1081,10 @@ int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, doub
     if ((flags & GPE_WANT_HESS) && !hess) return fail(GPE_ERR_INVALID, "GPE_WANT_HESS set but hess is NULL");
     if (!mu && !var && !deriv && !hess) return fail(GPE_ERR_INVALID, "no output requested");
     CUDA_TRY(cudaSetDevice(m->device));
-    if (flags & GPE_HOST_PTRS) return predict_host(m, testing, N, mu, var, deriv, hess);
+    if (flags & GPE_HOST_PTRS) {
+        std::lock_guard<std::mutex> lock(m->host_mu);
+        return predict_host(m, testing, N, mu, var, deriv, hess);
+    }
     return predict_device(m, testing, N, mu, var, deriv, hess, 1, 1, m->D, (int64_t)m->D * m->D,
                           (cudaStream_t)stream);
 }
@@ -1104,8 +1108,9 @@ int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, fl
     // long sums dominates the error anyway (1.1e-5 vs 1.5e-5 at M = 1000) and the split costs 3.6x: there the
     // single pass is the default and GPE_F32_FORCE_3X opts in
     const bool fast = (flags & GPE_F32_FAST_TF32) != 0 || (m->M > 256 && !(flags & GPE_F32_FORCE_3X));
+    std::lock_guard<std::mutex> lock(m->host_mu);   // also covers the lazy packing of the FP32 operands
     if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, fast, (cudaStream_t)stream);
-    // host pointers: the same two-slot overlapped pipeline as the FP64 path
+    // host pointers: the same overlapped pipeline as the FP64 path
     return predict_host_t<float>(m, testing, N, mu, var, deriv, (float*)nullptr,
                                  [&](float* d_in, int64_t n, float* a, float* b, float* c, float*, cudaStream_t st) {
                                      return predict_device_f32(m, d_in, n, a, b, c, fast, st);

@@ -10,8 +10,10 @@
  * last failure on the calling thread is available from gpe_last_error().  Nothing here calls
  * exit() (the reference does: gp_emulator/gpu/gpu_predict.h:131-154, kernel_cdist.cu:28-32).
  *
- * Threading: a handle may be used from one host thread at a time.  Calls with device pointers are
- * asynchronous on the given stream; calls with host pointers return after the outputs are written.
+ * Threading: different handles are independent.  Host-pointer calls on the same handle are serialised
+ * inside the library (they share the handle's staging buffers); device-pointer calls are asynchronous on
+ * the given stream and may be issued from several threads.  Creation / destruction of a handle must not
+ * race with its use.
  */
 #ifndef GPEMU_H_
 #define GPEMU_H_

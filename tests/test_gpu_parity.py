@@ -218,6 +218,27 @@ def test_staged_pipeline_concurrent_models(gpemu):
     assert len(res) == 3 and max(res.values()) < TOL, res
 
 
+def test_one_model_shared_by_threads(gpemu):
+    """The numpy reference is re-entrant; here host-pointer calls on one handle are serialised by the library, so
+    several Python threads (ctypes releases the GIL) may share one GaussianProcess."""
+    import threading
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(100, 6, 1, seed=31)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    rs = np.random.RandomState(3)
+    batches = [rs.random_sample((n, 6)) for n in (50_000, 120_001, 777, 64_000)]
+    want = [m.predict(b) for b in batches]
+    got = [None] * len(batches)
+    def work(i):
+        for _ in range(3):
+            got[i] = m.predict(batches[i])
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for w, g_ in zip(want, got):
+        for k in ("mu", "var", "deriv"):
+            assert np.array_equal(w[k], g_[k]), k
+
+
 def test_preallocated_and_pinned_outputs(gpemu):
     import torch
     inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 7, 70000, seed=6)
