@@ -8,4 +8,4 @@ $SHORT > gpurun_out/plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_predict_full -s 1 -c 1 -o gpurun_out/prof_full_final -f $SHORT > gpurun_out/ncu_full.log 2>&1
 python tools/prof_tf32.py > gpurun_out/plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_predict_tf32 -s 1 -c 1 -o gpurun_out/prof_tf32 -f python tools/prof_tf32.py > gpurun_out/ncu_tf32.log 2>&1
-tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_tf32.log
+tail -n 2 gpurun_out/ncu_full.log; tail -n 2 gpurun_out/ncu_tf32.log
