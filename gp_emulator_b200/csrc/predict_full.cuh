@@ -88,6 +88,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     // phase C: the TN / 8 row tiles go to warp % NMT, the NCT column tiles are dealt cyclically to the CG = NW / NMT
     // warps that share a row tile (8 warps, TN = 64: one row tile and all column tiles per warp -- balanced across
     // the four SM sub-partitions, which warp % 4 maps onto)
+    // cfg 0 / 1 (MT = 4): tile-start chores after the row barrier and the conflict-free epilogue loads (+0.9 % at
+    // M = 250).  cfg 2 (MT = 2, 16-point tiles) measured 2 % slower with either change -- same source in the hot loop,
+    // different ptxas schedule -- so it keeps the first arrangement.
+    constexpr bool kLateChores = (MT >= 4);
     constexpr int NMT = TN / 8;
     constexpr int CG = (NW >= NMT) ? NW / NMT : 1;
     constexpr int NCT = (DP * (DP + 1) / 2 + 7) / 8;
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
 
     // test-row prefetch state
     uint32_t tpar = 0;  // bit `buf` = parity of the next completion of bar_t[buf]
-    auto prefetch_rows = [&](int64_t tile, int buf) -> bool {  // thread 0 only; false if this tile must be loaded in-line
+    auto prefetch_rows = [&](int64_t tile, int buf) -> bool {  // one thread; false if this tile must be loaded in-line
         const int64_t n0 = tile * TN;
         if (!ts_tma_ok || n0 + TN > p.N) return false;
         fence_proxy_async();  // the buffer was last written through the generic proxy (output staging)
@@ -243,8 +247,8 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         const int npts = (int)min((int64_t)TN, p.N - n0);
         double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
         GPE_TRACE(0);
-        // B-operand prefetch for this tile's contraction lands while phase A runs (unless the buffers are shared)
-        if (nit_tot > 0 && !alias_x && tid == 0) issue_burst();
+        // (16-point tiles keep the B-operand burst here, before the row wait: see kLateChores below)
+        if (!kLateChores && nit_tot > 0 && !alias_x && tid == 0) issue_burst();
 
         // ---- this tile's test rows: prefetched by TMA during the previous tile, or loaded in-line ------------
         if (rows_prefetched(tile)) {
@@ -279,9 +283,14 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             tma_bulk_g2s(Xc, p.xchunks, bytes, bar_x);
         }
         __syncthreads();  // ts_s is reused as the output staging area below; the other buffer is free for prefetch
+        // Two serial chores, ~0.5 k and ~0.3 k cycles each, given to lane 0 of two different warps AFTER the barrier so
+        // that nobody waits for them (they overlap the other warps' phase A): the B-operand burst for this tile's
+        // contraction (lands while phase A runs, unless the ring shares its buffer with the chunk), and the TMA
+        // prefetch of the next tile's test rows.
+        if (kLateChores && nit_tot > 0 && !alias_x && tid == 0) issue_burst();
         {
             const int64_t next = tile + gridDim.x;
-            if (tid == 0 && next < ntiles) prefetch_rows(next, buf ^ 1);
+            if (tid == ((kLateChores && NW > 1) ? 32 : 0) && next < ntiles) prefetch_rows(next, buf ^ 1);
         }
 
         GPE_TRACE(1);
@@ -462,15 +471,27 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             double vs[MT];
 #pragma unroll
             for (int i = 0; i < MT; ++i) vs[i] = 0.0;
+            // K* in C-fragment layout: row lane / 4, columns 2 (lane % 4) + {0, 1}.  One 16-byte load per lane would
+            // put rows r and r + 1 of a quarter-warp on overlapping banks (pitch = 4 mod 16 doubles, chosen for the
+            // A fragments): 2-way conflicts on all 131 KB of the tile, 2.1 k cycles per tile.  Two 8-byte loads with the
+            // column order swapped on odd rows are conflict-free (each half-warp covers all 32 banks exactly once).
+            const int odd = (lane >> 2) & 1;
             const double* k_base = Ks + (wrow * MT * 8 + (lane >> 2)) * pitch + wcol * 8 + 2 * (lane & 3);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 if (FULLNT || j < nt_act) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        const double2 kk = *reinterpret_cast<const double2*>(k_base + i * 8 * pitch + j * (WC * 8));
-                        vs[i] = fma(acc[i][j][0], kk.x, vs[i]);
-                        vs[i] = fma(acc[i][j][1], kk.y, vs[i]);
+                        const double* kp = k_base + i * 8 * pitch + j * (WC * 8);
+                        if (kLateChores) {
+                            const double k_first = kp[odd], k_second = kp[odd ^ 1];
+                            vs[i] = fma(acc[i][j][0], odd ? k_second : k_first, vs[i]);
+                            vs[i] = fma(acc[i][j][1], odd ? k_first : k_second, vs[i]);
+                        } else {
+                            const double2 kk = *reinterpret_cast<const double2*>(kp);
+                            vs[i] = fma(acc[i][j][0], kk.x, vs[i]);
+                            vs[i] = fma(acc[i][j][1], kk.y, vs[i]);
+                        }
                     }
                 }
             }
