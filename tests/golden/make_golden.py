@@ -15,7 +15,7 @@ goldens is therefore the reference's own numpy/scipy code:
   GaussianProcess._set_params             gp_emulator/GaussianProcess.py:52-75, 127-139
   MultivariateEmulator (dump=...) .predict gp_emulator/multivariate_gp.py:40-121, 195-222
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--only S1500]
 """
 import hashlib
 import os
@@ -69,8 +69,11 @@ def main():
     RefGP, RefMV = load_reference()
 
     # ---- S: tests/benchmark.py-style all-U(0,1) model (config 1 and config 3 shapes) ---------------
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None   # regenerate one fixture
     for tag, (M, D, N, seed, nh) in {"S250": (250, 10, 300, 0, 40), "S1000": (1000, 10, 64, 3, 0),
-                                     "S37": (37, 3, 130, 5, 130)}.items():
+                                     "S37": (37, 3, 130, 5, 130), "S1500": (1500, 6, 48, 7, 8)}.items():
+        if only and tag != only:
+            continue
         inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed)
         gp = ref_gp(RefGP, inputs, theta, invQ, invQt)
         mu, var, deriv = gp.predict(testing)
@@ -83,6 +86,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)
         print(tag, "mu[:2]", mu[:2], "var[:2]", var[:2])
 
+    if only and only not in ("T", "P"):
+        return
     # ---- T: genuinely conditioned model through the reference's own _set_params ---------------------
     inputs, targets, theta, _, _, testing = orc.make_T_model(M=100, D=4, N=200, seed=1)
     gp = RefGP(inputs, targets)

@@ -30,7 +30,7 @@ def _check(out, ref_mu, ref_var, ref_deriv, tol=TOL):
         assert orc.ref_err(out["var"], ref_var) < tol
 
 
-@pytest.mark.parametrize("tag", ["S250", "S1000", "S37"])
+@pytest.mark.parametrize("tag", ["S250", "S1000", "S37", "S1500"])
 def test_golden_S(gpemu, tag):
     g = golden(tag)
     inputs, theta, invQ, invQt, testing = orc.make_S_model(int(g["M"]), int(g["D"]), int(g["N"]), int(g["seed"]))

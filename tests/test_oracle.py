@@ -17,7 +17,7 @@ def _sha(*arrays):
     return h.hexdigest()
 
 
-@pytest.mark.parametrize("tag", ["S250", "S1000", "S37"])
+@pytest.mark.parametrize("tag", ["S250", "S1000", "S37", "S1500"])
 def test_oracle_matches_reference_S(tag):
     g = golden(tag)
     model = orc.make_S_model(int(g["M"]), int(g["D"]), int(g["N"]), int(g["seed"]))
