@@ -86,7 +86,21 @@ s_pc, r = timeit(lambda: bank.predict(t, want_var=False, want_deriv=True))
 s_all, r = timeit(lambda: bank.predict(t, want_var=False, want_deriv=True, project=True))
 s_var, r = timeit(lambda: bank.predict(t, want_var=True, want_deriv=True))
 proj_s = s_all - s_pc
+# the BASELINE size: 1e7 test inputs, walked in chunks of N points (the 168 GB of spectra are produced chunk-wise and
+# dropped, as SURVEY 8d prescribes); fresh random inputs are generated per chunk outside the timed kernels' stream order
+def full_size(fn, n_chunk, n_total):
+    reps = n_total // n_chunk
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        r = fn()
+        del r
+    e1.record(); torch.cuda.synchronize()
+    return reps * n_chunk / (e0.elapsed_time(e1) * 1e-3)
+full4 = full_size(lambda: bank.predict(t, want_var=False, want_deriv=True, project=True), N, 10_000_000)
 out.append({"config": "4: MultivariateEmulator P=20 W=2101 M=250 D=10 FP64", "N": N,
+            "full_size_1e7_points_chunked_points_per_s": full4,
             "pc_mean_grad_points_per_s": N / s_pc, "pc_mean_var_grad_points_per_s": N / s_var,
             "mean_grad_plus_backprojection_points_per_s": N / s_all,
             "backprojection_only": {"seconds": proj_s, "output_GBps": N * W * 8 / proj_s / 1e9,
@@ -107,7 +121,9 @@ par5 = {"mu": orc.ref_err(ob["mu"], mu_o), "var": orc.ref_err(ob["var"], var_o),
 t = torch.rand(N, D, dtype=torch.float64, device="cuda")
 s5, r = timeit(lambda: bank.predict(t, want_var=True, want_deriv=True, want_hess=True), reps=2, warm=1)
 Fh = F(M, D) + M * (D * D + 2 * D) + D
+full5 = full_size(lambda: bank.predict(t, want_var=True, want_deriv=True, want_hess=True), N, 1_000_000)
 out.append({"config": "5: bank of 64 GPs, shared test points, mu+var+grad+Hessian, M=250 D=10 FP64", "N": N,
+            "chunked_1e6_points_points_per_s": full5,
             "points_per_s": N / s5, "emulator_points_per_s": N * E / s5, "alg_tflops": N * E * Fh / s5 / 1e12,
             "frac_of_dmma_peak": N * E * Fh / s5 / 1e12 / P64, "output_GBps": N * E * 112 * 8 / s5 / 1e9, "parity": par5})
 print(json.dumps({"fp64_peaks": peaks, "configs": out}, indent=1))
