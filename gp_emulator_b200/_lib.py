@@ -24,7 +24,7 @@ MAX_TRAIN, MAX_INPUTS = 4096, 32
 SYMBOLS = (
     "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
     "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_destroy", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
-    "gpe_bank_project", "gpe_measure_fp64_peaks", "gpe_launch_count",
+    "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
 )
 
 
@@ -79,6 +79,8 @@ def load():
     lib.gpe_bank_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint, C.c_void_p]
     lib.gpe_bank_project.restype = C.c_int
     lib.gpe_bank_project.argtypes = [C.c_void_p, dp, dp, C.c_int64, dp, dp, C.c_void_p]
+    lib.gpe_bank_forward.restype = C.c_int
+    lib.gpe_bank_forward.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp]
     lib.gpe_measure_fp64_peaks.restype = C.c_int
     lib.gpe_measure_fp64_peaks.argtypes = [C.c_int, dp]
     _lib = lib

@@ -103,6 +103,7 @@ struct gpe_model {
     bool has_invQ = false;
     bool symmetric = false;      // GPE_OPT_SYMMETRIC_VARIANCE: s_tiled holds the upper-triangular fold of invQ
     FullPlan full;
+    FullPlan full_small;         // 16-point tiles for small batches (valid only if it can share the main plan's operands)
     MeanPlan mean;
     double* d_xchunks_full = nullptr;
     double* d_stiled = nullptr;
@@ -136,6 +137,11 @@ struct gpe_bank {
     MeanBankEntry* d_entries = nullptr;  // per-emulator phase-A data for the one-launch bank mean / Hessian kernel
     double* d_basis = nullptr;   // basis pre-tiled as [ceil(E/4)][Wp][4], Wp = W rounded up to 256
     int Wp = 0;
+    // gpe_bank_forward (host in, host out, one synchronisation): stream + staging buffers, grown on demand
+    std::mutex fwd_mu;
+    cudaStream_t fwd_st = nullptr;
+    double *fwd_h = nullptr, *fwd_d = nullptr;
+    size_t fwd_h_cap = 0, fwd_d_cap = 0;
 };
 
 namespace {
@@ -184,13 +190,17 @@ cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_
 //          2 x ~100 KB the phase-A chunk buffer overlays the B-operand ring (alias_x).
 //   cfg 0: same Mp range, TN = 64, 8 warps, 1 CTA/SM (kept selectable with GPE_FULL_CFG=0 for comparison)
 //   cfg 1 / 2: Mp <= 512 / 1024, TN = 32 / 16, 8 warps, 1 CTA/SM
-FullPlan plan_full(int M, int D, int DP) {
+// small_Mp > 0: the low-latency plan for small batches -- 16-point tiles (cfg 2) on the padded width of the main
+// plan, so that both share s_tiled / xchunks.
+FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     FullPlan f;
     const int m32 = (M + 31) / 32 * 32, m64 = (M + 63) / 64 * 64;
     int force = -1;
     if (const char* e = getenv("GPE_FULL_CFG")) force = atoi(e);
     uint32_t smem_cap = kSmemMax;
-    if (m32 <= 256) {
+    if (small_Mp > 0) {
+        f.cfg = 2; f.TN = 16; f.WC = 8; f.GH = 4; f.Mp = small_Mp; f.nt_act = small_Mp / 64;
+    } else if (m32 <= 256) {
         f.Mp = m32; f.nt_act = m32 / 32;
         if (force == 3) { f.cfg = 3; f.TN = 32; f.WC = 4; f.GH = 1; f.alias_x = 1; smem_cap = (233472 - 2 * 1024) / 2; }
         else if (force == 4) { f.cfg = 4; f.TN = 64; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64; }
@@ -358,7 +368,10 @@ int build_hessian_operand(gpe_model* m, const double* inputs, const double* invQ
 // Launch the kernels for device-resident data on `st`.  Output strides allow bank (point-major) layouts.
 int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                    double* hess, int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess,
-                   cudaStream_t st) {
+                   cudaStream_t st, int64_t call_N = -1) {
+    // call_N: size of the API call this launch is a chunk of (the host pipeline); plan choices that change the
+    // summation order depend on it, not on the chunk, so that one call is internally consistent
+    if (call_N < 0) call_N = N;
     if (N == 0) return GPE_OK;
     bool mean_done = false;
     static const bool force_full = getenv("GPE_FORCE_FULL") != nullptr;  // dev aid: time phase A alone
@@ -402,7 +415,9 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         if (var != nullptr && !m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
         if (!m->full.valid)
             return fail(GPE_ERR_UNSUPPORTED, "variance contraction supports M <= %d (got M = %d)", GPE_MAX_TRAIN, m->M);
-        const FullPlan& f = m->full;
+        // up to three waves of 16-point tiles finish sooner than one wave of 64-point tiles
+        const bool small = m->full_small.valid && !fuse_hess && call_N <= 3 * 16 * (int64_t)m->sms;
+        const FullPlan& f = small ? m->full_small : m->full;
         FullParams p;
         memset(&p, 0, sizeof(p));
         p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
@@ -711,7 +726,7 @@ int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, dou
     const int64_t D = m->D;
     return predict_host_t<double>(m, testing, N, mu, var, deriv, hess,
                                   [&](double* d_in, int64_t n, double* a, double* b, double* c, double* h, cudaStream_t st) {
-                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st);
+                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st, N);
                                   });
 }
 
@@ -1024,6 +1039,11 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
             if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
             rc = build_hessian_operand(m, inputs, invQt);
             if (rc) { gpe_model_destroy(m); return rc; }
+            // low-latency plan for small batches: a 64-point tile costs ~45 us at M = 250 even for one point
+            if (f.cfg == 0 && f.Mp % 64 == 0 && getenv("GPE_NO_SMALL_PLAN") == nullptr) {
+                FullPlan fs = plan_full(M, D, m->DP, f.Mp);
+                if (fs.valid && fs.JC == f.JC && fs.nchunks == f.nchunks && fs.kblk == f.kblk) m->full_small = fs;
+            }
         } else if (M <= GPE_MAX_TRAIN) {
             // beyond the fused kernel: s_tiled with the contraction padded to Mp (the K* scratch pads are zero)
             m->large_Mp = (M + 63) / 64 * 64;
@@ -1244,6 +1264,9 @@ int gpe_bank_destroy(gpe_bank* b) {
     for (gpe_model* m : b->models) gpe_model_destroy(m);
     if (b->d_basis) { cudaSetDevice(b->device); cudaFree(b->d_basis); }
     if (b->d_entries) { cudaSetDevice(b->device); cudaFree(b->d_entries); }
+    if (b->fwd_h) cudaFreeHost(b->fwd_h);
+    if (b->fwd_d) { cudaSetDevice(b->device); cudaFree(b->fwd_d); }
+    if (b->fwd_st) cudaStreamDestroy(b->fwd_st);
     delete b;
     return GPE_OK;
 }
@@ -1334,6 +1357,47 @@ int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t
     if (deriv_full) {
         if (!deriv) return fail(GPE_ERR_INVALID, "deriv_full requested but deriv is NULL");
         CUDA_TRY(run(deriv, N * D, D, (int64_t)E * D, D, 1, deriv_full));
+    }
+    return GPE_OK;
+}
+
+int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd, double* deriv_full) {
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (!b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing || !fwd) return fail(GPE_ERR_INVALID, "testing / fwd is NULL");
+    std::lock_guard<std::mutex> lock(b->fwd_mu);
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (!b->fwd_st) CUDA_TRY(cudaStreamCreateWithFlags(&b->fwd_st, cudaStreamNonBlocking));
+    const int64_t E = b->E, D = b->D, W = b->W;
+    // per point: testing D | mu E | deriv E*D stay on the device; fwd W [| deriv_full D*W] come back
+    const int64_t out_pp = W + (deriv_full ? D * W : 0);
+    const int64_t dev_pp = D + E + E * D + out_pp;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(64u << 20) / (8 * out_pp)));
+    int rc = ensure(&b->fwd_d, &b->fwd_d_cap, (size_t)chunk * dev_pp * 8, false);
+    if (rc) return rc;
+    rc = ensure(&b->fwd_h, &b->fwd_h_cap, (size_t)chunk * (D + out_pp) * 8, true);
+    if (rc) return rc;
+    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+        const int64_t n = std::min(chunk, N - n0);
+        double* d_t = b->fwd_d;
+        double* d_mu = d_t + n * D;
+        double* d_der = d_mu + n * E;
+        double* d_out = d_der + n * E * D;          // fwd (n, W) | deriv_full (n, D, W)
+        double* h_t = b->fwd_h;
+        double* h_out = h_t + n * D;
+        par_memcpy(h_t, testing + n0 * D, (size_t)n * D * 8);
+        CUDA_TRY(cudaMemcpyAsync(d_t, h_t, (size_t)n * D * 8, cudaMemcpyHostToDevice, b->fwd_st));
+        rc = gpe_bank_predict(b, d_t, n, d_mu, nullptr, deriv_full ? d_der : nullptr, nullptr,
+                              GPE_WANT_MU | (deriv_full ? GPE_WANT_DERIV : 0u), b->fwd_st);
+        if (rc) return rc;
+        rc = gpe_bank_project(b, d_mu, deriv_full ? d_der : nullptr, n, d_out, deriv_full ? d_out + n * W : nullptr, b->fwd_st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)n * out_pp * 8, cudaMemcpyDeviceToHost, b->fwd_st));
+        CUDA_TRY(cudaStreamSynchronize(b->fwd_st));
+        par_memcpy(fwd + n0 * W, h_out, (size_t)n * W * 8);
+        if (deriv_full) par_memcpy(deriv_full + n0 * D * W, h_out + n * W, (size_t)n * D * W * 8);
     }
     return GPE_OK;
 }

@@ -295,6 +295,21 @@ class DeviceBank:
 
     host_chunk_bytes = 1 << 30   # device bytes of results per chunk when the caller passes numpy arrays
 
+    def forward(self, testing, want_deriv=True):
+        """numpy (N, D) -> fwd (N, W) [, deriv_full (N, D, W)] through ``gpe_bank_forward``: one call, one
+        synchronisation, nothing but the spectra (and Jacobians) crosses PCIe.  This is what
+        ``MultivariateEmulator.predict`` (reference multivariate_gp.py:195-222) runs on."""
+        if self.W == 0:
+            raise GpemuError("bank has no basis functions to project onto")
+        t = f64c(testing)
+        if t.ndim != 2 or t.shape[1] != self.D:
+            raise ValueError(f"testing must be (N, {self.D})")
+        N = t.shape[0]
+        fwd = np.empty((N, self.W))
+        dfull = np.empty((N, self.D, self.W)) if want_deriv else None
+        check(_lib.load().gpe_bank_forward(self._h, addr(t), N, addr(fwd), addr(dfull)))
+        return (fwd, dfull) if want_deriv else fwd
+
     def _predict_device(self, t, want_var, want_deriv, want_hess, project, project_deriv):
         import torch
         lib = _lib.load()

@@ -110,14 +110,19 @@ class MultivariateEmulator(object):
         One point, as in the reference (multivariate_gp.py:195-222): returns ``fwd (N_full,)`` and
         ``deriv (N_params, N_full)``.  N > 1 points (new): ``fwd (N, N_full)``, ``deriv (N, N_params, N_full)``.
         """
-        y2 = np.atleast_2d(y)
-        out = self._device_bank().predict(y2, want_var=False, want_deriv=False, project=True,
-                                          project_deriv=do_deriv)
-        fwd = out["fwd"]
+        bank = self._device_bank()
+        if isinstance(y, np.ndarray) or not hasattr(y, "is_cuda"):
+            # host caller: one library call (latency matters: the reference is used one point per call)
+            y2 = np.atleast_2d(y)
+            res = bank.forward(y2, want_deriv=do_deriv)
+            fwd, dfull = res if do_deriv else (res, None)
+        else:                                # torch CUDA tensor: everything stays on the device
+            y2 = y if y.dim() == 2 else y.reshape(1, -1)
+            out = bank.predict(y2, want_var=False, want_deriv=False, project=True, project_deriv=do_deriv)
+            fwd, dfull = out["fwd"], out.get("deriv_full")
         if y2.shape[0] == 1:
-            fwd = fwd[0]
-            return (fwd, out["deriv_full"][0]) if do_deriv else fwd
-        return (fwd, out["deriv_full"]) if do_deriv else fwd
+            return (fwd[0], dfull[0]) if do_deriv else fwd[0]
+        return (fwd, dfull) if do_deriv else fwd
 
     def predict_pcs(self, y, do_unc=True, do_deriv=True):
         """PC-space outputs for N points: dict with mu (N, P), var (N, P), deriv (N, P, D)."""

@@ -146,6 +146,12 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
 int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t N, double* fwd,
                      double* deriv_full, void* stream);
 
+/* MultivariateEmulator.predict for host callers in ONE call (gp_emulator/multivariate_gp.py:195-222): test points
+ * (N, D) on the host -> fwd (N, W) and, if deriv_full is not NULL, deriv_full (N, D, W) on the host; the per-PC
+ * means / gradients never leave the device.  Built for the reference's usage pattern -- one point, or a few, per
+ * call inside an optimisation loop: one H2D copy, three launches, one D2H copy and one synchronisation per chunk. */
+int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd, double* deriv_full);
+
 /* FP64 pipe peaks of the device, measured live (roofline denominators the driver's
  * MEASURED_PEAKS.json does not hold).  out9: DFMA TFLOP/s, DMMA TFLOP/s, mixed total, mixed DFMA part,
  * mixed DMMA part, gpe exp Gexp/s, CUDA exp Gexp/s, SM MHz under FP64 load, SM count. */

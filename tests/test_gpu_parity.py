@@ -178,6 +178,48 @@ def test_bank_host_batches_are_chunked(gpemu):
     assert np.array_equal(fwd, ref["fwd"])
 
 
+def test_small_batch_plan_threshold(gpemu):
+    """Calls of up to 3 * 16 * #SM points run 16-point tiles (lower latency), larger ones 64-point tiles; both sides of
+    the switch meet the oracle, and a host call uses one plan for all of its chunks."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(250, 10, 1, seed=17)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    rs = np.random.RandomState(18)
+    for N in (48 * sms, 48 * sms + 1):
+        testing = rs.random_sample((N, 10))
+        out = m.predict(testing)
+        idx = np.r_[0:40, N // 2:N // 2 + 40, N - 40:N]
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing[idx])
+        assert orc.ref_err(out["mu"][idx], mu) < TOL and orc.ref_err(out["var"][idx], var) < TOL
+        assert orc.ref_err(out["deriv"][idx], deriv) < TOL
+        dev = m.predict(torch.from_numpy(testing).cuda())
+        assert np.array_equal(dev["var"].cpu().numpy(), out["var"])
+
+
+def test_bank_forward_single_call(gpemu):
+    """gpe_bank_forward (what MultivariateEmulator.predict runs on for host callers): same values as the two-step
+    device path, for one point, a few, and more than one internal chunk; Jacobian optional."""
+    rs = np.random.RandomState(13)
+    M, D, E, W = 60, 4, 5, 300
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    basis = rs.standard_normal((E, W))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
+    for N in (1, 7, 6001):
+        t = rs.random_sample((N, D))
+        ref = bank.predict(t, want_var=False, want_deriv=False, project=True, project_deriv=True)
+        fwd, dfull = bank.forward(t)
+        assert np.array_equal(fwd, ref["fwd"]) and np.array_equal(dfull, ref["deriv_full"]), N
+        assert np.array_equal(bank.forward(t, want_deriv=False), ref["fwd"])
+    models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(E)]
+    t = rs.random_sample((3, D))
+    fwd, dfull = bank.forward(t)
+    for k in range(3):
+        f_o, d_o = orc.mv_predict_point(models, basis, t[k])
+        assert orc.ref_err(fwd[k], f_o) < TOL and orc.ref_err(dfull[k], d_o) < TOL
+
+
 def test_staged_pipeline_chunk_seams(gpemu):
     """Pageable callers go through the three-slot staged pipeline (copy-in thread / GPU / copy-out thread).  Sizes
     around its chunking decisions must give bit-identical results to the device-resident call, repeatedly (slot
