@@ -721,12 +721,14 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
     return GPE_OK;
 }
 
+// call_N: size of the user's call when this is one device's share of it (gpe_multi_predict), else N
 int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
-                 double* hess) {
+                 double* hess, int64_t call_N = -1) {
     const int64_t D = m->D;
+    if (call_N < 0) call_N = N;
     return predict_host_t<double>(m, testing, N, mu, var, deriv, hess,
                                   [&](double* d_in, int64_t n, double* a, double* b, double* c, double* h, cudaStream_t st) {
-                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st, N);
+                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st, call_N);
                                   });
 }
 
@@ -1207,9 +1209,20 @@ int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* m
         const int64_t lo = g * base + std::min<int64_t>(g, rem), n = base + (g < rem ? 1 : 0);
         if (n == 0) continue;
         th.emplace_back([=, &rcs, &msgs] {
-            rcs[g] = gpe_predict(mm->models[g], testing + lo * D, n, mu ? mu + lo : nullptr, var ? var + lo : nullptr,
-                                 deriv ? deriv + lo * D : nullptr, hess ? hess + lo * D * D : nullptr,
-                                 flags | GPE_HOST_PTRS, nullptr);
+            gpe_model* m = mm->models[g];
+            const bool w_mu = flags & GPE_WANT_MU, w_var = flags & GPE_WANT_VAR, w_der = flags & GPE_WANT_DERIV,
+                       w_hes = flags & GPE_WANT_HESS;
+            if ((w_mu && !mu) || (w_var && !var) || (w_der && !deriv) || (w_hes && !hess) ||
+                !(w_mu || w_var || w_der || w_hes) || !testing) {
+                rcs[g] = fail(GPE_ERR_INVALID, "output flag set with a NULL array, or nothing requested");
+            } else if (cudaSetDevice(m->device) != cudaSuccess) {
+                rcs[g] = fail(GPE_ERR_CUDA, "cudaSetDevice(%d) failed", m->device);
+            } else {
+                // the plan (tile size) follows the size of the whole call, so G devices reproduce one device bit for bit
+                std::lock_guard<std::mutex> lock(m->host_mu);
+                rcs[g] = predict_host(m, testing + lo * D, n, w_mu ? mu + lo : nullptr, w_var ? var + lo : nullptr,
+                                      w_der ? deriv + lo * D : nullptr, w_hes ? hess + lo * D * D : nullptr, N);
+            }
             if (rcs[g]) msgs[g] = gpe_last_error();   // thread-local in the worker: carry it out
         });
     }

@@ -638,6 +638,13 @@ def test_one_call_multi_device_fanout(lib, gpemu):
         assert np.array_equal(a[k], b[k]), k
     h = mm.predict(testing[:300], want_var=False, want_deriv=False, want_hess=True)["hess"]
     assert orc.ref_err(h, orc.hessian(inputs, theta, invQt, testing[:300])) < TOL
+    # a call whose per-device shares fall below the small-batch switch while the call itself does not: the tile plan
+    # follows the call, so the fan-out still reproduces the single-device result bit for bit
+    single = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    for n in (10_000, 7_104, 300):
+        a = mm.predict(testing[:n]); b = single.predict(testing[:n])
+        for k in ("mu", "var", "deriv"):
+            assert np.array_equal(a[k], b[k]), (n, k)
 
 
 def test_random_shape_sweep(gpemu):
