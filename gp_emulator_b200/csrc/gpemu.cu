@@ -565,7 +565,8 @@ void par_memcpy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy
 // Host-resident caller: stream chunks through a few slots so the H2D copy of chunk i+1, the kernels of chunk i and
 // the D2H copy of chunk i-1 overlap.
 //   pinned caller buffers   : DMA'd directly, two slots, 2^18-point chunks;
-//   pageable caller buffers : staged through page-locked slot buffers.  The caller's thread stages inputs and
+//   pageable caller buffers : staged through page-locked slot buffers -- inputs and outputs independently, so a
+//                             caller with pageable inputs and page-locked result arrays only pays for the copy-in.  The caller's thread stages inputs and
 //                             enqueues (copy-in -> H2D -> kernels -> D2H -> event), a second thread waits for each
 //                             chunk's event and copies its results out, both copying through the CopyPool; three
 //                             slots keep the GPU busy while either side is late.  Chunks are about a quarter of the
@@ -578,8 +579,14 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
     constexpr size_t ES = sizeof(T);
     const int D = m->D;
     const int64_t per_out = (mu ? 1 : 0) + (var ? 1 : 0) + (deriv ? D : 0) + (hess ? (int64_t)D * D : 0);
-    const bool direct = is_pinned_or_null(testing) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
-                        is_pinned_or_null(deriv) && is_pinned_or_null(hess);
+    // inputs and outputs are staged independently: page-locked caller memory is DMA'd directly on either side
+    // (a pointer query on pageable memory costs ~10 us: a small call with pageable inputs does not ask about its
+    // outputs -- staging a few KB is cheaper than finding out)
+    const bool in_direct = is_pinned_or_null(testing);
+    const bool tiny = N <= 3 * 64 * (int64_t)m->sms;
+    const bool out_direct = (in_direct || !tiny) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
+                            is_pinned_or_null(deriv) && is_pinned_or_null(hess);
+    const bool direct = in_direct && out_direct;
     int64_t CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(N, 1));
     if (!direct) {
         const int64_t wave = 64 * (int64_t)m->sms;
@@ -595,9 +602,11 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         if (rc) return rc;
         rc = ensure(&s.d_out, &s.d_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, false);
         if (rc) return rc;
-        if (!direct) {
+        if (!in_direct) {
             rc = ensure(&s.h_in, &s.h_in_cap, (size_t)CH * D * ES, true);
             if (rc) return rc;
+        }
+        if (!out_direct) {
             rc = ensure(&s.h_out, &s.h_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, true);
             if (rc) return rc;
         }
@@ -613,6 +622,13 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         r.hes = hess ? o : nullptr;
         return r;
     };
+    auto d2h_direct = [&](Slot& s, const Outs& o, int64_t n0, int64_t n) -> int {
+        if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, o.mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+        if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, o.var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
+        if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, o.der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
+        if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, o.hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
+        return GPE_OK;
+    };
     if (direct) {
         int which = 0;
         for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
@@ -623,16 +639,14 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
             CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
             int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
             if (rc) return rc;
-            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, o.mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-            if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, o.var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-            if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, o.der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
-            if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, o.hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
+            rc = d2h_direct(s, o, n0, n);
+            if (rc) return rc;
         }
         for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(m->slots[i].st));
         return GPE_OK;
     }
 
-    // ---- staged path ---------------------------------------------------------------------------------------
+    // ---- staged path (inputs and / or outputs in pageable memory) -------------------------------------------
     static const bool pipe_trace = getenv("GPE_PIPE_TRACE") != nullptr;   // dev aid: host-side time split of a call
     double t_wait = 0, t_out = 0, t_in = 0, t_block = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -641,6 +655,7 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         cudaError_t e = cudaEventSynchronize(s.done);
         if (e != cudaSuccess) return e;
         t_wait += now() - t0; t0 = now();
+        if (out_direct) return cudaSuccess;          // the D2H copies went straight into the caller's arrays
         const int64_t n0 = s.pend_n0, n = s.pend_n;
         const T* src = reinterpret_cast<const T*>(s.h_out);
         if (mu) { par_memcpy(mu + n0, src, (size_t)n * ES); src += n; }
@@ -651,15 +666,24 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         return cudaSuccess;
     };
     auto stage_in = [&](Slot& s, int64_t n0, int64_t n) -> int {   // copy-in + enqueue of one chunk on the slot
-        double t0 = now();
-        par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
-        t_in += now() - t0;
         T* const d_in = reinterpret_cast<T*>(s.d_in);
         const Outs o = carve(s, n);
-        CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
+        if (in_direct) {
+            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
+        } else {
+            double t0 = now();
+            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
+            t_in += now() - t0;
+            CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
+        }
         int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
+        if (out_direct) {
+            rc = d2h_direct(s, o, n0, n);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
+        }
         CUDA_TRY(cudaEventRecord(s.done, s.st));
         s.pend_n0 = n0; s.pend_n = n;
         return GPE_OK;
@@ -670,6 +694,20 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         rc = stage_in(m->slots[0], 0, N);
         if (rc) return rc;
         CUDA_TRY(copy_out(m->slots[0]));
+    } else if (out_direct) {
+        // only the inputs are staged: no second thread, a slot is reused once its previous chunk has finished
+        for (int64_t c = 0; c < nchunks; ++c) {
+            Slot& s = m->slots[c % 3];
+            if (c >= 3) {
+                const double t0 = now();
+                CUDA_TRY(cudaEventSynchronize(s.done));
+                t_block += now() - t0;
+            }
+            const int64_t n0 = c * CH;
+            rc = stage_in(s, n0, std::min(CH, N - n0));
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+        }
+        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(m->slots[i].st));
     } else {
         // chunk c lives in slot c % 3.  `staged` / `drained` count chunks handed to / finished by the output thread.
         std::mutex mx;
@@ -715,9 +753,10 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
         if (out_err != cudaSuccess) return fail(GPE_ERR_CUDA, "result copy-out failed: %s", cudaGetErrorString(out_err));
     }
     if (pipe_trace)
-        fprintf(stderr, "[gpemu pipe] N=%lld in %lld chunks of %lld: out-thread wait %.3f ms, copy-out %.3f ms | copy-in %.3f ms, "
-                        "caller blocked on a slot %.3f ms\n",
-                (long long)N, (long long)nchunks, (long long)CH, t_wait * 1e3, t_out * 1e3, t_in * 1e3, t_block * 1e3);
+        fprintf(stderr, "[gpemu pipe] N=%lld in %lld chunks of %lld (in %s, out %s): out-thread wait %.3f ms, copy-out %.3f ms | "
+                        "copy-in %.3f ms, caller blocked on a slot %.3f ms\n",
+                (long long)N, (long long)nchunks, (long long)CH, in_direct ? "direct" : "staged",
+                out_direct ? "direct" : "staged", t_wait * 1e3, t_out * 1e3, t_in * 1e3, t_block * 1e3);
     return GPE_OK;
 }
 

@@ -144,7 +144,7 @@ class GaussianProcess:
         self._dev_model, self._dev_key = None, None
 
     def predict(self, testing, do_unc=True, do_deriv=True, is_gpu=True, precision=np.float64, threshold=2e5,
-                out=None, pinned=False):
+                out=None, pinned=None):
         """Mean, variance and input gradient at ``testing`` (N, D)  (reference GaussianProcess.py:327-341).
 
         Returns ``(mu, var, deriv)``; ``(mu, deriv)`` if ``do_unc`` is False (as the reference's CPU branch,
@@ -153,8 +153,9 @@ class GaussianProcess:
         tensor) is given and M <= 1024: then the single-precision tensor-core path runs (for larger M the FP64
         results are cast).
         ``testing`` may also be a float64 torch CUDA tensor, in which case torch tensors are returned.
-        ``out`` (dict with any of "mu", "var", "deriv") supplies preallocated result buffers, ``pinned=True``
-        makes freshly allocated host results page-locked (see ``DeviceModel.predict``).
+        ``out`` (dict with any of "mu", "var", "deriv") supplies preallocated result buffers; ``pinned``
+        chooses the memory of freshly allocated host results (None: page-locked from the second call of the same
+        size on; see ``DeviceModel.predict``).
         """
         if getattr(testing, "ndim", None) != 2 and not hasattr(testing, "dim"):
             raise ValueError("testing must always be a 2-D array (N, D)")

@@ -260,6 +260,30 @@ def test_staged_pipeline_concurrent_models(gpemu):
     assert len(res) == 3 and max(res.values()) < TOL, res
 
 
+def test_mixed_staging_and_auto_pinned_results(gpemu):
+    """Inputs and outputs are staged independently: pageable inputs with page-locked results (what repeated calls get
+    automatically from the second call of a size on) skip the copy-out; every combination gives the same bits."""
+    import torch
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(90, 5, 1, seed=41)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    N = 300_017
+    testing = np.random.RandomState(42).random_sample((N, 5))
+    ref = m.predict(testing, pinned=False)
+    assert not torch.from_numpy(ref["deriv"]).is_pinned()
+    forced = m.predict(testing, pinned=True)                       # pageable in, page-locked out, several chunks
+    assert torch.from_numpy(forced["deriv"]).is_pinned()
+    pin_in = torch.from_numpy(testing).pin_memory().numpy()
+    mixed = m.predict(pin_in, pinned=False)                        # page-locked in, pageable out
+    first = m.predict(testing)                                     # auto: first request of this size -> pageable
+    again = m.predict(testing)                                     # second request -> page-locked
+    assert torch.from_numpy(again["deriv"]).is_pinned()
+    for other in (forced, mixed, first, again):
+        for k in ("mu", "var", "deriv"):
+            assert np.array_equal(other[k], ref[k]), k
+    small = m.predict(testing[:100]); small2 = m.predict(testing[:100])   # below 1 MB: never page-locked
+    assert not torch.from_numpy(small2["deriv"]).is_pinned() and np.array_equal(small["mu"], small2["mu"])
+
+
 def test_one_model_shared_by_threads(gpemu):
     """The numpy reference is re-entrant; here host-pointer calls on one handle are serialised by the library, so
     several Python threads (ctypes releases the GIL) may share one GaussianProcess."""
