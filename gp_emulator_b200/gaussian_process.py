@@ -12,7 +12,6 @@ re-read at every call -- the reference's own benchmark overwrites them between c
 from __future__ import annotations
 
 import warnings
-import zlib
 
 import numpy as np
 
@@ -27,15 +26,6 @@ def k_fold_cross_validation(X, K, randomise=False):
         random.shuffle(items)
     for k in range(K):
         yield ([x for i, x in enumerate(items) if i % K != k], [x for i, x in enumerate(items) if i % K == k])
-
-
-def _digest(*arrays):
-    h = 0
-    for a in arrays:
-        a = np.ascontiguousarray(a)
-        h = zlib.crc32(memoryview(a).cast("B"), h)
-        h = zlib.crc32(repr(a.shape).encode(), h)
-    return h
 
 
 class GaussianProcess:
@@ -119,16 +109,20 @@ class GaussianProcess:
     def _device_model(self):
         """Device copy of the current numpy state, re-uploaded only when the arrays change.
 
-        The reference's benchmark REBINDS the attributes between calls (tests/benchmark.py:11-15), so the key
-        holds a CRC of the small arrays (inputs, theta, invQt) and, for the M x M ``invQ`` (500 KB at M = 250:
-        a full CRC would cost more than a small predict), its identity, address, shape and a CRC of every 61st
-        element.  After editing a few entries of ``invQ`` in place call ``invalidate_device()``.
+        The reference's benchmark REBINDS the attributes between calls (tests/benchmark.py:11-15), so every predict
+        checks a key: the bytes of the small vectors (theta, invQt) and, for the two matrices (``inputs`` 20 KB and
+        ``invQ`` 500 KB at M = 250 -- hashing them would cost 10-15 us, a fifth of a one-point predict), identity,
+        shape and the bytes of every 61st element (4 us in total).  After editing a few entries of ``inputs`` / ``invQ`` IN PLACE
+        call ``invalidate_device()``.
         """
+        def fingerprint(a):      # ~1 us: identity, shape and the bytes of every 61st element
+            q = np.asarray(a)
+            return (id(a), q.shape, q.dtype.str, q.ravel()[::61].tobytes())
+
         invQ = getattr(self, "invQ", None)
-        key = [_digest(self.inputs, self.theta, self.invQt), self.device]
+        key = [np.asarray(self.theta).tobytes(), np.asarray(self.invQt).tobytes(), self.device, fingerprint(self.inputs)]
         if invQ is not None:
-            q = np.asarray(invQ)
-            key += [id(invQ), q.__array_interface__["data"][0], q.shape, _digest(q.reshape(-1)[::61])]
+            key.append(fingerprint(invQ))
         key = tuple(key)
         if self._dev_model is None or key != self._dev_key:
             if self._dev_model is not None:
