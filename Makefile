@@ -8,7 +8,7 @@ BUILD     := build/obj
 DPS       := 2 4 6 8 10 12 16 24 32
 LIB       := gp_emulator_b200/libgpemu.so
 
-OBJS := $(BUILD)/gpemu.o $(BUILD)/peaks.o $(BUILD)/var_large.o $(BUILD)/tf32.o $(foreach d,$(DPS),$(BUILD)/inst_dp$(d).o)
+OBJS := $(BUILD)/gpemu.o $(BUILD)/peaks.o $(BUILD)/var_large.o $(BUILD)/tf32.o $(BUILD)/train.o $(foreach d,$(DPS),$(BUILD)/inst_dp$(d).o)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/gpemu.h
 
 all: $(LIB)
@@ -24,6 +24,9 @@ $(BUILD)/peaks.o: $(CSRC)/peaks.cu $(HDRS) | $(BUILD)
 
 $(BUILD)/var_large.o: $(CSRC)/predict_var_large.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/var_large.ptxas.log || (cat $(BUILD)/var_large.ptxas.log; exit 1)
+
+$(BUILD)/train.o: $(CSRC)/train.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/train.ptxas.log || (cat $(BUILD)/train.ptxas.log; exit 1)
 
 $(BUILD)/tf32.o: $(CSRC)/predict_tf32_inst.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(BUILD)/tf32.ptxas.log || (cat $(BUILD)/tf32.ptxas.log; exit 1)

@@ -19,12 +19,14 @@ OPT_SYMMETRIC_VARIANCE = 0x1
 F32_FAST_TF32 = 0x200
 F32_FORCE_3X = 0x400
 MAX_TRAIN, MAX_INPUTS = 4096, 32
+TRAIN_MAX_M = 1024
 
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
     "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_destroy", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
     "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
+    "gpe_trainer_create", "gpe_trainer_eval", "gpe_trainer_destroy",
 )
 
 
@@ -83,6 +85,12 @@ def load():
     lib.gpe_bank_forward.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp]
     lib.gpe_measure_fp64_peaks.restype = C.c_int
     lib.gpe_measure_fp64_peaks.argtypes = [C.c_int, dp]
+    lib.gpe_trainer_create.restype = C.c_int
+    lib.gpe_trainer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_void_p)]
+    lib.gpe_trainer_eval.restype = C.c_int
+    lib.gpe_trainer_eval.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, dp]
+    lib.gpe_trainer_destroy.restype = C.c_int
+    lib.gpe_trainer_destroy.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

@@ -26,6 +26,7 @@
 #include "../../include/gpemu.h"
 #include "launch.h"
 #include "gpe_math.cuh"
+#include "host_common.h"
 
 using namespace gpe;
 
@@ -1006,6 +1007,20 @@ gpe_model* g_wrap_model = nullptr;
 uint64_t g_wrap_key = 0;
 
 }  // namespace
+
+namespace gpe {
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int require_device(int device, int* sms) { return check_device(device, sms); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+}  // namespace gpe
 
 // =================================================================================================
 extern "C" {

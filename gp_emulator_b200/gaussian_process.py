@@ -1,9 +1,10 @@
 """Drop-in ``GaussianProcess`` (same constructor, attributes and method names as the reference class in
 gp_emulator/GaussianProcess.py:28-366) whose prediction runs on the B200 engine.
 
-Training (``learn_hyperparameters`` and the invQ / invQt precompute) stays on the host in numpy, as the
-scope requires; it is restated here only so the class is usable under Python 3 (the reference file is
-Python 2).  ``predict`` and ``hessian`` always go through libgpemu: there is no CPU prediction path, and the
+Training (``learn_hyperparameters`` and the invQ / invQt precompute) stays on the host in numpy by default, as
+the scope requires; it is restated here so the class is usable under Python 3 (the reference file is Python 2).
+``learn_hyperparameters(batched=True)`` serves the optimiser's cost / gradient evaluations from the GPU
+(``training.py``); the state prediction reads is always built by the host ``_set_params``.  ``predict`` and ``hessian`` always go through libgpemu: there is no CPU prediction path, and the
 ``is_gpu`` / ``threshold`` arguments of the reference signature are accepted and ignored (chunking lives
 below the C ABI).  Model attributes (``inputs, theta, invQ, invQt``) stay plain numpy arrays and are
 re-read at every call -- the reference's own benchmark overwrites them between calls
@@ -92,14 +93,25 @@ class GaussianProcess:
             res = [self.current_theta, 9999]
         return res
 
-    def learn_hyperparameters(self, n_tries=15, verbose=False):
-        """Multi-start fit; returns (min cost, theta) (reference GaussianProcess.py:183-209)."""
-        costs, params = [], []
-        for theta in 5.0 * (np.random.rand(n_tries, self.D + 2) - 0.5):
-            T = self._learn(theta, verbose)
-            costs.append(T[1])
-            params.append(T[0])
-        costs = np.array(costs)
+    def learn_hyperparameters(self, n_tries=15, verbose=False, batched=False):
+        """Multi-start fit; returns (min cost, theta) (reference GaussianProcess.py:183-209).
+
+        ``batched=True`` runs the same ``n_tries`` L-BFGS-B descents from the same random starts, but in lockstep with
+        every round of cost + gradient evaluations served by one GPU launch (``training.minimise_batched``); the
+        default is the reference's sequential host path.
+        """
+        starts = 5.0 * (np.random.rand(n_tries, self.D + 2) - 0.5)
+        if batched:
+            from .training import DeviceTrainer, minimise_batched
+            trainer = DeviceTrainer(self.inputs, self.targets, device=self.device)
+            try:
+                fits, _ = minimise_batched(trainer.evaluate, [(0, th) for th in starts], verbose=verbose)
+            finally:
+                trainer.close()
+        else:
+            fits = [self._learn(theta, verbose) for theta in starts]
+        costs = np.array([T[1] for T in fits])
+        params = [T[0] for T in fits]
         idx = int(np.argsort(costs)[0])
         print("After %d, the minimum cost was %e" % (n_tries, costs[idx]))
         self._set_params(params[idx])

@@ -18,7 +18,8 @@ from .gaussian_process import GaussianProcess
 
 
 class MultivariateEmulator(object):
-    def __init__(self, dump=None, X=None, y=None, hyperparams=None, thresh=0.98, n_tries=5, device=0):
+    def __init__(self, dump=None, X=None, y=None, hyperparams=None, thresh=0.98, n_tries=5, device=0,
+                 batched_training=False):
         """See reference multivariate_gp.py:40-121.  ``X`` (N_train, N_full) model outputs, ``y``
         (N_train, N_params) the parameters that produced them, ``hyperparams`` (N_params + 2, n_pcs)."""
         basis_functions = None
@@ -62,7 +63,7 @@ class MultivariateEmulator(object):
         if hyperparams is not None:
             assert (y.shape[1] + 2 == hyperparams.shape[0]) and (self.n_pcs == hyperparams.shape[1])
         self._bank = None
-        self.train_emulators(X, y, hyperparams=hyperparams, n_tries=n_tries)
+        self.train_emulators(X, y, hyperparams=hyperparams, n_tries=n_tries, batched=batched_training)
 
     def dump_emulator(self, fname):
         """Save for reuse, reference npz format (multivariate_gp.py:124-137)."""
@@ -77,19 +78,41 @@ class MultivariateEmulator(object):
         self.basis_functions = V[: keep.size][keep]
         self.n_pcs = int(np.sum(keep))
 
-    def train_emulators(self, X, y, hyperparams, n_tries=2):
-        """One GP per PC on the compressed outputs (reference multivariate_gp.py:162-188)."""
+    def train_emulators(self, X, y, hyperparams, n_tries=2, batched=False):
+        """One GP per PC on the compressed outputs (reference multivariate_gp.py:162-188).
+
+        ``batched=True`` (only meaningful when ``hyperparams`` is None): all ``n_pcs * n_tries`` L-BFGS-B descents run
+        in lockstep, their cost + gradient evaluations served by one GPU launch per round (``training.py``) -- the PCs
+        share the training inputs ``y``, so they are one batch of (theta, target vector) problems.
+        """
         self.emulators = []
         train_data = self.compress(X)
         self.hyperparams = np.zeros((2 + y.shape[1], self.n_pcs))
-        for i in range(self.n_pcs):
-            gp = GaussianProcess(np.atleast_2d(y), train_data[i], device=self.device)
-            if hyperparams is None:
-                self.hyperparams[:, i] = gp.learn_hyperparameters(n_tries=n_tries)[1]
-            else:
-                self.hyperparams[:, i] = hyperparams[:, i]
-                gp._set_params(hyperparams[:, i])
-            self.emulators.append(gp)
+        gps = [GaussianProcess(np.atleast_2d(y), train_data[i], device=self.device) for i in range(self.n_pcs)]
+        if hyperparams is None and batched:
+            from .training import DeviceTrainer, minimise_batched
+            D = y.shape[1]
+            # the same random draws, in the same order, as n_pcs sequential learn_hyperparameters calls
+            starts = [(i, th) for i in range(self.n_pcs) for th in 5.0 * (np.random.rand(n_tries, D + 2) - 0.5)]
+            trainer = DeviceTrainer(np.atleast_2d(y), train_data, device=self.device)
+            try:
+                fits, self.training_stats = minimise_batched(trainer.evaluate, starts)
+            finally:
+                trainer.close()
+            for i, gp in enumerate(gps):
+                mine = fits[i * n_tries:(i + 1) * n_tries]
+                best = int(np.argsort(np.array([f[1] for f in mine]))[0])
+                print("After %d, the minimum cost was %e" % (n_tries, mine[best][1]))
+                self.hyperparams[:, i] = mine[best][0]
+                gp._set_params(self.hyperparams[:, i])
+        else:
+            for i, gp in enumerate(gps):
+                if hyperparams is None:
+                    self.hyperparams[:, i] = gp.learn_hyperparameters(n_tries=n_tries)[1]
+                else:
+                    self.hyperparams[:, i] = hyperparams[:, i]
+                    gp._set_params(hyperparams[:, i])
+        self.emulators = gps
         self._bank = None
 
     def compress(self, X):

@@ -157,6 +157,28 @@ int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd,
  * mixed DMMA part, gpe exp Gexp/s, CUDA exp Gexp/s, SM MHz under FP64 load, SM count. */
 int gpe_measure_fp64_peaks(int device, double* out9);
 
+/* ---- batched training objective (the caller on the input side of the prediction path) -------------
+ * Evaluates, for B (theta, target vector) problems at once, what the reference computes one theta at a time inside its
+ * optimiser loop: GaussianProcess.loglikelihood (gp_emulator/GaussianProcess.py:78-95, i.e. _set_params ->
+ * _prepare_likelihood :52-75) and GaussianProcess.partial_devs (:97-125).  All problems share the training inputs
+ * (MultivariateEmulator.train_emulators fits every principal component on the same y_train,
+ * gp_emulator/multivariate_gp.py:176-186).  Host pointers; synchronous.
+ *   inputs   (M, D)      training inputs            == self.inputs
+ *   targets  (T, M)      T target vectors           == self.targets of each GP
+ *   target_index (B)     which target vector problem b fits (NULL: all use row 0)
+ *   thetas   (B, D + 2)  hyper-parameters (log inverse squared length scales, log signal variance, log noise)
+ *   loglik   (B)         the reference's cost: 1/2 log|Q| + 1/2 t' invQ t + M/2 log(2 pi)
+ *   grad     (B, D + 2)  its gradient, as partial_devs returns it
+ *   status   (B)         0, or 1 where Q is not positive definite / not finite (the reference's LinAlgError from
+ *                        np.linalg.cholesky, :73-75): loglik and grad of that problem are NaN
+ */
+#define GPE_TRAIN_MAX_M 1024
+typedef struct gpe_trainer gpe_trainer;
+int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, const double* targets, gpe_trainer** out);
+int gpe_trainer_eval(gpe_trainer* t, int B, const int* target_index, const double* thetas, double* loglik, double* grad,
+                     int* status);
+int gpe_trainer_destroy(gpe_trainer* t);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches claim). */
 int64_t gpe_launch_count(void);
 

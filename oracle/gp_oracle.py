@@ -20,9 +20,9 @@ import numpy as np
 import scipy.spatial.distance as _dist
 
 __all__ = [
-    "cross_covariance", "predict", "hessian", "prepare_likelihood", "predict_longdouble",
+    "cross_covariance", "predict", "hessian", "prepare_likelihood", "loglikelihood_and_grad", "predict_longdouble",
     "mv_compress", "mv_predict_point", "mv_predict_batch", "bank_predict",
-    "ref_err", "var_cond_err", "make_S_model", "make_T_model",
+    "ref_err", "var_cond_err", "make_S_model", "make_T_model", "make_training_problem",
 ]
 
 
@@ -116,6 +116,47 @@ def prepare_likelihood(inputs, targets, theta):
     invQ = np.linalg.inv(Q)
     invQt = np.dot(invQ, targets)
     return invQ, invQt
+
+
+def loglikelihood_and_grad(inputs, targets, theta):
+    """The training cost and its gradient at ``theta``: ``(loglik, partial_d (D + 2,))``.
+
+    gp_emulator/GaussianProcess.py:78-95 (loglikelihood = _set_params -> _prepare_likelihood :52-75, then
+    0.5 log|Q| + 0.5 t.invQt + 0.5 n log 2 pi) followed by partial_devs (:97-125) at the same theta -- the pair of
+    calls scipy's L-BFGS-B makes per evaluation (:171-173).  Same numpy calls, same operand order.
+    """
+    n, D = inputs.shape
+    e = np.exp(theta)
+    Z = np.zeros((n, n))
+    for d in range(D):                                                  # :61-66
+        col = np.tile(inputs[:, d], (n, 1))
+        Z = Z + e[d] * (col - col.T) ** 2
+    Z = e[D] * np.exp(-0.5 * Z)
+    Q = Z + e[D + 1] * np.eye(n)
+    invQ = np.linalg.inv(Q)
+    invQt = np.dot(invQ, targets)
+    logdetQ = 2.0 * np.sum(np.log(np.diag(np.linalg.cholesky(Q))))     # :73-75 (raises LinAlgError if Q is not PD)
+    ll = 0.5 * logdetQ + 0.5 * np.dot(targets, invQt) + 0.5 * n * np.log(2.0 * np.pi)   # :90-92
+    partial_d = np.zeros(D + 2)
+    for d in range(D):                                                  # :108-116
+        col = np.tile(inputs[:, d], (n, 1))
+        V = ((col - col.T) ** 2).T * Z
+        partial_d[d] = np.exp(theta[d]) * (np.dot(invQt, np.dot(V, invQt)) - np.sum(invQ * V)) / 4.0
+    partial_d[D] = 0.5 * np.sum(invQ * Z) - 0.5 * np.dot(invQt, np.dot(Z, invQt))        # :117-119
+    partial_d[D + 1] = 0.5 * np.trace(invQ) * np.exp(theta[D + 1]) - 0.5 * np.dot(invQt, invQt) * np.exp(theta[D + 1])
+    return ll, partial_d
+
+
+def make_training_problem(M=60, D=4, T=3, B=6, seed=21):
+    """Seeded training inputs (M, D), T smooth target vectors (T, M), B thetas drawn as the reference draws its
+    L-BFGS-B starts (5 (U - 0.5), gp_emulator/GaussianProcess.py:201) and the target row each theta is paired with."""
+    rs = np.random.RandomState(seed)
+    inputs = rs.random_sample((M, D))
+    k = np.arange(1, T + 1)[:, None]
+    targets = np.sin(k * (inputs @ np.linspace(1.0, 2.0, D))[None, :]) + 0.3 * np.cos(3.0 * inputs[:, 0])[None, :] / k
+    thetas = 5.0 * (rs.random_sample((B, D + 2)) - 0.5)
+    tidx = (np.arange(B) % T).astype(np.int32)
+    return inputs, targets, thetas, tidx
 
 
 def predict_longdouble(inputs, theta, invQ, invQt, testing, do_hess=False):

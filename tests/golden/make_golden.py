@@ -14,6 +14,7 @@ goldens is therefore the reference's own numpy/scipy code:
   GaussianProcess.hessian                 gp_emulator/GaussianProcess.py:345-366
   GaussianProcess._set_params             gp_emulator/GaussianProcess.py:52-75, 127-139
   MultivariateEmulator (dump=...) .predict gp_emulator/multivariate_gp.py:40-121, 195-222
+  GaussianProcess.loglikelihood / partial_devs  gp_emulator/GaussianProcess.py:78-125
 
     python tests/golden/make_golden.py [--only S1500]
 """
@@ -86,6 +87,20 @@ def main():
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % tag), **out)
         print(tag, "mu[:2]", mu[:2], "var[:2]", var[:2])
 
+    # ---- L: training objective and gradient (loglikelihood + partial_devs) at the reference's start distribution ----
+    if not only or only == "L":
+        out = {}
+        for tag, (M, D, T, B, seed) in {"a": (60, 4, 3, 6, 21), "b": (250, 10, 2, 4, 22), "c": (33, 2, 1, 5, 23)}.items():
+            inputs, targets, thetas, tidx = orc.make_training_problem(M, D, T, B, seed)
+            ll = np.empty(B); grad = np.empty((B, D + 2))
+            for n in range(B):
+                gp = RefGP(inputs, targets[tidx[n]])
+                ll[n] = gp.loglikelihood(thetas[n])
+                grad[n] = gp.partial_devs(thetas[n])
+            out.update({"shape_" + tag: np.array([M, D, T, B, seed]), "ll_" + tag: ll, "grad_" + tag: grad,
+                        "sha_" + tag: sha(inputs, targets, thetas)})
+            print("L%s  ll[:2]" % tag, ll[:2])
+        np.savez_compressed(os.path.join(HERE, "golden_L.npz"), **out)
     if only and only not in ("T", "P"):
         return
     # ---- T: genuinely conditioned model through the reference's own _set_params ---------------------
