@@ -9,10 +9,10 @@
 //
 // Per problem (one 1024-thread CTA, matrices in an L2-resident workspace, vectors in shared memory):
 //   1. Z_ij = b exp(-1/2 sum_d w_d (x_id - x_jd)^2), Q = Z + noise I                      (:61-69)
-//   2. in-place Gauss-Jordan inversion of Q without pivoting (Q is symmetric positive definite, so the pivots
-//      are the LDL^T pivots: log|Q| = sum log p_k, and a pivot <= 0 is the reference's LinAlgError from
-//      np.linalg.cholesky, :73-75).  M rank-1 updates of the whole matrix: M^3 FMA, 16 M^2 bytes of L2
-//      traffic per pivot.
+//   2. in-place block Gauss-Jordan inversion of Q without pivoting (Q is symmetric positive definite, so the
+//      pivots are the LDL^T pivots: log|Q| = sum log p_k, and a pivot <= 0 is the reference's LinAlgError from
+//      np.linalg.cholesky, :73-75).  M / 8 rank-8 updates of the whole matrix: M^3 FMA, 16 M^2 bytes of L2
+//      traffic per 8 pivots.
 //   3. alpha = invQ t, t.alpha, alpha.alpha, trace(invQ)                                   (:71-72, :118-121)
 //   4. g_d = -w_d/4 sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2,  g_D = 1/2 sum_ij (...) Z_ij,
 //      g_{D+1} = noise/2 (trace(invQ) - alpha.alpha)                                       (:108-122)
@@ -61,16 +61,22 @@ __device__ __forceinline__ double block_sum(double v, double* red, int lane, int
     return warp_sum(red[lane]);
 }
 
+constexpr int kNB = 8;  // pivots eliminated per pass over the matrix
+
 __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainParams p) {
     extern __shared__ double sm[];
+    __shared__ double Ps[kNB * kNB];   // pivot block -> its inverse
+    __shared__ int s_bad;
     const int M = p.M, D = p.D, nb = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    double* xs = sm;              // [M][D]
-    double* tt = xs + M * D;      // [M] targets
+    const int un = max(M * D, 3 * kNB * M);
+    double* xs = sm;              // [M][D]            (phases 1 and 4)
+    double* Rr = sm;              // [kNB][M] pivot rows, staged         (phase 2, aliases xs)
+    double* Cc = sm + kNB * M;      // [M][kNB] pivot columns, staged
+    double* Cf = sm + 2 * kNB * M;  // [M][kNB] per-row update coefficients
+    double* tt = sm + un;         // [M] targets
     double* alpha = tt + M;       // [M]
-    double* rowk = alpha + M;     // [M] pivot row, staged
-    double* colk = rowk + M;      // [M] pivot column, staged
-    double* ew = colk + M;        // [D + 2] exp(theta)
+    double* ew = alpha + M;       // [D + 2] exp(theta)
     double* red = ew + 40;        // [32]
     double* A = p.work + (size_t)nb * 2 * M * M;
     double* Z = A + (size_t)M * M;
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     const double* t = p.targets + (size_t)p.tidx[nb] * M;
     for (int i = tid; i < M; i += kTrainThreads) tt[i] = t[i];
     if (tid < D + 2) ew[tid] = exp(p.thetas[(size_t)nb * (D + 2) + tid]);
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     const double bb = ew[D], noise = ew[D + 1];
 
@@ -96,44 +103,95 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
         }
     __syncthreads();
 
-    // 2. Gauss-Jordan, pivot by pivot; two rows per warp pass so 16 loads are in flight per thread
+    // 2. block Gauss-Jordan: kNB pivots per pass.  With K the pivot index block, R = A[K, :], C = A[:, K], P = A[K, K]:
+    //      A[K, K] <- inv(P),  A[K, J] <- inv(P) R,  A[I, K] <- -C inv(P),  A[I, J] <- A[I, J] - C inv(P) R
+    //    i.e. every row i is  base_i + coef_i . R  with coef_i = inv(P)[i - k0, :] (base 0) for pivot rows and
+    //    -C[i, :] inv(P) (base A[i, :]) otherwise, and in the pivot columns the new value is coef_i[j - k0].
+    //    inv(P) by scalar Gauss-Jordan inside the block (one warp): its pivots are the LDL^T pivots of Q.
     double logdet = 0.0;
     bool bad = false;
-    for (int k = 0; k < M; ++k) {
-        for (int i = tid; i < M; i += kTrainThreads) {
-            rowk[i] = A[(size_t)k * M + i];
-            colk[i] = A[(size_t)i * M + k];
+    for (int k0 = 0; k0 < M; k0 += kNB) {
+        const int n = min(kNB, M - k0);
+        for (int e = tid; e < kNB * M; e += kTrainThreads) {
+            const int a = e / M, j = e - a * M;
+            Rr[e] = (a < n) ? A[(size_t)(k0 + a) * M + j] : 0.0;
+        }
+        for (int e = tid; e < M * kNB; e += kTrainThreads) {
+            const int i = e / kNB, a = e - i * kNB;
+            Cc[e] = (a < n) ? A[(size_t)i * M + k0 + a] : 0.0;
         }
         __syncthreads();
-        const double piv = rowk[k];
-        if (!(piv > 0.0) || !(piv < 1e300)) { bad = true; break; }   // same value in every thread: uniform exit
-        const double ip = 1.0 / piv;
-        if (tid == 0) logdet += log(piv);
-        for (int i0 = wid; i0 < M; i0 += 2 * kTrainWarps) {
-            const int i1 = i0 + kTrainWarps;
-            const bool has1 = i1 < M;
-            const double c0 = colk[i0] * ip, c1 = has1 ? colk[i1] * ip : 0.0;
-            double* a0 = A + (size_t)i0 * M;
-            double* a1 = A + (size_t)(has1 ? i1 : i0) * M;
-            for (int j0 = lane; j0 < M; j0 += 256) {
-                double v0[8], v1[8];
+        if (wid == 0) {
+            // lane owns block entries (a0, b) and (a0 + 4, b); a short last block is padded with the identity
+            const int a0 = lane >> 3, a1 = a0 + 4, b = lane & 7;
+            double v0 = (a0 < n && b < n) ? Rr[a0 * M + k0 + b] : (a0 == b ? 1.0 : 0.0);
+            double v1 = (a1 < n && b < n) ? Rr[a1 * M + k0 + b] : (a1 == b ? 1.0 : 0.0);
+            Ps[a0 * kNB + b] = v0;
+            Ps[a1 * kNB + b] = v1;
+            __syncwarp();
+            bool wbad = false;
+            double mypiv = 1.0;   // lane k keeps pivot k: the logarithms are taken after the loop, in parallel
+            for (int k = 0; k < kNB; ++k) {
+                const double piv = Ps[k * kNB + k];
+                if (!(piv > 0.0) || !(piv < 1e300)) { wbad = true; break; }   // same value in every lane
+                const double ip = 1.0 / piv;
+                const double r = Ps[k * kNB + b], c0 = Ps[a0 * kNB + k] * ip, c1 = Ps[a1 * kNB + k] * ip;
+                __syncwarp();
+                v0 = (a0 == k) ? ((b == k) ? ip : r * ip) : ((b == k) ? -c0 : fma(-c0, r, v0));
+                v1 = (a1 == k) ? ((b == k) ? ip : r * ip) : ((b == k) ? -c1 : fma(-c1, r, v1));
+                Ps[a0 * kNB + b] = v0;
+                Ps[a1 * kNB + b] = v1;
+                if (lane == k) mypiv = piv;
+                __syncwarp();
+            }
+            if (wbad) {
+                if (lane == 0) s_bad = 1;
+            } else {
+                logdet += warp_sum(lane < kNB ? log(mypiv) : 0.0);   // (identity padding contributes log 1 = 0)
+            }
+        }
+        __syncthreads();
+        if (s_bad) { bad = true; break; }   // uniform
+        for (int e = tid; e < M * kNB; e += kTrainThreads) {
+            const int i = e / kNB, bq = e - i * kNB, ai = i - k0;
+            double s = 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = j0 + 32 * u;
-                    v0[u] = (j < M) ? a0[j] : 0.0;
-                    v1[u] = (has1 && j < M) ? a1[j] : 0.0;
+            for (int a = 0; a < kNB; ++a) s = fma(Cc[i * kNB + a], Ps[a * kNB + bq], s);
+            Cf[e] = (ai >= 0 && ai < n) ? Ps[ai * kNB + bq] : -s;
+        }
+        __syncthreads();
+        for (int j = lane; j < M; j += 32) {
+            double rr[kNB];
+#pragma unroll
+            for (int a = 0; a < kNB; ++a) rr[a] = Rr[a * M + j];
+            const int jj = j - k0;
+            const bool jpiv = jj >= 0 && jj < n;
+            for (int i0 = wid; i0 < M; i0 += 8 * kTrainWarps) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = i0 + q * kTrainWarps;
+                    v[q] = (i < M) ? A[(size_t)i * M + j] : 0.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = j0 + 32 * u;
-                    if (j < M) {
-                        const double r = rowk[j];
-                        a0[j] = (i0 == k) ? ((j == k) ? ip : r * ip) : ((j == k) ? -c0 : fma(-c0, r, v0[u]));
-                        if (has1) a1[j] = (i1 == k) ? ((j == k) ? ip : r * ip) : ((j == k) ? -c1 : fma(-c1, r, v1[u]));
+                for (int q = 0; q < 8; ++q) {
+                    const int i = i0 + q * kTrainWarps;
+                    if (i < M) {
+                        const double* cf = Cf + i * kNB;   // warp-uniform address: broadcast loads
+                        const bool ipiv = (unsigned)(i - k0) < (unsigned)n;
+                        double acc = ipiv ? 0.0 : v[q];
+#pragma unroll
+                        for (int a = 0; a < kNB; ++a) acc = fma(cf[a], rr[a], acc);
+                        if (jpiv) acc = cf[jj];
+                        A[(size_t)i * M + j] = acc;
                     }
                 }
             }
         }
+        __syncthreads();
+    }
+    if (!bad) {   // the staging buffers overwrote the training inputs
+        for (int i = tid; i < M * D; i += kTrainThreads) xs[i] = p.x[i];
         __syncthreads();
     }
     const int G = D + 2;
@@ -148,8 +206,16 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
 
     // 3. alpha = invQ t and the scalar sums
     for (int i = wid; i < M; i += kTrainWarps) {
+        const double* ai = A + (size_t)i * M;
         double s = 0.0;
-        for (int j = lane; j < M; j += 32) s = fma(A[(size_t)i * M + j], tt[j], s);
+        for (int j0 = lane; j0 < M; j0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (j0 + 32 * u < M) ? ai[j0 + 32 * u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + 32 * u < M) s = fma(v[u], tt[j0 + 32 * u], s);
+        }
         s = warp_sum(s);
         if (lane == 0) alpha[i] = s;
     }
@@ -164,25 +230,53 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     s_aa = block_sum(s_aa, red, lane, wid);
     s_tr = block_sum(s_tr, red, lane, wid);
 
-    // 4. gradient: one pass over (invQ - alpha alpha^T) o Z per hyper-parameter (D + 1 passes, L2-resident)
-    for (int d = 0; d <= D; ++d) {
-        double acc = 0.0;
-        for (int i = wid; i < M; i += kTrainWarps) {
-            const double ai = alpha[i];
-            const double xi = (d < D) ? xs[i * D + d] : 0.0;
-            double part = 0.0;
-            for (int j = lane; j < M; j += 32) {
-                double w = fma(-ai, alpha[j], A[(size_t)i * M + j]) * Z[(size_t)i * M + j];
-                if (d < D) {
-                    const double df = xi - xs[j * D + d];
-                    w *= df * df;
+    // 4. gradient sums  S_d = sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2  (d < D)  and  S_D = sum_ij (...) Z_ij,
+    //    kGS accumulators per pass over the two matrices (D = 10: two passes), four rows in flight per thread
+    constexpr int kGS = 8;
+    for (int d0 = 0; d0 <= D; d0 += kGS) {
+        double acc[kGS];
+#pragma unroll
+        for (int dd = 0; dd < kGS; ++dd) acc[dd] = 0.0;
+        for (int j = lane; j < M; j += 32) {
+            const double aj = alpha[j];
+            double xj[kGS];
+#pragma unroll
+            for (int dd = 0; dd < kGS; ++dd) xj[dd] = (d0 + dd < D) ? xs[j * D + d0 + dd] : 0.0;
+            for (int i0 = wid; i0 < M; i0 += 4 * kTrainWarps) {
+                double va[4], vz[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * kTrainWarps;
+                    va[q] = (i < M) ? A[(size_t)i * M + j] : 0.0;
+                    vz[q] = (i < M) ? Z[(size_t)i * M + j] : 0.0;
                 }
-                part += w;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * kTrainWarps;
+                    if (i < M) {
+                        const double wz = fma(-alpha[i], aj, va[q]) * vz[q];
+#pragma unroll
+                        for (int dd = 0; dd < kGS; ++dd) {
+                            const int d = d0 + dd;
+                            if (d < D) {
+                                const double df = xs[i * D + d] - xj[dd];
+                                acc[dd] = fma(wz * df, df, acc[dd]);
+                            } else if (d == D) {
+                                acc[dd] += wz;
+                            }
+                        }
+                    }
+                }
             }
-            acc += part;
         }
-        acc = block_sum(acc, red, lane, wid);
-        if (tid == 0) p.grad[(size_t)nb * G + d] = (d < D) ? -0.25 * ew[d] * acc : 0.5 * acc;
+#pragma unroll
+        for (int dd = 0; dd < kGS; ++dd) {
+            const int d = d0 + dd;
+            if (d <= D) {   // uniform
+                const double sum = block_sum(acc[dd], red, lane, wid);
+                if (tid == 0) p.grad[(size_t)nb * G + d] = (d < D) ? -0.25 * ew[d] * sum : 0.5 * sum;
+            }
+        }
     }
     if (tid == 0) {
         p.grad[(size_t)nb * G + D + 1] = 0.5 * noise * (s_tr - s_aa);
@@ -257,7 +351,7 @@ int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, co
     if (D > GPE_MAX_INPUTS) return set_error(GPE_ERR_UNSUPPORTED, "D = %d exceeds GPE_MAX_INPUTS = %d", D, GPE_MAX_INPUTS);
     if (M > GPE_TRAIN_MAX_M) return set_error(GPE_ERR_UNSUPPORTED, "M = %d exceeds GPE_TRAIN_MAX_M = %d", M, GPE_TRAIN_MAX_M);
     if (!inputs || !targets) return set_error(GPE_ERR_INVALID, "inputs / targets is NULL");
-    const size_t smem = ((size_t)M * D + 4 * (size_t)M + 40 + 32) * 8;
+    const size_t smem = (std::max((size_t)M * D, (size_t)24 * M) + 2 * (size_t)M + 40 + 32) * 8;
     if (smem > 232448) return set_error(GPE_ERR_UNSUPPORTED, "M x D = %d x %d needs %zu bytes of shared memory per CTA", M, D, smem);
     int sms = 0;
     int rc = require_device(device, &sms);

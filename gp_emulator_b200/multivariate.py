@@ -19,11 +19,11 @@ from .gaussian_process import GaussianProcess
 
 class MultivariateEmulator(object):
     def __init__(self, dump=None, X=None, y=None, hyperparams=None, thresh=0.98, n_tries=5, device=0,
-                 batched_training=False):
+                 batched_training=False, basis_functions=None, n_pcs=None):
         """See reference multivariate_gp.py:40-121.  ``X`` (N_train, N_full) model outputs, ``y``
         (N_train, N_params) the parameters that produced them, ``hyperparams`` (N_params + 2, n_pcs)."""
-        basis_functions = None
-        n_pcs = None
+        if basis_functions is not None and n_pcs is None:      # (EmulatorStorage hands a stored basis back in)
+            n_pcs = basis_functions.shape[0]
         if dump is not None:
             if X is not None or y is not None:
                 raise ValueError("You specified both a dump file and X and y")

@@ -15,6 +15,7 @@ goldens is therefore the reference's own numpy/scipy code:
   GaussianProcess._set_params             gp_emulator/GaussianProcess.py:52-75, 127-139
   MultivariateEmulator (dump=...) .predict gp_emulator/multivariate_gp.py:40-121, 195-222
   GaussianProcess.loglikelihood / partial_devs  gp_emulator/GaussianProcess.py:78-125
+  lhd                                     gp_emulator/lhd.py:11-269
 
     python tests/golden/make_golden.py [--only S1500]
 """
@@ -101,6 +102,21 @@ def main():
                         "sha_" + tag: sha(inputs, targets, thetas)})
             print("L%s  ll[:2]" % tag, ll[:2])
         np.savez_compressed(os.path.join(HERE, "golden_L.npz"), **out)
+    # ---- U: lhd designs under a seeded legacy numpy RNG (gp_emulator/lhd.py:11-269) ---------------------------------
+    if not only or only == "U":
+        import scipy.stats as ss
+        lhd_mod = types.ModuleType("ref_lhd")
+        with open(os.path.join(REF, "gp_emulator", "lhd.py")) as f:
+            exec(compile(py2to3(f.read()), "ref:lhd.py", "exec"), lhd_mod.__dict__)
+        d0, d1, d2, d3 = ss.uniform(loc=-1, scale=2), ss.norm(loc=0, scale=1), ss.beta(2, 5), ss.expon(scale=1 / 1.5)
+        out = {}
+        np.random.seed(5); out["single"] = lhd_mod.lhd(dist=d0, size=5)
+        np.random.seed(6); out["dims"] = lhd_mod.lhd(dist=d1, size=7, dims=5)
+        np.random.seed(7); out["multi"] = lhd_mod.lhd(dist=(d1, d2, d3), size=6)
+        np.random.seed(8); out["big"] = lhd_mod.lhd(dist=(d0, d1, d2, d3), size=100)
+        np.random.seed(9); out["space"] = lhd_mod.lhd(dist=(d0, d1, d2, d3), size=12, form="spacefilling", iterations=7)
+        np.savez_compressed(os.path.join(HERE, "golden_U.npz"), **out)
+        print("U   single", out["single"].ravel())
     if only and only not in ("T", "P"):
         return
     # ---- T: genuinely conditioned model through the reference's own _set_params ---------------------
