@@ -11,8 +11,8 @@
 //   1. Z_ij = b exp(-1/2 sum_d w_d (x_id - x_jd)^2), Q = Z + noise I                      (:61-69)
 //   2. in-place block Gauss-Jordan inversion of Q without pivoting (Q is symmetric positive definite, so the
 //      pivots are the LDL^T pivots: log|Q| = sum log p_k, and a pivot <= 0 is the reference's LinAlgError from
-//      np.linalg.cholesky, :73-75).  M / 8 rank-8 updates of the whole matrix: M^3 FMA, 16 M^2 bytes of L2
-//      traffic per 8 pivots.
+//      np.linalg.cholesky, :73-75).  M / 8 rank-8 updates of the whole matrix on the FP64 tensor cores
+//      (DMMA.8x8x4): M^3 FMA, 16 M^2 bytes of L2 traffic per 8 pivots.
 //   3. alpha = invQ t, t.alpha, alpha.alpha, trace(invQ)                                   (:71-72, :118-121)
 //   4. g_d = -w_d/4 sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2,  g_D = 1/2 sum_ij (...) Z_ij,
 //      g_{D+1} = noise/2 (trace(invQ) - alpha.alpha)                                       (:108-122)
@@ -61,25 +61,27 @@ __device__ __forceinline__ double block_sum(double v, double* red, int lane, int
     return warp_sum(red[lane]);
 }
 
-constexpr int kNB = 8;  // pivots eliminated per pass over the matrix
+constexpr int kNB = 8;  // pivots eliminated per pass over the matrix == DMMA tile edge
 
+// Work matrices are stored with pitch Mp = M rounded up to 8 and padded with the identity (Q_pad = diag(Q, I)), so
+// that every 8 x 8 tile is full: inv(Q_pad) = diag(inv(Q), I), the padded pivots are 1 and add log 1 = 0.
 __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainParams p) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     __shared__ double Ps[kNB * kNB];   // pivot block -> its inverse
     __shared__ int s_bad;
-    const int M = p.M, D = p.D, nb = blockIdx.x;
+    const int M = p.M, D = p.D, Mp = (M + 7) & ~7, nb = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int un = max(M * D, 3 * kNB * M);
-    double* xs = sm;              // [M][D]            (phases 1 and 4)
-    double* Rr = sm;              // [kNB][M] pivot rows, staged         (phase 2, aliases xs)
-    double* Cc = sm + kNB * M;      // [M][kNB] pivot columns, staged
-    double* Cf = sm + 2 * kNB * M;  // [M][kNB] per-row update coefficients
-    double* tt = sm + un;         // [M] targets
-    double* alpha = tt + M;       // [M]
-    double* ew = alpha + M;       // [D + 2] exp(theta)
-    double* red = ew + 40;        // [32]
-    double* A = p.work + (size_t)nb * 2 * M * M;
-    double* Z = A + (size_t)M * M;
+    const int un = max(M * D, 3 * kNB * Mp);
+    double* xs = sm;                  // [M][D]                                    (phases 1 and 4)
+    double* RrT = sm;                 // [2][Mp][4]: RrT[kk][j][c] = A[k0 + 4 kk + c][j], the DMMA B operand (phase 2)
+    double* Cc = sm + kNB * Mp;       // [Mp][8] pivot columns, staged
+    double* CfT = sm + 2 * kNB * Mp;  // [2][Mp][4]: CfT[kk][i][c] = coef_i[4 kk + c], the DMMA A operand
+    double* tt = sm + un;             // [M] targets
+    double* alpha = tt + M;           // [M]
+    double* ew = alpha + M;           // [D + 2] exp(theta)
+    double* red = ew + 40;            // [32]
+    double* A = p.work + (size_t)nb * 2 * Mp * Mp;
+    double* Z = A + (size_t)Mp * Mp;
 
     for (int i = tid; i < M * D; i += kTrainThreads) xs[i] = p.x[i];
     const double* t = p.targets + (size_t)p.tidx[nb] * M;
@@ -89,43 +91,47 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     __syncthreads();
     const double bb = ew[D], noise = ew[D + 1];
 
-    // 1. covariance of the training set
-    for (int i = wid; i < M; i += kTrainWarps)
-        for (int j = lane; j < M; j += 32) {
-            double r2 = 0.0;
-            for (int d = 0; d < D; ++d) {
-                const double df = xs[i * D + d] - xs[j * D + d];
-                r2 += ew[d] * (df * df);
+    // 1. covariance of the training set (reference GaussianProcess.py:61-69), identity in the padding
+    for (int i = wid; i < Mp; i += kTrainWarps)
+        for (int j = lane; j < Mp; j += 32) {
+            if (i < M && j < M) {
+                double r2 = 0.0;
+                for (int d = 0; d < D; ++d) {
+                    const double df = xs[i * D + d] - xs[j * D + d];
+                    r2 += ew[d] * (df * df);
+                }
+                const double z = bb * exp_neg(-0.5 * r2);
+                Z[i * Mp + j] = z;
+                A[i * Mp + j] = (i == j) ? z + noise : z;
+            } else {
+                A[i * Mp + j] = (i == j) ? 1.0 : 0.0;
             }
-            const double z = bb * exp_neg(-0.5 * r2);
-            Z[(size_t)i * M + j] = z;
-            A[(size_t)i * M + j] = (i == j) ? z + noise : z;
         }
     __syncthreads();
 
-    // 2. block Gauss-Jordan: kNB pivots per pass.  With K the pivot index block, R = A[K, :], C = A[:, K], P = A[K, K]:
+    // 2. block Gauss-Jordan, 8 pivots per pass.  With K the pivot index block, R = A[K, :], C = A[:, K], P = A[K, K]:
     //      A[K, K] <- inv(P),  A[K, J] <- inv(P) R,  A[I, K] <- -C inv(P),  A[I, J] <- A[I, J] - C inv(P) R
-    //    i.e. every row i is  base_i + coef_i . R  with coef_i = inv(P)[i - k0, :] (base 0) for pivot rows and
-    //    -C[i, :] inv(P) (base A[i, :]) otherwise, and in the pivot columns the new value is coef_i[j - k0].
-    //    inv(P) by scalar Gauss-Jordan inside the block (one warp): its pivots are the LDL^T pivots of Q.
+    //    i.e. every row i becomes  base_i + coef_i . R  with coef_i = inv(P)[i - k0, :] and base 0 for the pivot rows,
+    //    coef_i = -C[i, :] inv(P) and base A[i, :] otherwise, except in the pivot columns where the new value is
+    //    coef_i[j - k0].  That rank-8 update of the whole matrix runs on the FP64 tensor cores: per 8 x 8 tile two
+    //    DMMA.8x8x4 with the accumulator fragment loaded from / stored to the L2-resident matrix (16 bytes per lane,
+    //    64 contiguous bytes per row), operands pre-arranged in shared memory in fragment order (conflict-free).
+    //    inv(P) by scalar Gauss-Jordan inside the block (warp 0): its pivots are the LDL^T pivots of Q.
     double logdet = 0.0;
     bool bad = false;
-    for (int k0 = 0; k0 < M; k0 += kNB) {
-        const int n = min(kNB, M - k0);
-        for (int e = tid; e < kNB * M; e += kTrainThreads) {
-            const int a = e / M, j = e - a * M;
-            Rr[e] = (a < n) ? A[(size_t)(k0 + a) * M + j] : 0.0;
+    const int g = lane >> 2, c4 = lane & 3, ntile = Mp / kNB;
+    for (int k0 = 0; k0 < Mp; k0 += kNB) {
+        for (int e = tid; e < kNB * Mp; e += kTrainThreads) {
+            const int a = e / Mp, j = e - a * Mp;
+            RrT[(a >> 2) * Mp * 4 + j * 4 + (a & 3)] = A[(k0 + a) * Mp + j];
         }
-        for (int e = tid; e < M * kNB; e += kTrainThreads) {
-            const int i = e / kNB, a = e - i * kNB;
-            Cc[e] = (a < n) ? A[(size_t)i * M + k0 + a] : 0.0;
-        }
+        for (int e = tid; e < Mp * kNB; e += kTrainThreads) Cc[e] = A[(e >> 3) * Mp + k0 + (e & 7)];
         __syncthreads();
         if (wid == 0) {
-            // lane owns block entries (a0, b) and (a0 + 4, b); a short last block is padded with the identity
+            // lane owns block entries (a0, b) and (a0 + 4, b)
             const int a0 = lane >> 3, a1 = a0 + 4, b = lane & 7;
-            double v0 = (a0 < n && b < n) ? Rr[a0 * M + k0 + b] : (a0 == b ? 1.0 : 0.0);
-            double v1 = (a1 < n && b < n) ? Rr[a1 * M + k0 + b] : (a1 == b ? 1.0 : 0.0);
+            double v0 = RrT[(k0 + b) * 4 + a0];                  // A[k0 + a0][k0 + b]
+            double v1 = RrT[Mp * 4 + (k0 + b) * 4 + a0];         // A[k0 + a0 + 4][k0 + b]
             Ps[a0 * kNB + b] = v0;
             Ps[a1 * kNB + b] = v1;
             __syncwarp();
@@ -147,51 +153,46 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
             if (wbad) {
                 if (lane == 0) s_bad = 1;
             } else {
-                logdet += warp_sum(lane < kNB ? log(mypiv) : 0.0);   // (identity padding contributes log 1 = 0)
+                logdet += warp_sum(lane < kNB ? log(mypiv) : 0.0);
             }
         }
         __syncthreads();
         if (s_bad) { bad = true; break; }   // uniform
-        for (int e = tid; e < M * kNB; e += kTrainThreads) {
-            const int i = e / kNB, bq = e - i * kNB, ai = i - k0;
+        for (int e = tid; e < Mp * kNB; e += kTrainThreads) {
+            const int i = e >> 3, bq = e & 7;
             double s = 0.0;
 #pragma unroll
             for (int a = 0; a < kNB; ++a) s = fma(Cc[i * kNB + a], Ps[a * kNB + bq], s);
-            Cf[e] = (ai >= 0 && ai < n) ? Ps[ai * kNB + bq] : -s;
+            const bool prow = (i & ~7) == k0;
+            CfT[(bq >> 2) * Mp * 4 + i * 4 + (bq & 3)] = prow ? Ps[(i & 7) * kNB + bq] : -s;
         }
         __syncthreads();
-        for (int j = lane; j < M; j += 32) {
-            double rr[kNB];
-#pragma unroll
-            for (int a = 0; a < kNB; ++a) rr[a] = Rr[a * M + j];
-            const int jj = j - k0;
-            const bool jpiv = jj >= 0 && jj < n;
-            for (int i0 = wid; i0 < M; i0 += 8 * kTrainWarps) {
-                double v[8];
+        for (int rt = wid; rt < ntile; rt += kTrainWarps) {
+            const int i0 = rt * kNB;
+            const bool prow = (i0 == k0);
+            const double a_lo = CfT[(i0 + g) * 4 + c4], a_hi = CfT[Mp * 4 + (i0 + g) * 4 + c4];
+            double* arow = A + (i0 + g) * Mp + 2 * c4;   // this lane's two accumulator columns of tile 0
+            for (int ct0 = 0; ct0 < ntile; ct0 += 8) {
+                double2 c[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int i = i0 + q * kTrainWarps;
-                    v[q] = (i < M) ? A[(size_t)i * M + j] : 0.0;
+                    c[q] = make_double2(0.0, 0.0);
+                    if (ct0 + q < ntile && !prow) c[q] = *reinterpret_cast<const double2*>(arow + (ct0 + q) * kNB);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int i = i0 + q * kTrainWarps;
-                    if (i < M) {
-                        const double* cf = Cf + i * kNB;   // warp-uniform address: broadcast loads
-                        const bool ipiv = (unsigned)(i - k0) < (unsigned)n;
-                        double acc = ipiv ? 0.0 : v[q];
-#pragma unroll
-                        for (int a = 0; a < kNB; ++a) acc = fma(cf[a], rr[a], acc);
-                        if (jpiv) acc = cf[jj];
-                        A[(size_t)i * M + j] = acc;
+                    const int j0 = (ct0 + q) * kNB;
+                    if (ct0 + q < ntile) {   // warp-uniform
+                        const double b_lo = RrT[(j0 + g) * 4 + c4], b_hi = RrT[Mp * 4 + (j0 + g) * 4 + c4];
+                        dmma_m8n8k4(c[q].x, c[q].y, a_lo, b_lo);
+                        dmma_m8n8k4(c[q].x, c[q].y, a_hi, b_hi);
+                        if (j0 == k0)        // pivot columns: coef_i[2 c4], coef_i[2 c4 + 1]
+                            c[q] = *reinterpret_cast<const double2*>(CfT + (c4 >> 1) * Mp * 4 + (i0 + g) * 4 + ((2 * c4) & 3));
+                        *reinterpret_cast<double2*>(arow + j0) = c[q];
                     }
                 }
             }
         }
-        __syncthreads();
-    }
-    if (!bad) {   // the staging buffers overwrote the training inputs
-        for (int i = tid; i < M * D; i += kTrainThreads) xs[i] = p.x[i];
         __syncthreads();
     }
     const int G = D + 2;
@@ -203,10 +204,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
         }
         return;
     }
+    for (int i = tid; i < M * D; i += kTrainThreads) xs[i] = p.x[i];   // the staging buffers overwrote the inputs
+    __syncthreads();
 
     // 3. alpha = invQ t and the scalar sums
     for (int i = wid; i < M; i += kTrainWarps) {
-        const double* ai = A + (size_t)i * M;
+        const double* ai = A + i * Mp;
         double s = 0.0;
         for (int j0 = lane; j0 < M; j0 += 256) {
             double v[8];
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     for (int i = tid; i < M; i += kTrainThreads) {
         s_ta = fma(tt[i], alpha[i], s_ta);
         s_aa = fma(alpha[i], alpha[i], s_aa);
-        s_tr += A[(size_t)i * M + i];
+        s_tr += A[i * Mp + i];
     }
     s_ta = block_sum(s_ta, red, lane, wid);
     s_aa = block_sum(s_aa, red, lane, wid);
@@ -247,8 +250,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = i0 + q * kTrainWarps;
-                    va[q] = (i < M) ? A[(size_t)i * M + j] : 0.0;
-                    vz[q] = (i < M) ? Z[(size_t)i * M + j] : 0.0;
+                    va[q] = (i < M) ? A[i * Mp + j] : 0.0;
+                    vz[q] = (i < M) ? Z[i * Mp + j] : 0.0;
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -329,7 +332,7 @@ void free_batch_buffers(gpe_trainer* t) {
 int reserve(gpe_trainer* t, int nb) {
     if (nb <= t->cap) return GPE_OK;
     free_batch_buffers(t);
-    const size_t G = (size_t)t->D + 2, mm = (size_t)t->M * t->M;
+    const size_t G = (size_t)t->D + 2, mp = ((size_t)t->M + 7) / 8 * 8, mm = mp * mp;
     TR_TRY(cudaMalloc((void**)&t->d_work, (size_t)nb * 2 * mm * 8));
     TR_TRY(cudaMalloc((void**)&t->d_theta, (size_t)nb * G * 8));
     TR_TRY(cudaMalloc((void**)&t->d_ll, (size_t)nb * 8));
@@ -351,7 +354,7 @@ int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, co
     if (D > GPE_MAX_INPUTS) return set_error(GPE_ERR_UNSUPPORTED, "D = %d exceeds GPE_MAX_INPUTS = %d", D, GPE_MAX_INPUTS);
     if (M > GPE_TRAIN_MAX_M) return set_error(GPE_ERR_UNSUPPORTED, "M = %d exceeds GPE_TRAIN_MAX_M = %d", M, GPE_TRAIN_MAX_M);
     if (!inputs || !targets) return set_error(GPE_ERR_INVALID, "inputs / targets is NULL");
-    const size_t smem = (std::max((size_t)M * D, (size_t)24 * M) + 2 * (size_t)M + 40 + 32) * 8;
+    const size_t smem = (std::max((size_t)M * D, (size_t)24 * ((M + 7) / 8 * 8)) + 2 * (size_t)M + 40 + 32) * 8;
     if (smem > 232448) return set_error(GPE_ERR_UNSUPPORTED, "M x D = %d x %d needs %zu bytes of shared memory per CTA", M, D, smem);
     int sms = 0;
     int rc = require_device(device, &sms);
@@ -396,7 +399,7 @@ int gpe_trainer_eval(gpe_trainer* t, int B, const int* target_index, const doubl
                 return set_error(GPE_ERR_INVALID, "target_index[%d] = %d out of range [0, %d)", i, target_index[i], t->T);
     std::lock_guard<std::mutex> lock(t->mu);
     TR_TRY(cudaSetDevice(t->device));
-    const size_t G = (size_t)t->D + 2, mm = (size_t)t->M * t->M;
+    const size_t G = (size_t)t->D + 2, mp = ((size_t)t->M + 7) / 8 * 8, mm = mp * mp;
     // problems per launch: whole waves of CTAs, workspace bounded by 4 GB
     const int by_mem = (int)std::max<size_t>(1, ((size_t)4 << 30) / (2 * mm * 8));
     const int chunk = std::min(B, std::min(by_mem, 8 * t->sms));
