@@ -157,6 +157,29 @@ def test_trainer_default_target_and_reuse():
 
 
 @pytest.mark.gpu
+def test_trainer_batches_larger_than_one_launch_and_shared_by_threads():
+    """More problems than one launch takes (8 per SM) are walked in chunks; threads may share a trainer (serialised)."""
+    import threading
+    inputs, targets, thetas, tidx = orc.make_training_problem(9, 2, 3, 1500, seed=12)
+    tr = DeviceTrainer(inputs, targets)
+    ll, grad, st = tr.evaluate(thetas, tidx)
+    assert not st.any()
+    for n in (0, 1183, 1184, 1185, 1499):
+        ll_o, grad_o = orc.loglikelihood_and_grad(inputs, targets[tidx[n]], thetas[n])
+        assert abs(ll[n] - ll_o) <= TOL * abs(ll_o) and orc.ref_err(grad[n], grad_o) < TOL
+    got = {}
+
+    def work(k):
+        got[k] = tr.evaluate(thetas[k * 100:(k + 1) * 100], tidx[k * 100:(k + 1) * 100])
+    th = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    tr.close()
+    for k in range(6):
+        assert np.array_equal(got[k][0], ll[k * 100:(k + 1) * 100]) and np.array_equal(got[k][1], grad[k * 100:(k + 1) * 100])
+
+
+@pytest.mark.gpu
 def test_trainer_flags_non_positive_definite_covariance():
     """Duplicate training inputs and (numerically) zero noise make Q singular: np.linalg.cholesky raises in the reference
     (GaussianProcess.py:73-75); here the problem comes back with status 1 and NaNs, its neighbours untouched."""
