@@ -5,7 +5,7 @@ The reference fits each GP with ``n_tries`` independent L-BFGS-B descents (gp_em
 (gp_emulator/multivariate_gp.py:176-186): n_pcs x n_tries descents, each evaluation a fresh M x M inverse in numpy
 (~0.1 s at M = 250, D = 10).  Here the descents stay what they are -- scipy's ``fmin_l_bfgs_b`` with the reference's
 settings (``factr=0.1, pgtol=1e-20``), one per start, so every descent follows the reference's trajectory to rounding --
-but they run in lockstep threads, and every round of function + gradient requests is served by ONE call of
+but they advance in lockstep, and every round of function + gradient requests is served by ONE call of
 ``gpe_trainer_eval`` (one CTA per (theta, target) problem, csrc/train.cu).
 
 The final state of the chosen theta (``invQ``, ``invQt``) is still produced by the host ``_set_params``
@@ -118,7 +118,145 @@ class _Rendezvous:
                 self._flush()
 
 
-def minimise_batched(evaluate, starts, verbose=False):
+# ---- single-thread lockstep driver ---------------------------------------------------------------------------------
+# scipy's L-BFGS-B is a reverse-communication routine: ``setulb`` returns to its caller whenever it needs the cost and
+# gradient at a new point.  ``fmin_l_bfgs_b`` hides that behind a callback, which is why the portable driver below needs
+# one thread per descent; driving ``setulb`` directly lets ONE thread advance every descent to its next request, evaluate
+# the batch, and hand the values back -- no thread hand-offs (they cost ~4x the optimiser's own work per evaluation).
+# ``setulb`` is private to scipy, so this driver mirrors the loop of ``scipy.optimize._lbfgsb_py._minimize_lbfgsb`` and is
+# only used after a self-test has reproduced ``fmin_l_bfgs_b`` bit for bit on the installed scipy (else: threads).
+_RC_STATE = {"checked": False, "ok": False}
+
+
+class _Descent:
+    """Workspace of one L-BFGS-B minimisation in reverse-communication form (m = 10, maxls = 20, no bounds,
+    maxfun = maxiter = 15000: the defaults ``fmin_l_bfgs_b`` runs with in the reference call)."""
+    M_CORR, MAXLS, MAXFUN, MAXITER = 10, 20, 15000, 15000
+
+    def __init__(self, setulb, int_dtype, x0, factr, pgtol):
+        n = x0.size
+        m = self.M_CORR
+        self._setulb, self.factr, self.pgtol = setulb, factr, pgtol
+        self.x = np.array(x0, dtype=np.float64)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n, dtype=np.float64)
+        self.nbd = np.zeros(n, dtype=int_dtype)
+        self.low = np.zeros(n, dtype=np.float64)
+        self.up = np.zeros(n, dtype=np.float64)
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=int_dtype)
+        self.task = np.zeros(2, dtype=int_dtype)
+        self.ln_task = np.zeros(2, dtype=int_dtype)
+        self.lsave = np.zeros(4, dtype=int_dtype)
+        self.isave = np.zeros(44, dtype=int_dtype)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.nit = 0
+        self.nfev = 0
+
+    def advance(self):
+        """Run the optimiser until it asks for cost + gradient at ``self.x`` (True) or stops (False)."""
+        while True:
+            self._setulb(self.M_CORR, self.x, self.low, self.up, self.nbd, self.f, self.g, self.factr, self.pgtol,
+                         self.wa, self.iwa, self.task, self.lsave, self.isave, self.dsave, self.MAXLS, self.ln_task)
+            if self.task[0] == 3:
+                return True
+            if self.task[0] == 1:
+                self.nit += 1
+                if self.nit >= self.MAXITER:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > self.MAXFUN:
+                    self.task[0], self.task[1] = 5, 502
+            else:
+                return False
+
+    def supply(self, f, g):
+        self.f = float(f)
+        self.g = np.array(g, dtype=np.float64)
+        self.nfev += 1
+
+
+def _setulb_handle():
+    from scipy.optimize import _lbfgsb_py as mod
+    return mod._lbfgsb.setulb, (np.int64 if mod.HAS_ILP64 else np.int32)
+
+
+def _minimise_reverse_communication(evaluate, starts, verbose=False):
+    setulb, int_dtype = _setulb_handle()
+    runs = [_Descent(setulb, int_dtype, np.asarray(s[1], dtype=np.float64).ravel(), 0.1, 1e-20) for s in starts]
+    tidx = [int(s[0]) for s in starts]
+    last_good = [np.array(s[1], dtype=np.float64) for s in starts]
+    failed = [False] * len(runs)
+    pending = [k for k, r in enumerate(runs) if r.advance()]
+    rounds = evaluations = 0
+    while pending:
+        ll, grad, status = evaluate(np.stack([runs[k].x for k in pending]),
+                                    np.array([tidx[k] for k in pending], dtype=np.int32))
+        rounds += 1
+        evaluations += len(pending)
+        nxt = []
+        for n, k in enumerate(pending):
+            if status[n] != 0:                       # the reference's LinAlgError: (last theta that evaluated, 9999)
+                failed[k] = True
+                continue
+            last_good[k] = runs[k].x.copy()
+            runs[k].supply(ll[n], grad[n])
+            if runs[k].advance():
+                nxt.append(k)
+        pending = nxt
+    results = []
+    for k, r in enumerate(runs):
+        results.append((last_good[k], 9999) if failed[k] else (r.x, float(r.f)))
+        if verbose:
+            print("L-BFGS-B %d: cost %e after %d evaluations" % (k, results[-1][1], r.nfev))
+    return results, {"rounds": rounds, "evaluations": evaluations, "driver": "reverse-communication"}
+
+
+def _reverse_communication_ok():
+    """True if driving scipy's private ``setulb`` reproduces the public ``fmin_l_bfgs_b`` exactly (checked once)."""
+    if _RC_STATE["checked"]:
+        return _RC_STATE["ok"]
+    _RC_STATE["checked"] = True
+    try:
+        from scipy.optimize import fmin_l_bfgs_b
+        scale = np.array([1.0, 7.0, 0.3, 40.0])
+
+        def fg(x):
+            return float(0.5 * np.sum(scale * x * x) + np.sum(np.cos(x)) + 0.1 * (x[0] - x[1] ** 2) ** 2), \
+                scale * x - np.sin(x) + 0.2 * (x[0] - x[1] ** 2) * np.array([1.0, -2.0 * x[1], 0.0, 0.0])
+
+        def evaluate(thetas, tidx):
+            vals = [fg(t) for t in thetas]
+            return (np.array([v[0] for v in vals]), np.array([v[1] for v in vals]), np.zeros(len(vals), dtype=np.int32))
+        x0s = [np.array([1.5, -0.7, 2.0, 0.1]), np.array([-2.0, 2.2, 0.4, -1.0])]
+        mine, _ = _minimise_reverse_communication(evaluate, [(0, x) for x in x0s])
+        ok = True
+        for x0, got in zip(x0s, mine):
+            ref = fmin_l_bfgs_b(fg, x0, factr=0.1, pgtol=1e-20)
+            ok = ok and np.array_equal(ref[0], got[0]) and ref[1] == got[1]
+        _RC_STATE["ok"] = bool(ok)
+    except Exception:
+        _RC_STATE["ok"] = False
+    return _RC_STATE["ok"]
+
+
+def minimise_batched(evaluate, starts, verbose=False, driver=None):
+    """Run one L-BFGS-B descent per ``(target_index, theta0)`` in ``starts``, evaluations batched across descents.
+
+    ``driver``: ``"reverse-communication"`` (one thread drives scipy's ``setulb`` for every descent), ``"threads"`` (one
+    ``fmin_l_bfgs_b`` per thread, public API only) or None: reverse communication when the installed scipy passes the
+    self-test, threads otherwise.  Both give every descent exactly the iterates scipy would compute from the values
+    ``evaluate`` returns.  See ``_minimise_threads`` for the return value.
+    """
+    if driver is None:
+        driver = "reverse-communication" if _reverse_communication_ok() else "threads"
+    if driver == "reverse-communication":
+        return _minimise_reverse_communication(evaluate, starts, verbose)
+    if driver != "threads":
+        raise ValueError("driver must be 'reverse-communication', 'threads' or None")
+    return _minimise_threads(evaluate, starts, verbose)
+
+
+def _minimise_threads(evaluate, starts, verbose=False):
     """Run one L-BFGS-B descent per ``(target_index, theta0)`` in ``starts``, evaluations batched across descents.
 
     ``evaluate(thetas (B, G), target_index (B,)) -> (loglik, grad, status)``, e.g. ``DeviceTrainer.evaluate``.
@@ -162,4 +300,4 @@ def minimise_batched(evaluate, starts, verbose=False):
         t.join()
     if errors:
         raise errors[0]
-    return results, {"rounds": rv.rounds, "evaluations": rv.evaluations}
+    return results, {"rounds": rv.rounds, "evaluations": rv.evaluations, "driver": "threads"}

@@ -60,11 +60,18 @@ def test_lockstep_descents_equal_sequential_descents():
     """The batching driver changes WHEN evaluations happen, not what each descent sees: with the same evaluator every
     descent must end exactly where the sequential reference loop (GaussianProcess._learn) ends."""
     inputs, targets, thetas, tidx = orc.make_training_problem(M=24, D=2, T=2, B=5, seed=3)
-    fits, stats = minimise_batched(_host_evaluate(inputs, targets), [(int(tidx[n]), thetas[n]) for n in range(5)])
-    assert stats["evaluations"] >= 5 and stats["rounds"] <= stats["evaluations"]
-    for n in range(5):
-        ref = GaussianProcess(inputs, targets[tidx[n]])._learn(thetas[n], False)
-        assert np.array_equal(fits[n][0], ref[0]) and fits[n][1] == ref[1]
+    from gp_emulator_b200 import training
+    assert training._reverse_communication_ok(), "the installed scipy should pass the reverse-communication self-test"
+    refs = [GaussianProcess(inputs, targets[tidx[n]])._learn(thetas[n], False) for n in range(5)]
+    for driver in (None, "reverse-communication", "threads"):
+        fits, stats = minimise_batched(_host_evaluate(inputs, targets), [(int(tidx[n]), thetas[n]) for n in range(5)],
+                                       driver=driver)
+        assert stats["evaluations"] >= 5 and stats["rounds"] <= stats["evaluations"]
+        assert stats["driver"] == (driver or "reverse-communication")
+        for n in range(5):
+            assert np.array_equal(fits[n][0], refs[n][0]) and fits[n][1] == refs[n][1], (driver, n)
+    with pytest.raises(ValueError):
+        minimise_batched(_host_evaluate(inputs, targets), [(0, thetas[0])], driver="nonsense")
 
 
 def test_lockstep_driver_failure_conventions():
@@ -75,23 +82,26 @@ def test_lockstep_driver_failure_conventions():
         ll, g, st = host(th, np.zeros_like(ti))
         st[np.asarray(ti) == 1] = 1
         return ll, g, st
-    fits, _ = minimise_batched(one_bad, [(0, thetas[0]), (1, thetas[1]), (0, thetas[2])])
-    assert fits[1][1] == 9999 and np.array_equal(fits[1][0], thetas[1])      # reference GaussianProcess.py:174-179
-    for n in (0, 2):                        # the other descents are not disturbed by the drop-out
-        ref = GaussianProcess(inputs, targets[0])._learn(thetas[n], False)
-        assert np.array_equal(fits[n][0], ref[0]) and fits[n][1] == ref[1]
+    for driver in ("reverse-communication", "threads"):
+        fits, _ = minimise_batched(one_bad, [(0, thetas[0]), (1, thetas[1]), (0, thetas[2])], driver=driver)
+        assert fits[1][1] == 9999 and np.array_equal(fits[1][0], thetas[1])      # reference GaussianProcess.py:174-179
+        for n in (0, 2):                        # the other descents are not disturbed by the drop-out
+            ref = GaussianProcess(inputs, targets[0])._learn(thetas[n], False)
+            assert np.array_equal(fits[n][0], ref[0]) and fits[n][1] == ref[1]
 
     def broken(th, ti):
         raise RuntimeError("device lost")
-    with pytest.raises(RuntimeError):
-        minimise_batched(broken, [(0, thetas[0]), (0, thetas[1])])
+    for driver in ("reverse-communication", "threads"):
+        with pytest.raises(RuntimeError):
+            minimise_batched(broken, [(0, thetas[0]), (0, thetas[1])], driver=driver)
 
     def not_pd(th, ti):
         ll, g, st = host(th, ti)
         st[:] = 1
         return ll, g, st
-    fits, _ = minimise_batched(not_pd, [(0, thetas[0])])
-    assert fits[0][1] == 9999 and np.array_equal(fits[0][0], thetas[0])     # reference GaussianProcess.py:174-179
+    for driver in ("reverse-communication", "threads"):
+        fits, _ = minimise_batched(not_pd, [(0, thetas[0])], driver=driver)
+        assert fits[0][1] == 9999 and np.array_equal(fits[0][0], thetas[0])     # reference GaussianProcess.py:174-179
 
 
 def test_trainer_argument_validation_and_no_fallback(lib):
