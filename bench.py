@@ -322,6 +322,21 @@ def main():
                     "~3e-6, meets the reference FP32 bar 1e-5; 1x: ~6e-5)",
         }
         del sym, t32, tv, hout
+        # the caller on the input side of the path: cost + gradient of the hyper-parameter fit, one
+        # (theta, target) problem per SM, timed through the C ABI with host buffers (wall clock, synchronous call)
+        from gp_emulator_b200.training import DeviceTrainer
+        rs_t = np.random.RandomState(1)
+        nprob = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        trainer = DeviceTrainer(model["inputs"], np.sin(model["inputs"].sum(axis=1)), device=local_rank)
+        thetas = 5.0 * (rs_t.random_sample((nprob, D + 2)) - 0.5)
+        trainer.evaluate(thetas)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            trainer.evaluate(thetas)
+        variants["training_objective_evaluations_per_s"] = 5 * nprob / (time.perf_counter() - t0)
+        variants["training_note"] = ("loglikelihood + partial_devs (GaussianProcess.py:78-125) for %d thetas per launch, "
+                                     "M=%d D=%d: block Gauss-Jordan on DMMA, k_train_eval" % (nprob, M, D))
+        trainer.close()
     if rank == 0:
         from oracle import gp_oracle as orc
         mu_o, var_o, _ = orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], t_head)

@@ -25,7 +25,7 @@ TRAIN_MAX_M = 1024
 SYMBOLS = (
     "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
     "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_destroy", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
-    "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
+    "gpe_bank_cost", "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
     "gpe_trainer_create", "gpe_trainer_eval", "gpe_trainer_destroy",
 )
 
@@ -79,6 +79,8 @@ def load():
     lib.gpe_bank_destroy.argtypes = [C.c_void_p]
     lib.gpe_bank_predict.restype = C.c_int
     lib.gpe_bank_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint, C.c_void_p]
+    lib.gpe_bank_cost.restype = C.c_int
+    lib.gpe_bank_cost.argtypes = [C.c_void_p, dp, C.c_int64, dp, C.c_int64, dp, dp, dp, C.c_void_p]
     lib.gpe_bank_project.restype = C.c_int
     lib.gpe_bank_project.argtypes = [C.c_void_p, dp, dp, C.c_int64, dp, dp, C.c_void_p]
     lib.gpe_bank_forward.restype = C.c_int

@@ -143,6 +143,11 @@ struct gpe_bank {
     cudaStream_t fwd_st = nullptr;
     double *fwd_h = nullptr, *fwd_d = nullptr;
     size_t fwd_h_cap = 0, fwd_d_cap = 0;
+    // gpe_bank_cost: per-chunk mu / deriv scratch, shared by every stream that reduces with this bank
+    std::mutex cost_mu;
+    double* cost_d = nullptr;
+    size_t cost_cap = 0;
+    cudaEvent_t cost_free = nullptr;
 };
 
 namespace {
@@ -1334,6 +1339,8 @@ int gpe_bank_destroy(gpe_bank* b) {
     if (b->fwd_h) cudaFreeHost(b->fwd_h);
     if (b->fwd_d) { cudaSetDevice(b->device); cudaFree(b->fwd_d); }
     if (b->fwd_st) cudaStreamDestroy(b->fwd_st);
+    if (b->cost_d) { cudaSetDevice(b->device); cudaFree(b->cost_d); }
+    if (b->cost_free) cudaEventDestroy(b->cost_free);
     delete b;
     return GPE_OK;
 }
@@ -1398,6 +1405,84 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
         const size_t smem = do_hess ? m0->mean.smem_hess : m0->mean.smem;
         CUDA_TRY(launch_mean(m0->DP, do_hess, p, dim3(gx, (unsigned)E), smem, (cudaStream_t)stream));
     }
+    return GPE_OK;
+}
+
+// Least-squares reduction over the emulators of a bank (outputs consumed on the fly).  One warp per
+// point: lanes stride over the emulators for the residuals, then lane d accumulates column d of the gradient.
+__global__ void __launch_bounds__(128) k_bank_cost(const double* __restrict__ mu, const double* __restrict__ deriv,
+                                                   const double* __restrict__ obs, int64_t obs_ld,
+                                                   const double* __restrict__ weights, double* __restrict__ cost,
+                                                   double* __restrict__ grad, int64_t n, int E, int D) {
+    extern __shared__ double wr_s[];                     // [4 warps][E] weighted residuals
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* wr = wr_s + (size_t)w * E;
+    for (int64_t pt = (int64_t)blockIdx.x * 4 + w; pt < n; pt += (int64_t)gridDim.x * 4) {
+        double c = 0.0;
+        for (int e = lane; e < E; e += 32) {
+            const double r = mu[pt * E + e] - obs[pt * obs_ld + e];
+            const double we = weights ? weights[e] : 1.0;
+            wr[e] = we * r;
+            c = fma(we * r, r, c);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && cost) cost[pt] = 0.5 * c;
+        __syncwarp();
+        if (grad != nullptr && lane < D) {
+            const double* dp = deriv + pt * E * D + lane;
+            double g = 0.0;
+            for (int e = 0; e < E; ++e) g = fma(wr[e], dp[(size_t)e * D], g);
+            grad[pt * D + lane] = g;
+        }
+        __syncwarp();
+    }
+}
+
+int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
+                  double* cost, double* grad, void* stream) {
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing || !obs) return fail(GPE_ERR_INVALID, "testing / obs is NULL");
+    if (!cost && !grad) return fail(GPE_ERR_INVALID, "no output requested");
+    if (obs_ld != 0 && obs_ld < b->E) return fail(GPE_ERR_INVALID, "obs_ld must be 0 (one observation vector) or >= E");
+    CUDA_TRY(cudaSetDevice(b->device));
+    const int64_t E = b->E, D = b->D;
+    const int64_t per_point = E * (1 + (grad ? D : 0));
+    // points per chunk: whole waves of 64-point tiles, scratch bounded by 256 MB
+    int64_t chunk = std::max<int64_t>(64, (((int64_t)256 << 20) / (per_point * 8)) / 64 * 64);
+    chunk = std::min(chunk, (N + 63) / 64 * 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lock(b->cost_mu);
+    if (!b->cost_free) CUDA_TRY(cudaEventCreateWithFlags(&b->cost_free, cudaEventDisableTiming));
+    // the scratch may still be read by a reduction enqueued on another stream
+    CUDA_TRY(cudaStreamWaitEvent(st, b->cost_free, 0));
+    if (b->cost_cap < (size_t)(chunk * per_point)) {
+        if (b->cost_d) {
+            CUDA_TRY(cudaEventSynchronize(b->cost_free));
+            CUDA_TRY(cudaFree(b->cost_d));
+            b->cost_d = nullptr; b->cost_cap = 0;
+        }
+        CUDA_TRY(cudaMalloc((void**)&b->cost_d, (size_t)(chunk * per_point) * 8));
+        b->cost_cap = (size_t)(chunk * per_point);
+    }
+    double* d_mu = b->cost_d;
+    double* d_der = grad ? b->cost_d + chunk * E : nullptr;
+    int sms = b->models[0]->sms;
+    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+        const int64_t n = std::min(chunk, N - n0);
+        int rc = gpe_bank_predict(b, testing + n0 * D, n, d_mu, nullptr, d_der, nullptr,
+                                  GPE_WANT_MU | (grad ? GPE_WANT_DERIV : 0u), stream);
+        if (rc) return rc;
+        const int grid = (int)std::min<int64_t>((n + 3) / 4, (int64_t)sms * 16);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        k_bank_cost<<<grid, 128, (size_t)4 * E * 8, st>>>(d_mu, d_der, obs + n0 * obs_ld, obs_ld, weights,
+                                                          cost ? cost + n0 : nullptr, grad ? grad + n0 * D : nullptr, n,
+                                                          (int)E, (int)D);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(b->cost_free, st));
     return GPE_OK;
 }
 

@@ -316,6 +316,48 @@ class DeviceBank:
             raise ValueError(f"testing must be float64 (N, {D})")
         return self._predict_device(t, want_var, want_deriv, want_hess, project, project_deriv)
 
+    def cost(self, testing, obs, weights=None, want_grad=True):
+        """Least-squares misfit of the bank's means against observations, reduced over the emulators on the device:
+        ``cost (N,) = 1/2 sum_e w_e (mu_ne - obs_ne)^2`` and ``grad (N, D) = sum_e w_e (mu_ne - obs_ne) deriv_ned``
+        (``gpe_bank_cost``).  ``obs`` is (E,) -- one observation for every point -- or (N, E); ``weights`` (E,) or None.
+        numpy in -> numpy out; torch CUDA in -> torch CUDA out (asynchronous on the current stream)."""
+        import torch
+        D, E = self.D, self.E
+        as_numpy = not _is_torch(testing)
+        dev = torch.device("cuda", self.device)
+        if as_numpy:
+            th = f64c(testing)
+            if th.ndim != 2 or th.shape[1] != D:
+                raise ValueError(f"testing must be float64 (N, {D})")
+            t = torch.from_numpy(th).to(dev)
+        else:
+            t = testing.contiguous()
+            if t.dim() != 2 or t.shape[1] != D or t.dtype != torch.float64:
+                raise ValueError(f"testing must be float64 (N, {D})")
+        N = t.shape[0]
+        o = torch.as_tensor(np.asarray(obs, dtype=np.float64) if not _is_torch(obs) else obs, dtype=torch.float64,
+                            device=dev).contiguous()
+        if tuple(o.shape) == (E,):
+            obs_ld = 0
+        elif tuple(o.shape) == (N, E):
+            obs_ld = E
+        else:
+            raise ValueError(f"obs must be ({E},) or ({N}, {E})")
+        wt = None
+        if weights is not None:
+            wt = torch.as_tensor(np.asarray(weights, dtype=np.float64) if not _is_torch(weights) else weights,
+                                 dtype=torch.float64, device=dev).contiguous()
+            if tuple(wt.shape) != (E,):
+                raise ValueError(f"weights must be ({E},)")
+        out = {"cost": torch.empty(N, dtype=torch.float64, device=dev)}
+        if want_grad:
+            out["grad"] = torch.empty(N, D, dtype=torch.float64, device=dev)
+        check(_lib.load().gpe_bank_cost(self._h, addr(t), N, addr(o), obs_ld, addr(wt), addr(out["cost"]),
+                                        addr(out.get("grad")), _current_stream_ptr(self.device)))
+        if as_numpy:
+            return {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
     host_chunk_bytes = 1 << 30   # device bytes of results per chunk when the caller passes numpy arrays
 
     def forward(self, testing, want_deriv=True):

@@ -139,6 +139,17 @@ int gpe_bank_destroy(gpe_bank* b);
 int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var,
                      double* deriv, double* hess, unsigned flags, void* stream);
 
+/* Least-squares cost of the bank's means against observations and its input gradient, reduced over the E emulators
+ * on the fly so the (N, E) means and (N, E, D) gradients never leave the device (they exist for one chunk at a time):
+ *   cost_n = 1/2 sum_e w_e (mu_ne - obs_ne)^2        grad_nd = sum_e w_e (mu_ne - obs_ne) deriv_ned
+ * What a caller of a per-band bank builds in numpy from E separate predicts (the loop of
+ * gp_emulator/tests/test_perband_emulator.py:39-47 followed by the comparison with the observed bands); the reference
+ * has no such function -- it is the "outputs consumed on the fly" item of SURVEY.md 8f-3.
+ *   obs (N, E) with obs_ld >= E, or one (E) vector shared by every point with obs_ld = 0; weights (E) or NULL (all 1);
+ *   cost (N) or NULL; grad (N, D) or NULL.  Device pointers, asynchronous on `stream`. */
+int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
+                  const double* weights, double* cost, double* grad, void* stream);
+
 /* PCA back-projection of bank means: fwd (N, W) = mu (N, E) @ basis (E, W)
  * (the accumulation `fwd += pred_mu * basis_functions[i]`, gp_emulator/multivariate_gp.py:216, batched
  * over N points), and optionally deriv_full (N, D, W) = sum_e deriv[n, e, d] * basis[e, w] (:218).

@@ -21,7 +21,7 @@ import scipy.spatial.distance as _dist
 
 __all__ = [
     "cross_covariance", "predict", "hessian", "prepare_likelihood", "loglikelihood_and_grad", "predict_longdouble",
-    "mv_compress", "mv_predict_point", "mv_predict_batch", "bank_predict",
+    "mv_compress", "mv_predict_point", "mv_predict_batch", "bank_predict", "bank_cost",
     "ref_err", "var_cond_err", "make_S_model", "make_T_model", "make_training_problem",
 ]
 
@@ -231,6 +231,17 @@ def bank_predict(models, testing, do_hess=False):
         if do_hess:
             hess[:, i] = hessian(inputs, theta, invQt, testing)
     return (mu, var, deriv, hess) if do_hess else (mu, var, deriv)
+
+
+def bank_cost(models, testing, obs, weights=None):
+    """Least-squares misfit of E per-band GPs against observed bands, and its gradient w.r.t. the inputs, built the way a
+    caller of the reference builds it: one ``predict`` per emulator (tests/test_perband_emulator.py:39-47), then
+    cost_n = 1/2 sum_e w_e (mu_ne - obs_ne)^2 and grad_nd = sum_e w_e (mu_ne - obs_ne) deriv_ned.  (Not a reference
+    function: the checker for ``gpe_bank_cost``)"""
+    mu, _, deriv = bank_predict(models, testing)
+    r = mu - np.asarray(obs)
+    w = np.ones(mu.shape[1]) if weights is None else np.asarray(weights)
+    return 0.5 * np.sum(w * r * r, axis=1), np.einsum("ne,ned->nd", w * r, deriv)
 
 
 def mv_predict_batch(models, basis_functions, testing, want_deriv_full=False):

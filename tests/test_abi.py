@@ -71,6 +71,7 @@ def test_argument_validation(lib):
     assert lib.gpe_model_create(0, 4, 33, x.ctypes.data, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
     assert lib.gpe_model_create(0, 4, 2, None, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
     assert lib.gpe_predict(None, None, 1, None, None, None, None, 1, None) == -1
+    assert lib.gpe_bank_cost(None, None, 1, None, 0, None, None, None, None) == -1
     assert lib.gpe_predict_wrap(e.ctypes.data, x.ctypes.data, a.ctypes.data, x.ctypes.data, x.ctypes.data,
                                 a.ctypes.data, a.ctypes.data, a.ctypes.data, 1, 4, 2, 2) == -1  # theta_size < D+1
 

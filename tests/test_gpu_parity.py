@@ -178,6 +178,37 @@ def test_bank_host_batches_are_chunked(gpemu):
     assert np.array_equal(fwd, ref["fwd"])
 
 
+@pytest.mark.parametrize("M,D,E,N", [(60, 4, 5, 1037), (250, 10, 64, 3000), (33, 1, 1, 7), (40, 32, 3, 129)])
+def test_bank_cost_reduction_on_the_fly(gpemu, M, D, E, N):
+    """gpe_bank_cost: misfit against observations and its gradient, reduced over the emulators on the device, equals
+    the E separate predicts + numpy reduction a caller of the reference would write (oracle bank_cost)."""
+    import torch
+    rs = np.random.RandomState(M + E)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+    t = rs.random_sample((N, D))
+    models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
+    mu_o = orc.bank_predict(models, t)[0]
+    obs1 = mu_o.mean(axis=0) * 1.1                         # one observed vector for every point
+    obsN = mu_o * (1.0 + 0.2 * rs.standard_normal(mu_o.shape))
+    w = rs.random_sample(E) + 0.5
+    for obs, wt in ((obs1, None), (obsN, w), (obs1, w)):
+        c_o, g_o = orc.bank_cost(models, t, obs, wt)
+        got = bank.cost(t, obs, wt)
+        assert got["cost"].shape == (N,) and got["grad"].shape == (N, D)
+        assert orc.ref_err(got["cost"], c_o) < TOL and orc.ref_err(got["grad"], g_o) < TOL
+    only = bank.cost(t, obs1, want_grad=False)
+    assert set(only) == {"cost"} and orc.ref_err(only["cost"], orc.bank_cost(models, t, obs1)[0]) < TOL
+    td = torch.from_numpy(t).cuda()
+    dev = bank.cost(td, torch.from_numpy(obsN).cuda(), torch.from_numpy(w).cuda())       # device in, device out
+    c_o, g_o = orc.bank_cost(models, t, obsN, w)
+    assert dev["cost"].is_cuda and orc.ref_err(dev["cost"].cpu().numpy(), c_o) < TOL
+    assert orc.ref_err(dev["grad"].cpu().numpy(), g_o) < TOL
+    with pytest.raises(ValueError):
+        bank.cost(t, np.zeros(E + 1))
+
+
 def test_small_batch_plan_threshold(gpemu):
     """Calls of up to 3 * 16 * #SM points run 16-point tiles (lower latency), larger ones 64-point tiles; both sides of
     the switch meet the oracle, and a host call uses one plan for all of its chunks."""
