@@ -139,6 +139,29 @@ float time_ms(F launch, int reps) {
 // out[0]=DFMA TFLOP/s, out[1]=DMMA TFLOP/s, out[2]=mixed total TFLOP/s, out[3]=mixed DFMA part,
 // out[4]=mixed DMMA part, out[5]=gpe exp Gexp/s, out[6]=CUDA exp Gexp/s, out[7]=SM MHz under FP64 load,
 // out[8]=#SMs.  Returns 0 on success, a cudaError_t otherwise.
+// Developer aid (not in the public header): y[i] = exp_neg(x[i]) on the device, host pointers.
+// tests/test_gpu_parity.py::test_device_exp_accuracy holds it against mpmath.
+__global__ void k_exp_eval(const double* x, double* y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = gpe::exp_neg(x[i]);
+}
+
+extern "C" int gpe_debug_exp(const double* x, double* y, long long n) {
+    if (n <= 0) return 0;
+    double *dx = nullptr, *dy = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dx, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dy, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_exp_eval<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost);
+    if (dx) cudaFree(dx);
+    if (dy) cudaFree(dy);
+    return e == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int gpe_measure_fp64_peaks(int device, double* out9) {
     cudaError_t err = cudaSetDevice(device);
     if (err != cudaSuccess) return (int)err;

@@ -209,6 +209,28 @@ def test_bank_cost_reduction_on_the_fly(gpemu, M, D, E, N):
         bank.cost(t, np.zeros(E + 1))
 
 
+def test_device_exp_accuracy(lib, gpemu):
+    """The FP64 exp behind K* (gpe_math.cuh::exp_neg) against mpmath: <= 1 ulp on [-708, 0], exactly 1 at 0, flush to 0
+    below the normal range."""
+    import mpmath as mp
+    mp.mp.prec = 120
+    rs = np.random.RandomState(3)
+    x = np.concatenate([-rs.uniform(0, 708, 30000), -rs.uniform(0, 40, 30000), -10.0 ** rs.uniform(-300, 0, 2000),
+                        np.array([0.0, -0.0, -708.0, -707.999, -1e-320, -np.log(2) / 2, -np.log(2), -745.0, -1e4])])
+    y = np.empty_like(x)
+    lib.gpe_debug_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+    assert lib.gpe_debug_exp(x.ctypes.data, y.ctypes.data, x.size) == 0
+    worst = 0.0
+    for v, got in zip(x, y):
+        if v < -708.0:
+            assert got == 0.0
+            continue
+        r = mp.exp(mp.mpf(float(v)))
+        worst = max(worst, float(abs(mp.mpf(float(got)) - r) / np.spacing(float(r))))
+    assert y[np.where(x == 0.0)[0][0]] == 1.0
+    assert worst <= 1.0, worst
+
+
 def test_small_batch_plan_threshold(gpemu):
     """Calls of up to 3 * 16 * #SM points run 16-point tiles (lower latency), larger ones 64-point tiles; both sides of
     the switch meet the oracle, and a host call uses one plan for all of its chunks."""
