@@ -283,8 +283,17 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     }
     if (tid == 0) {
         p.grad[(size_t)nb * G + D + 1] = 0.5 * noise * (s_tr - s_aa);
-        p.loglik[nb] = 0.5 * logdet + 0.5 * s_ta + 0.5 * (double)M * 1.8378770664093453;  // log(2 pi)
-        p.status[nb] = 0;
+        const double ll = 0.5 * logdet + 0.5 * s_ta + 0.5 * (double)M * 1.8378770664093453;  // log(2 pi)
+        p.loglik[nb] = ll;
+        // positive pivots but an overflowed / NaN result (e.g. a numerically singular Q): report it like a failed
+        // factorisation rather than handing non-finite numbers to the optimiser
+        bool finite = isfinite(ll);
+        for (int d = 0; d < G; ++d) finite = finite && isfinite(p.grad[(size_t)nb * G + d]);
+        p.status[nb] = finite ? 0 : 1;
+        if (!finite) {
+            p.loglik[nb] = nan("");
+            for (int d = 0; d < G; ++d) p.grad[(size_t)nb * G + d] = nan("");
+        }
     }
 }
 

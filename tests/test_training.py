@@ -200,6 +200,10 @@ def test_trainer_flags_non_positive_definite_covariance():
     ll, grad, st = tr.evaluate(thetas)
     tr.close()
     assert list(st) == [0, 1, 0] and np.isnan(ll[1]) and np.isnan(grad[1]).all()
+    huge = thetas.copy()
+    huge[2, 0] = 800.0                                    # exp(800) overflows: non-finite results are failures too
+    ll_h, grad_h, st_h = DeviceTrainer(inputs, targets).evaluate(huge)
+    assert st_h[2] == 1 and np.isnan(ll_h[2]) and np.isnan(grad_h[2]).all() and st_h[0] == 0
     with pytest.raises(np.linalg.LinAlgError):
         orc.loglikelihood_and_grad(inputs, targets[0], thetas[1])
     for n in (0, 2):
