@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
 // reduce-scatter.  32 points per 128-thread CTA.
 // KSTAR: also store K* (without alpha) into the scratch consumed by k_var_large (M > 1024 variance path).
 template <int DP, bool KSTAR>
-__global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams p) {
+__global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_mean2(const MeanParams p) {
     constexpr int TN = kMeanTN;
     constexpr int NV = DP + 1;
     extern __shared__ __align__(128) unsigned char smem_m2[];
@@ -226,14 +226,32 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams
     bool x_resident = false;
     const int chunk_doubles = p.JC * (DP + 1);
 
+    // The test rows of the NEXT tile are fetched into registers while the current tile computes (the global-load
+    // latency at every tile start showed up as 0.4 long-scoreboard + 0.2 barrier stall cycles per issue in ncu).
+    constexpr int PF = (TN * DP + kMeanThreads - 1) / kMeanThreads;
+    double pf[PF];
+    auto fetch_rows = [&](int64_t t) {
+        const int64_t m0 = t * TN;
+        const int mpts = (int)min((int64_t)TN, p.N - m0);
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            const int e = tid + q * kMeanThreads;
+            if (e < TN * D) {
+                const int r = e / D;
+                const int64_t src = (r < mpts) ? (m0 * D + e) : ((p.N - 1) * D + (e - r * D));
+                pf[q] = __ldg(p.testing + src);
+            }
+        }
+    };
+    if ((int64_t)blockIdx.x < ntiles) fetch_rows(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = tile * TN;
         const int npts = (int)min((int64_t)TN, p.N - n0);
         __syncthreads();
-        for (int e = tid; e < TN * D; e += kMeanThreads) {
-            const int r = e / D;
-            const int64_t src = (r < npts) ? (n0 * D + e) : ((p.N - 1) * D + (e - r * D));
-            ts_s[e] = __ldg(p.testing + src);
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            const int e = tid + q * kMeanThreads;
+            if (e < TN * D) ts_s[e] = pf[q];
         }
         __syncthreads();
         double tsa[DP], tsb[DP];
@@ -242,6 +260,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean2(const MeanParams
             tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
             tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
         }
+        if (tile + gridDim.x < ntiles) fetch_rows(tile + gridDim.x);
         double va[NV], vb[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) va[i] = vb[i] = 0.0;
