@@ -203,7 +203,8 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     const int m32 = (M + 31) / 32 * 32, m64 = (M + 63) / 64 * 64;
     int force = -1;
     if (const char* e = getenv("GPE_FULL_CFG")) force = atoi(e);
-    uint32_t smem_cap = kSmemMax;
+    // the kernels also hold static shared memory (exp table 512 B; HESS variants a 1 KB index table + 256 B): leave room
+    uint32_t smem_cap = kSmemMax - 2048;
     if (small_Mp > 0) {
         f.cfg = 2; f.TN = 16; f.WC = 8; f.GH = 4; f.Mp = small_Mp; f.nt_act = small_Mp / 64;
     } else if (m32 <= 256) {

@@ -139,21 +139,25 @@ float time_ms(F launch, int reps) {
 // out[0]=DFMA TFLOP/s, out[1]=DMMA TFLOP/s, out[2]=mixed total TFLOP/s, out[3]=mixed DFMA part,
 // out[4]=mixed DMMA part, out[5]=gpe exp Gexp/s, out[6]=CUDA exp Gexp/s, out[7]=SM MHz under FP64 load,
 // out[8]=#SMs.  Returns 0 on success, a cudaError_t otherwise.
-// Developer aid (not in the public header): y[i] = exp_neg(x[i]) on the device, host pointers.
-// tests/test_gpu_parity.py::test_device_exp_accuracy holds it against mpmath.
-__global__ void k_exp_eval(const double* x, double* y, long long n) {
+// Developer aid (not in the public header): y[i] = exp(x[i]) on the device with the kernels' own routines, host
+// pointers; which = 0: exp_neg_tab (table-driven, what the FP64 predict kernels use), 1: exp_neg (polynomial only, used
+// by the training kernel).  tests/test_gpu_parity.py::test_device_exp_accuracy holds both against mpmath.
+__global__ void k_exp_eval(const double* x, double* y, long long n, int which) {
+    __shared__ double tab[64];
+    gpe::exp_tab_load(tab, threadIdx.x);
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = gpe::exp_neg(x[i]);
+    if (i < n) y[i] = which ? gpe::exp_neg(x[i]) : gpe::exp_neg_tab(x[i], tab);
 }
 
-extern "C" int gpe_debug_exp(const double* x, double* y, long long n) {
+extern "C" int gpe_debug_exp(const double* x, double* y, long long n, int which) {
     if (n <= 0) return 0;
     double *dx = nullptr, *dy = nullptr;
     cudaError_t e = cudaMalloc((void**)&dx, n * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&dy, n * 8);
     if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        k_exp_eval<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n);
+        k_exp_eval<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n, which);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost);

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     double* hts = reinterpret_cast<double*>(smem + p.off_hts);   // HESS: [TN][D] centred scaled test rows
     __shared__ int htab[HESS ? 256 : 1];                         // HESS: (d, e) -> d | e << 8 | column << 16
     __shared__ double cen_s[HESS ? kMaxD : 1];
+    __shared__ double exp_tab[64];                               // 2^(j/64) for exp_neg_tab
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = p.D, M = p.M, Mp = p.Mp;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         fence_mbar_init();
     }
     if (tid < kMaxD) sqw_s[tid] = p.sqrt_w[tid];
+    exp_tab_load(exp_tab, tid);
     if (HESS) {
         if (tid < kMaxD) cen_s[tid] = p.centre[tid];
         for (int e = tid; e < p.D * p.D; e += NTHR) {
@@ -351,8 +353,8 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                         ra = fma(ua[d + 1], ua[d + 1], ra);
                         rb = fma(ub[d + 1], ub[d + 1], rb);
                     }
-                    const double ka = exp_neg(-0.5 * ra);
-                    const double kb = exp_neg(-0.5 * rb);
+                    const double ka = exp_neg_tab(-0.5 * ra, exp_tab);
+                    const double kb = exp_neg_tab(-0.5 * rb, exp_tab);
                     krow_a[jl] = ka;
                     krow_b[jl] = kb;
                     const double ca = ka * alj, cb = kb * alj;

@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     double* ts_s = reinterpret_cast<double*>(smem + p.off_ts);   // [TN][D]; reused as [TN][D+1] outs
     double* out_s = reinterpret_cast<double*>(smem + p.off_out); // HESS: [TN][D*D]
     __shared__ double sqw_s[32];
+    __shared__ double exp_tab[64];   // 2^(j/64) for exp_neg_tab; visible after the first CTA barrier
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M, DV = D + 1;
     const int em = blockIdx.y;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
                     r2 = fma(u[d], u[d], r2);
                     r2 = fma(u[d + 1], u[d + 1], r2);
                 }
-                return exp_neg(-0.5 * r2) * al[jl];
+                return exp_neg_tab(-0.5 * r2, exp_tab) * al[jl];
             };
             if (!HESS) {
                 // mean + gradient only: few registers -> many resident warps hide the chain; no pipelining needed
@@ -214,7 +216,9 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
     double* Xc = reinterpret_cast<double*>(smem_m2 + p.off_xc);
     double* ts_s = reinterpret_cast<double*>(smem_m2 + p.off_ts);   // [TN][D]; reused as [TN][D+1] outs
     __shared__ double sqw_s[32];
+    __shared__ double exp_tab[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    exp_tab_load(exp_tab, tid);   // visible after the barrier at the first tile start
     const int g_low = lane & 7, n_a = warp * 8 + (lane >> 3), n_b = n_a + 4;
     const int D = p.D, M = p.M, DV = D + 1;
     const int em = blockIdx.y;
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
                         ra = fma(ua[d + 1], ua[d + 1], ra);
                         rb = fma(ub[d + 1], ub[d + 1], rb);
                     }
-                    const double ka = exp_neg(-0.5 * ra), kb = exp_neg(-0.5 * rb);
+                    const double ka = exp_neg_tab(-0.5 * ra, exp_tab), kb = exp_neg_tab(-0.5 * rb, exp_tab);
                     if (KSTAR) {
                         const int jg = c * p.JC + jl;
                         const size_t col = ((size_t)(jg >> 2) * 16) * 4 + (jg & 3);
@@ -366,7 +370,9 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
     double* ts_s = reinterpret_cast<double*>(smem_h + p.off_ts);
     double* out_s = reinterpret_cast<double*>(smem_h + p.off_out);   // [TN][HR][D]
     __shared__ double sqw_s[32];
+    __shared__ double exp_tab[64];   // 2^(j/64) for exp_neg_tab; visible after the first CTA barrier
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M;
     const int em = blockIdx.y;
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
                         r2 = fma(u[d], u[d], r2);
                         r2 = fma(u[d + 1], u[d + 1], r2);
                     }
-                    const double cj = exp_neg(-0.5 * r2) * al[jl];
+                    const double cj = exp_neg_tab(-0.5 * r2, exp_tab) * al[jl];
                     mu += cj;
 #pragma unroll
                     for (int i = 0; i < HR; ++i) {
