@@ -14,19 +14,30 @@
 
 namespace gpe {
 
-template <int MT, int NT, int WR, int WC, int MINB, int KB>
+// EXACT: the caller guarantees p.nt_act == NT, so only the predicate-free (FULLNT) kernels are instantiated.  One
+// instantiation per number of active column tiles: in a wider instantiation the guard `if (j >= nt_act) break` inside the
+// unrolled DMMA loop keeps the B-fragment loads from being hoisted (measured: M = 200, nt_act = 7 of 8: 2.55e8 -> 3.0e8
+// points/s; M = 100: 7.1e8 -> 7.9e8).  !EXACT (developer configurations, the small-batch plan): both kernels.
+template <int MT, int NT, int WR, int WC, int MINB, int KB, bool EXACT>
 static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = p.symmetric ? ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, true, false>
-                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, true, false>)
-                            : ((p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, false>
-                                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, false>);
+    if (EXACT && p.nt_act != NT) return cudaErrorInvalidValue;
+    auto kern = p.symmetric ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, true, false>
+                            : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, false>;
+    if constexpr (!EXACT) {
+        if (p.nt_act != NT)
+            kern = p.symmetric ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, true, false>
+                               : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, false>;
+    }
 #if GPE_DP <= 16
     // fused Hessian variants (gpemu.cu only asks for them when cfg <= 2 and the model is not symmetric-folded)
     if (p.hess != nullptr) {
         if (p.symmetric || MINB != 1 || WR * WC != 8) return cudaErrorInvalidValue;
-        if constexpr (MINB == 1 && WR * WC == 8)
-            kern = (p.nt_act == NT) ? k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, true>
-                                    : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, true>;
+        if constexpr (MINB == 1 && WR * WC == 8) {
+            kern = k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, true, false, true>;
+            if constexpr (!EXACT) {
+                if (p.nt_act != NT) kern = k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, true>;
+            }
+        }
     }
 #else
     if (p.hess != nullptr) return cudaErrorInvalidValue;
@@ -40,11 +51,38 @@ static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaSt
 
 cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_cfg<4, 8, 2, 4, 1, 2>(p, grid, smem, st);   // TN = 64, Mp <= 256, 8 warps, 1 CTA/SM
-        case 1: return launch_cfg<4, 8, 1, 8, 1, 1>(p, grid, smem, st);   // TN = 32, Mp <= 512, 8 warps, 1 CTA/SM
-        case 2: return launch_cfg<2, 16, 1, 8, 1, 1>(p, grid, smem, st);  // TN = 16, Mp <= 1024, 8 warps, 1 CTA/SM
-        case 3: return launch_cfg<4, 8, 1, 4, 2, 1>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
-        case 4: return launch_cfg<4, 4, 2, 8, 1, 1>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
+        case 0:   // TN = 64, Mp = 32 nt_act <= 256, 8 warps as 2 x 4, 1 CTA/SM
+            switch (p.nt_act) {
+                case 1: return launch_cfg<4, 1, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 2: return launch_cfg<4, 2, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 3: return launch_cfg<4, 3, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 4: return launch_cfg<4, 4, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 5: return launch_cfg<4, 5, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 6: return launch_cfg<4, 6, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 7: return launch_cfg<4, 7, 2, 4, 1, 2, true>(p, grid, smem, st);
+                case 8: return launch_cfg<4, 8, 2, 4, 1, 2, true>(p, grid, smem, st);
+                default: return cudaErrorInvalidValue;
+            }
+        case 1:   // TN = 32, Mp = 64 nt_act <= 512, 8 warps as 1 x 8, 1 CTA/SM
+            switch (p.nt_act) {
+                case 5: return launch_cfg<4, 5, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 6: return launch_cfg<4, 6, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 7: return launch_cfg<4, 7, 1, 8, 1, 1, true>(p, grid, smem, st);
+                default: return launch_cfg<4, 8, 1, 8, 1, 1, false>(p, grid, smem, st);
+            }
+        case 2:   // TN = 16, Mp = 64 nt_act <= 1024, 8 warps as 1 x 8 (warp tile 16 x 128), 1 CTA/SM; also the small-batch plan
+            switch (p.nt_act) {
+                case 9: return launch_cfg<2, 9, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 10: return launch_cfg<2, 10, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 11: return launch_cfg<2, 11, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 12: return launch_cfg<2, 12, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 13: return launch_cfg<2, 13, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 14: return launch_cfg<2, 14, 1, 8, 1, 1, true>(p, grid, smem, st);
+                case 15: return launch_cfg<2, 15, 1, 8, 1, 1, true>(p, grid, smem, st);
+                default: return launch_cfg<2, 16, 1, 8, 1, 1, false>(p, grid, smem, st);
+            }
+        case 3: return launch_cfg<4, 8, 1, 4, 2, 1, false>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
+        case 4: return launch_cfg<4, 4, 2, 8, 1, 1, false>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
         default: return cudaErrorInvalidValue;
     }
 }
