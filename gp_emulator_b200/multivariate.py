@@ -73,7 +73,10 @@ class MultivariateEmulator(object):
     def calculate_decomposition(self, X, thresh):
         """PCA by SVD; keep the components whose cumulative singular-value share is <= thresh
         (reference multivariate_gp.py:140-160)."""
-        _, s, V = np.linalg.svd(X, full_matrices=True)
+        # (the reference asks LAPACK for the full (N_full, N_full) right factor and uses its first min(N_train, N_full)
+        # rows; the economy factorisation returns just those rows -- same singular values, vectors equal to the last
+        # bit or two -- and is 14x cheaper at 250 x 2101)
+        _, s, V = np.linalg.svd(X, full_matrices=False)
         keep = (s.cumsum() / s.sum()) <= thresh
         self.basis_functions = V[: keep.size][keep]
         self.n_pcs = int(np.sum(keep))
