@@ -53,6 +53,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr uint32_t kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int64_t kPipeChunk = 1 << 18;  // points per host-streaming chunk
+constexpr int64_t kZeroCopyMax = 256;    // host calls of up to this many points run on mapped page-locked buffers
 
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
@@ -697,7 +698,32 @@ int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* 
     };
     const int64_t nchunks = (N + CH - 1) / CH;
     int rc = GPE_OK;
-    if (nchunks == 1) {
+    static const bool no_zero_copy = getenv("GPE_NO_ZERO_COPY") != nullptr;   // dev aid: time the copy-based small path
+    if (N <= kZeroCopyMax && !in_direct && !out_direct && !no_zero_copy) {
+        // A handful of points (the reference is typically called with ONE): the two cudaMemcpyAsync of the staged
+        // path cost more than the kernel.  The staging buffers are page-locked, hence mapped into the device's address
+        // space (UVA): the kernels read the test rows from and write the results to host memory directly -- one launch
+        // and one synchronisation instead of copy, launch, copy, synchronise.
+        Slot& s = m->slots[0];
+        double t0 = now();
+        memcpy(s.h_in, testing, (size_t)N * D * ES);
+        t_in += now() - t0;
+        T* o = reinterpret_cast<T*>(s.h_out);
+        T* const z_mu = mu ? o : nullptr;    if (mu) o += N;
+        T* const z_var = var ? o : nullptr;  if (var) o += N;
+        T* const z_der = deriv ? o : nullptr; if (deriv) o += N * D;
+        T* const z_hes = hess ? o : nullptr;
+        rc = launch(reinterpret_cast<T*>(s.h_in), N, z_mu, z_var, z_der, z_hes, s.st);
+        if (rc) return rc;
+        t0 = now();
+        CUDA_TRY(cudaStreamSynchronize(s.st));
+        t_wait += now() - t0; t0 = now();
+        if (mu) memcpy(mu, z_mu, (size_t)N * ES);
+        if (var) memcpy(var, z_var, (size_t)N * ES);
+        if (deriv) memcpy(deriv, z_der, (size_t)N * D * ES);
+        if (hess) memcpy(hess, z_hes, (size_t)N * D * D * ES);
+        t_out += now() - t0;
+    } else if (nchunks == 1) {
         rc = stage_in(m->slots[0], 0, N);
         if (rc) return rc;
         CUDA_TRY(copy_out(m->slots[0]));
@@ -1541,6 +1567,19 @@ int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd,
         double* h_t = b->fwd_h;
         double* h_out = h_t + n * D;
         par_memcpy(h_t, testing + n0 * D, (size_t)n * D * 8);
+        static const bool no_zero_copy = getenv("GPE_NO_ZERO_COPY") != nullptr;
+        if (n <= kZeroCopyMax && (size_t)n * out_pp * 8 <= ((size_t)1 << 20) && !no_zero_copy) {
+            // a few points (the reference's call is one): the kernels read the test rows from and write the spectra to
+            // the page-locked staging buffer itself (mapped, UVA) -- no copy calls around the two launches
+            d_t = h_t;
+            d_out = h_out;
+            rc = gpe_bank_predict(b, d_t, n, d_mu, nullptr, deriv_full ? d_der : nullptr, nullptr,
+                                  GPE_WANT_MU | (deriv_full ? GPE_WANT_DERIV : 0u), b->fwd_st);
+            if (rc) return rc;
+            rc = gpe_bank_project(b, d_mu, deriv_full ? d_der : nullptr, n, d_out, deriv_full ? d_out + n * W : nullptr, b->fwd_st);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(b->fwd_st));
+        } else {
         CUDA_TRY(cudaMemcpyAsync(d_t, h_t, (size_t)n * D * 8, cudaMemcpyHostToDevice, b->fwd_st));
         rc = gpe_bank_predict(b, d_t, n, d_mu, nullptr, deriv_full ? d_der : nullptr, nullptr,
                               GPE_WANT_MU | (deriv_full ? GPE_WANT_DERIV : 0u), b->fwd_st);
@@ -1549,6 +1588,7 @@ int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd,
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)n * out_pp * 8, cudaMemcpyDeviceToHost, b->fwd_st));
         CUDA_TRY(cudaStreamSynchronize(b->fwd_st));
+        }
         par_memcpy(fwd + n0 * W, h_out, (size_t)n * W * 8);
         if (deriv_full) par_memcpy(deriv_full + n0 * D * W, h_out + n * W, (size_t)n * D * W * 8);
     }

@@ -232,6 +232,26 @@ def test_device_exp_accuracy(lib, gpemu):
         assert worst <= bound, (which, worst)
 
 
+def test_tiny_host_calls_run_on_mapped_buffers(gpemu):
+    """Host calls of a few points (the reference's usual call is ONE point) skip the copy engine: the kernels read and
+    write the library's page-locked staging buffers directly.  Same numbers as the DMA path that page-locked caller
+    arrays take, for every output, at the sizes around the switch (256 points)."""
+    import torch
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 6, 300, seed=31)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    for n in (1, 7, 256, 257):
+        t = testing[:n]
+        got = m.predict(t, want_hess=True, pinned=False)                    # pageable in / out: mapped buffers up to 256
+        tp = torch.from_numpy(t).pin_memory().numpy()
+        ref = m.predict(tp, want_hess=True, pinned=True)                    # page-locked in / out: direct DMA
+        for k in ("mu", "var", "deriv", "hess"):
+            assert np.array_equal(got[k], ref[k]), (n, k)
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, t)
+        _check(got, mu, var, deriv)
+    g32 = m.predict_f32(testing[:3].astype(np.float32))
+    assert orc.ref_err(g32["mu"], orc.predict(inputs, theta, invQ, invQt, testing[:3])[0]) < 1e-5
+
+
 def test_small_batch_plan_threshold(gpemu):
     """Calls of up to 3 * 16 * #SM points run 16-point tiles (lower latency), larger ones 64-point tiles; both sides of
     the switch meet the oracle, and a host call uses one plan for all of its chunks."""
