@@ -35,7 +35,7 @@ $(BUILD)/inst_dp%.o: $(CSRC)/predict_full_inst.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -DGPE_DP=$* -c $< -o $@ 2> $(BUILD)/inst_dp$*.ptxas.log || (cat $(BUILD)/inst_dp$*.ptxas.log; exit 1)
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
 build/fp64_peaks: $(CSRC)/peaks.cu $(HDRS)
 	mkdir -p build

@@ -1175,6 +1175,7 @@ int gpe_model_destroy(gpe_model* m) {
 
 int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
                 unsigned flags, void* stream) {
+    NvtxRange nvtx_range("gpe_predict");
     if (!m) return fail(GPE_ERR_INVALID, "model is NULL");
     if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
     if (N == 0) return GPE_OK;
@@ -1374,6 +1375,7 @@ int gpe_bank_destroy(gpe_bank* b) {
 
 int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                      double* hess, unsigned flags, void* stream) {
+    NvtxRange nvtx_range("gpe_bank_predict");
     if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
     if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
     if (N == 0) return GPE_OK;
@@ -1468,6 +1470,7 @@ __global__ void __launch_bounds__(128) k_bank_cost(const double* __restrict__ mu
 
 int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
                   double* cost, double* grad, void* stream) {
+    NvtxRange nvtx_range("gpe_bank_cost");
     if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
     if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
     if (N == 0) return GPE_OK;
@@ -1541,6 +1544,7 @@ int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t
 }
 
 int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd, double* deriv_full) {
+    NvtxRange nvtx_range("gpe_bank_forward");
     if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
     if (!b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
     if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");

@@ -1,6 +1,7 @@
 // Host-side helpers shared by the translation units of libgpemu.so (defined in gpemu.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 namespace gpe {
 
@@ -10,5 +11,14 @@ int set_error(int code, const char* fmt, ...);
 int require_device(int device, int* sms);
 // Count one kernel launch (gpe_launch_count).
 void count_launch();
+
+// NVTX range around a host-side stage (header-only NVTX 3: a no-op costing nanoseconds unless a profiler is attached;
+// `ncu --nvtx` / Nsight Systems then show the library's stages by name).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 }  // namespace gpe

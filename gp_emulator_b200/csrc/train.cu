@@ -398,6 +398,7 @@ int gpe_trainer_destroy(gpe_trainer* t) {
 
 int gpe_trainer_eval(gpe_trainer* t, int B, const int* target_index, const double* thetas, double* loglik, double* grad,
                      int* status) {
+    NvtxRange nvtx_range("gpe_trainer_eval");
     if (!t) return set_error(GPE_ERR_INVALID, "trainer is NULL");
     if (B < 0) return set_error(GPE_ERR_INVALID, "B must be >= 0");
     if (B == 0) return GPE_OK;
