@@ -113,7 +113,7 @@ def addr(a):
     if a is None:
         return None
     if isinstance(a, np.ndarray):
-        return a.ctypes.data
+        return a.__array_interface__["data"][0]   # (a.ctypes.data builds a helper object: 2.6 us against 0.5 us)
     return a.data_ptr()  # torch tensor
 
 

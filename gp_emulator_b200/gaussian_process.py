@@ -123,13 +123,13 @@ class GaussianProcess:
 
         The reference's benchmark REBINDS the attributes between calls (tests/benchmark.py:11-15), so every predict
         checks a key: the bytes of the small vectors (theta, invQt) and, for the two matrices (``inputs`` 20 KB and
-        ``invQ`` 500 KB at M = 250 -- hashing them would cost 10-15 us, a fifth of a one-point predict), identity,
-        shape and the bytes of every 61st element (4 us in total).  After editing a few entries of ``inputs`` / ``invQ`` IN PLACE
-        call ``invalidate_device()``.
+        ``invQ`` 500 KB at M = 250 -- hashing them would cost 10-15 us, a third of a one-point predict), identity,
+        shape and the bytes of ~64 evenly spaced elements (2 us in total).  After editing a few entries of ``inputs`` /
+        ``invQ`` IN PLACE call ``invalidate_device()``.
         """
-        def fingerprint(a):      # ~1 us: identity, shape and the bytes of every 61st element
+        def fingerprint(a):      # ~1 us: identity, shape and the bytes of ~64 evenly spaced elements
             q = np.asarray(a)
-            return (id(a), q.shape, q.dtype.str, q.ravel()[::61].tobytes())
+            return (id(a), q.shape, q.dtype.str, q.reshape(-1)[::max(1, q.size // 64)].tobytes())
 
         invQ = getattr(self, "invQ", None)
         key = [np.asarray(self.theta).tobytes(), np.asarray(self.invQt).tobytes(), self.device, fingerprint(self.inputs)]
