@@ -49,11 +49,8 @@ def main():
                                                                        np.sqrt(np.mean(truth ** 2))))
 
     bands = [40, 120, 200, 280, 360]                                          # 4. per-band GPs
-    gps = []
-    for bnd in bands:
-        gp = gpe.GaussianProcess(y_train, X_train[:, bnd])
-        gp.learn_hyperparameters(n_tries=10, batched=True)
-        gps.append(gp)
+    from gp_emulator_b200.training import fit_bank
+    gps, _ = fit_bank(y_train, X_train[:, bands].T, n_tries=10)              # all bands x starts in one batch
     mu, var, grad = gps[0].predict(y_test)
     hess = gps[0].hessian(y_test[:8])
     mu32, var32, _ = gps[0].predict(y_test.astype(np.float32), precision=np.float32)

@@ -301,3 +301,32 @@ def _minimise_threads(evaluate, starts, verbose=False):
     if errors:
         raise errors[0]
     return results, {"rounds": rv.rounds, "evaluations": rv.evaluations, "driver": "threads"}
+
+
+def fit_bank(inputs, targets, n_tries=5, device=0, verbose=False):
+    """Fit E GPs that share ``inputs`` (M, D) -- one per row of ``targets`` (E, M) -- in ONE batch of E x n_tries descents.
+
+    The per-band pattern of the reference (tests/test_perband_emulator.py:22-37: a loop of ``GaussianProcess(y_train,
+    band).learn_hyperparameters(n_tries=...)``) with every round of cost + gradient evaluations served by one GPU launch.
+    Random starts are drawn as E successive ``learn_hyperparameters`` calls would draw them.  Returns the list of fitted
+    ``GaussianProcess`` objects (state built by the host ``_set_params`` at the best theta of each) and the driver stats.
+    """
+    from .gaussian_process import GaussianProcess
+    inputs = np.asarray(inputs)
+    targets = np.atleast_2d(np.asarray(targets, dtype=np.float64))
+    E, D = targets.shape[0], inputs.shape[1]
+    starts = [(e, th) for e in range(E) for th in 5.0 * (np.random.rand(n_tries, D + 2) - 0.5)]
+    trainer = DeviceTrainer(inputs, targets, device=device)
+    try:
+        fits, stats = minimise_batched(trainer.evaluate, starts, verbose=verbose)
+    finally:
+        trainer.close()
+    gps = []
+    for e in range(E):
+        mine = fits[e * n_tries:(e + 1) * n_tries]
+        best = int(np.argsort(np.array([f[1] for f in mine]))[0])
+        gp = GaussianProcess(inputs, targets[e], device=device)
+        gp._set_params(np.array(mine[best][0]))
+        gp.fit_cost = mine[best][1]
+        gps.append(gp)
+    return gps, stats

@@ -250,3 +250,22 @@ def test_multivariate_emulator_batched_training(capsys):
         assert abs(ca - cb) <= 1e-5 * max(1.0, abs(cb))
     fwd, _ = mv.predict(y[4])
     assert fwd.shape == (50,) and np.max(np.abs(fwd - X[4])) < 0.5
+
+
+@pytest.mark.gpu
+def test_fit_bank_trains_all_bands_in_one_batch(capsys):
+    from gp_emulator_b200.training import fit_bank
+    rs = np.random.RandomState(4)
+    x = rs.random_sample((36, 2))
+    targets = np.stack([np.sin(3 * x[:, 0]) + x[:, 1], np.cos(2 * x[:, 1]) * x[:, 0], x[:, 0] ** 2 - x[:, 1]])
+    targets = targets + 0.03 * rs.standard_normal(targets.shape)
+    np.random.seed(11)
+    gps, stats = fit_bank(x, targets, n_tries=3)
+    assert len(gps) == 3 and stats["evaluations"] > stats["rounds"]
+    np.random.seed(11)
+    for e, gp in enumerate(gps):                       # same draws, same optimiser as E sequential host fits
+        host = GaussianProcess(x, targets[e])
+        c_host, _ = host.learn_hyperparameters(n_tries=3)
+        assert abs(gp.fit_cost - c_host) <= 1e-5 * max(1.0, abs(c_host))
+        mu, var, _ = gp.predict(x)
+        assert np.max(np.abs(mu - targets[e])) < 0.3 and (var > -1e-9).all()
