@@ -59,7 +59,9 @@ class DeviceModel:
 
     def __init__(self, inputs, theta, invQt, invQ=None, device=0, symmetric_variance=False):
         """``symmetric_variance=True`` opts into evaluating k^T invQ k through the upper-triangular fold of invQ
-        (exact identity for any invQ, half the tensor-core work, rounding differs at the 1e-16 level)."""
+        (exact identity for any invQ, half the tensor-core work, rounding differs at the 1e-16 level);
+        ``"auto"`` folds only when ``invQ`` is symmetric to 1e-6 of its largest entry -- what the inverse of a
+        covariance matrix is (``_prepare_likelihood``: ~3e-10), unlike the random ``invQ`` of the reference benchmark."""
         inputs = f64c(inputs)
         if inputs.ndim != 2:
             raise ValueError("inputs must be (M, D)")
@@ -78,9 +80,14 @@ class DeviceModel:
         self.device = int(device)
         self.has_var = invQ is not None
         h = C.c_void_p()
+        if isinstance(symmetric_variance, str):
+            if symmetric_variance != "auto":
+                raise ValueError('symmetric_variance must be True, False or "auto"')
+            symmetric_variance = (invQ is not None and self.M > 1
+                                  and float(np.max(np.abs(invQ - invQ.T))) <= 1e-6 * float(np.max(np.abs(invQ))))
         self.symmetric_variance = bool(symmetric_variance)
         check(_lib.load().gpe_model_create_ex(self.device, self.M, self.D, addr(inputs), addr(expx), addr(invQt),
-                                              addr(invQ), _lib.OPT_SYMMETRIC_VARIANCE if symmetric_variance else 0,
+                                              addr(invQ), _lib.OPT_SYMMETRIC_VARIANCE if self.symmetric_variance else 0,
                                               C.byref(h)))
         self._h = h
         self._fin = weakref.finalize(self, _lib.load().gpe_model_destroy, h)

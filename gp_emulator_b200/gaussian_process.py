@@ -32,11 +32,15 @@ def k_fold_cross_validation(X, K, randomise=False):
 class GaussianProcess:
     """Squared-exponential (ARD) GP emulator.  ``inputs`` (Ntrain, Ninputs), ``targets`` (Ntrain,)."""
 
-    def __init__(self, inputs, targets, device=0):
+    def __init__(self, inputs, targets, device=0, symmetric_variance=False):
+        """``symmetric_variance``: False (default) evaluates the variance with the general dense formula, as the reference
+        does; ``"auto"`` / True let the device fold ``invQ`` onto its upper triangle when it is symmetric / always
+        (``DeviceModel``): same value to rounding, 1.29x the throughput at M = 250."""
         self.inputs = inputs
         self.targets = targets
         (self.n, self.D) = self.inputs.shape
         self.device = device
+        self.symmetric_variance = symmetric_variance
         self._dev_model = None
         self._dev_key = None
 
@@ -132,14 +136,16 @@ class GaussianProcess:
             return (id(a), q.shape, q.dtype.str, q.reshape(-1)[::max(1, q.size // 64)].tobytes())
 
         invQ = getattr(self, "invQ", None)
-        key = [np.asarray(self.theta).tobytes(), np.asarray(self.invQt).tobytes(), self.device, fingerprint(self.inputs)]
+        key = [np.asarray(self.theta).tobytes(), np.asarray(self.invQt).tobytes(), self.device, self.symmetric_variance,
+               fingerprint(self.inputs)]
         if invQ is not None:
             key.append(fingerprint(invQ))
         key = tuple(key)
         if self._dev_model is None or key != self._dev_key:
             if self._dev_model is not None:
                 self._dev_model.close()
-            self._dev_model = DeviceModel(self.inputs, self.theta, self.invQt, invQ, device=self.device)
+            self._dev_model = DeviceModel(self.inputs, self.theta, self.invQt, invQ, device=self.device,
+                                          symmetric_variance=self.symmetric_variance)
             self._dev_key = key
         return self._dev_model
 

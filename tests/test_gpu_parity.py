@@ -577,6 +577,27 @@ def test_symmetric_variance_on_trained_model(gpemu):
     assert np.max(np.abs(out["var"] - lvar)) <= 2.0 * np.max(np.abs(g["var"] - lvar)) + 1e-18
 
 
+def test_symmetric_variance_auto_mode(gpemu):
+    """"auto" folds invQ only when it is symmetric (the inverse of a covariance matrix), never the random invQ of the
+    reference benchmark; the drop-in class passes the choice through and both stay inside the parity bars."""
+    g = golden("T")
+    m = gpemu.DeviceModel(g["inputs"], g["theta"], g["invQt"], g["invQ"], symmetric_variance="auto")
+    assert m.symmetric_variance is True
+    out = m.predict(g["testing"])
+    assert orc.var_cond_err(out["var"], g["var"], g["inputs"], g["theta"], g["invQ"], g["testing"]) < TOL
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(100, 5, 300, seed=13)
+    ms = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance="auto")
+    assert ms.symmetric_variance is False
+    gp = gpemu.GaussianProcess(g["inputs"], g["targets"], symmetric_variance="auto")
+    gp._set_params(g["theta"])
+    mu, var, deriv = gp.predict(g["testing"])
+    assert gp._dev_model.symmetric_variance is True
+    assert orc.ref_err(mu, g["mu"]) < TOL and orc.ref_err(deriv, g["deriv"]) < TOL
+    assert orc.var_cond_err(var, g["var"], g["inputs"], g["theta"], gp.invQ, g["testing"]) < TOL
+    with pytest.raises(ValueError):
+        gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance="sometimes")
+
+
 def test_documented_limits_raise_cleanly(gpemu):
     """M > GPE_MAX_TRAIN (variance) is reported as GPE_ERR_UNSUPPORTED, never a wrong answer."""
     rs = np.random.RandomState(1)
