@@ -235,13 +235,13 @@ def test_device_exp_accuracy(lib, gpemu):
 def test_tiny_host_calls_run_on_mapped_buffers(gpemu):
     """Host calls of a few points (the reference's usual call is ONE point) skip the copy engine: the kernels read and
     write the library's page-locked staging buffers directly.  Same numbers as the DMA path that page-locked caller
-    arrays take, for every output, at the sizes around the switch (256 points)."""
+    arrays take, for every output, at the sizes around the switch (16384 points)."""
     import torch
-    inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 6, 300, seed=31)
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(120, 6, 16385, seed=31)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
-    for n in (1, 7, 256, 257):
+    for n in (1, 7, 300, 16384, 16385):
         t = testing[:n]
-        got = m.predict(t, want_hess=True, pinned=False)                    # pageable in / out: mapped buffers up to 256
+        got = m.predict(t, want_hess=True, pinned=False)                    # pageable in / out: mapped buffers up to 16384
         tp = torch.from_numpy(t).pin_memory().numpy()
         ref = m.predict(tp, want_hess=True, pinned=True)                    # page-locked in / out: direct DMA
         for k in ("mu", "var", "deriv", "hess"):
