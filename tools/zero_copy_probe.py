@@ -1,5 +1,6 @@
+"""Latency of small host calls against the mapped-buffer threshold: GPE_ZERO_COPY_MAX=<points> python tools/zero_copy_probe.py"""
 import os, sys, time, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gp_emulator_b200 as g
 from oracle import gp_oracle as orc
 inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 20000, seed=0)
