@@ -102,3 +102,23 @@ def test_bind_host_to_gpu_is_a_noop_without_nvml_device():
     assert sharding.bind_host_to_gpu(0) is None or os.sched_getaffinity(0) <= before
     if sharding.bind_host_to_gpu(0) is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_argument_checks_that_need_no_device():
+    from gp_emulator_b200 import DeviceModel
+    from gp_emulator_b200.training import DeviceTrainer, minimise_batched
+    x = np.zeros((4, 2)); th = np.zeros(4); a = np.zeros(4); q = np.eye(4)
+    with pytest.raises(ValueError):
+        DeviceModel(x, th, a, q, symmetric_variance="sometimes")
+    with pytest.raises(ValueError):
+        DeviceModel(x, th[:2], a, q)                       # theta shorter than D + 1
+    with pytest.raises(ValueError):
+        DeviceModel(x, th, a[:3], q)
+    with pytest.raises(ValueError):
+        DeviceTrainer(x, np.zeros((2, 5)))                  # targets must be (T, M)
+    assert minimise_batched(lambda t, i: None, [])[0] == []
+    gp = GaussianProcess(x, a)
+    with pytest.raises(ValueError):
+        gp.predict([[0.0, 0.0]])                           # the reference indexes testing.shape: arrays only
+    with pytest.raises(AssertionError):
+        gp.predict(np.zeros((3, 5)))                       # wrong number of columns (reference :229 asserts)
