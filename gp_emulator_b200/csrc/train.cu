@@ -3,7 +3,7 @@
 // What it replaces: the inner loop of hyper-parameter fitting -- GaussianProcess.loglikelihood
 // (gp_emulator/GaussianProcess.py:78-95) = _set_params -> _prepare_likelihood (:52-75: Z, Q = Z + noise I, inv(Q),
 // invQ t, log|Q|) followed by partial_devs (:97-125) at the same theta.  The reference evaluates one theta at a time
-// (~0.1 s at M = 250, D = 10 in numpy); fitting a MultivariateEmulator runs n_pcs x n_tries independent L-BFGS-B
+// (5.5 ms at M = 250, D = 10 in numpy on the GPU box's 16 host cores); fitting a MultivariateEmulator runs n_pcs x n_tries independent L-BFGS-B
 // descents on the SAME training inputs (multivariate_gp.py:176-186), so their evaluations batch: one CTA per
 // (theta, target vector) problem, B problems per launch.
 //
@@ -12,7 +12,8 @@
 //   2. in-place block Gauss-Jordan inversion of Q without pivoting (Q is symmetric positive definite, so the
 //      pivots are the LDL^T pivots: log|Q| = sum log p_k, and a pivot <= 0 is the reference's LinAlgError from
 //      np.linalg.cholesky, :73-75).  M / 8 rank-8 updates of the whole matrix on the FP64 tensor cores
-//      (DMMA.8x8x4): M^3 FMA, 16 M^2 bytes of L2 traffic per 8 pivots.
+//      (DMMA.8x8x4): M^3 FMA, 16 M^2 bytes of L2 traffic per 8 pivots.  ncu (profiles/r01_ncu_train_summary.md): bound by
+//      the dependency chain of the M / 8 block steps (stage -> 8 x 8 inverse -> coefficients -> update), not by a pipe.
 //   3. alpha = invQ t, t.alpha, alpha.alpha, trace(invQ)                                   (:71-72, :118-121)
 //   4. g_d = -w_d/4 sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2,  g_D = 1/2 sum_ij (...) Z_ij,
 //      g_{D+1} = noise/2 (trace(invQ) - alpha.alpha)                                       (:108-122)
@@ -39,7 +40,7 @@ struct TrainParams {
     const double* targets;  // (T, M)
     const double* thetas;   // (B, D + 2)
     const int* tidx;        // (B) row of `targets` each problem fits
-    double* work;           // (B, 2, M, M): [0] Q -> invQ in place, [1] Z
+    double* work;           // (B, 2, Mp, Mp), Mp = M rounded up to 8: [0] Q -> invQ in place (identity in the padding), [1] Z
     double* loglik;         // (B)
     double* grad;           // (B, D + 2)
     int* status;            // (B) 0 ok, 1 Q not positive definite / non-finite
