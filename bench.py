@@ -14,6 +14,13 @@
   launch / launch duration with F = 2M^2 + M(5D+6) + D + 1 = 139,011; peak = the DMMA (FP64 tensor)
   throughput of THIS GPU measured live by the library's micro-benchmark, because the driver-written
   MEASURED_PEAKS.json holds no FP64 figure.
+* `configs`: the other BASELINE.json configurations on the same GPU, outside the headline's timed region -- cfg 1
+  (N = 1e5 through the API), cfg 3 (M = 1000, FP64 and TF32), cfg 4 (20 PCs x 2101 wavelengths with back-projection,
+  1e7 points in chunks; bound = HBM write), cfg 5 (bank of 64 GPs with gradient and Hessian, 1e7 points in chunks) --
+  each with points/s, the kernel, a roofline and parity against the oracle.  `strong_scaling`: configs[1] as written
+  (1e8 points in total, N/G per GPU).
+* N > 1: `e2e` holds both "torchrun ranks" (every rank streams its own host buffers, max over ranks) and "one
+  process" (rank 0 alone calls GaussianProcess(device=[0..N-1]).predict on host buffers: the drop-in call).
 * `cpu_baseline` / `--impl reference`: the reference's numpy/scipy cpu_predict (restated in oracle/, the
   reference itself is Python 2 and cannot be imported) on the box's host cores, bounded sample.
 """
@@ -46,6 +53,9 @@ def parse():
     ap.add_argument("--e2e-points", type=float, default=2e7, help="host-resident test points per GPU per step")
     ap.add_argument("--cpu-points", type=float, default=1e5, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1/3/4/5 block")
+    ap.add_argument("--multi-points", type=float, default=5e6, help="host-resident points per GPU of the one-process e2e (N > 1)")
+    ap.add_argument("--tripwire", type=int, default=100000, help="prefix and random-subset size of the oracle check")
     return ap.parse_args()
 
 
@@ -139,6 +149,200 @@ def cpu_baseline(model, npts, repeats=3):
             "sample": "%d points of the same workload (one 1e5-point chunk, as the reference materialises (M,N) "
                       "matrices), best of %d; numpy/scipy cpu_predict restated from GaussianProcess.py:211-251" %
                       (int(npts), repeats)}
+
+
+def flops_per_point(m, d, hess=False):
+    """2M^2 + M(5D+6) + D + 1 (+ M(D^2+2D) + D with the Hessian); exp evaluations not counted."""
+    return 2 * m * m + m * (5 * d + 6) + d + 1 + ((m * (d * d + 2 * d) + d) if hess else 0)
+
+
+def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
+    """BASELINE.json configs 1, 3, 4, 5 on one GPU: throughput, kernel, roofline, parity against the oracle."""
+    dev = torch.device("cuda", dev_index)
+    P64 = peaks["dmma_tflops"]
+    out = {}
+
+    def rate(fn, n_pts, reps=2, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return n_pts * reps / (a.elapsed_time(b) * 1e-3)
+
+    def tensor_roofline(pps, flop):
+        ach = pps * flop / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": P64, "unit": "TFLOP/s", "frac": ach / P64}
+
+    def errs(got, ref):
+        return {k: orc.ref_err(got[k].cpu().numpy() if hasattr(got[k], "cpu") else got[k], v) for k, v in ref.items()}
+
+    # ---- cfg 1: the reference's own CPU-runnable case, N = 1e5, through the drop-in API with plain numpy arrays ------
+    M, D, N = 250, 10, 100_000
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=0)
+    gp = gpe.GaussianProcess(inputs, [], device=dev_index)
+    gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt
+    for _ in range(3):
+        res = gp.predict(testing)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        res = gp.predict(testing)
+    api_pps = 5 * N / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    mu_o, var_o, der_o = orc.predict(inputs, theta, invQ, invQt, testing, chunk=100000)
+    cpu_s = time.perf_counter() - t0
+    td = torch.from_numpy(testing).to(dev)
+    dm = gp._device_model()
+    dev_pps = rate(lambda: dm.predict(td), N, reps=20, warm=3)
+    out["cfg1"] = {"workload": "GaussianProcess S-model (tests/benchmark.py recipe, seed 0) M=250 D=10, 1e5 test points, FP64 mu+var+grad",
+                   "api_numpy_points_per_s": api_pps, "device_resident_points_per_s": dev_pps, "kernel": dm.plan(N),
+                   "roofline": tensor_roofline(dev_pps, flops_per_point(M, D)),
+                   "oracle_cpu_points_per_s": N / cpu_s,
+                   "parity_vs_oracle": errs(dict(zip(("mu", "var", "deriv"), res)), {"mu": mu_o, "var": var_o, "deriv": der_o}),
+                   "note": "api = GaussianProcess.predict(numpy in, numpy out): H2D + kernel + D2H + result arrays per call; "
+                           "parity over all 1e5 points"}
+    del td, gp, dm
+
+    # ---- cfg 3: M = 1000, variance dominated; FP64 and single precision (tcgen05 / TF32) ------------------------------
+    M, D, N = 1000, 10, 10_000_000
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, 2000, seed=3)
+    m = gpe.DeviceModel(inputs, theta, invQt, invQ, device=dev_index)
+    mu_o, var_o, der_o = orc.predict(inputs, theta, invQ, invQt, testing)
+    par64 = errs(m.predict(testing), {"mu": mu_o, "var": var_o, "deriv": der_o})
+    t = torch.rand(N, D, dtype=torch.float64, device=dev)
+    pps64 = rate(lambda: m.predict(t), N, reps=2, warm=1)
+    t32 = t.to(torch.float32)
+    del t
+    o32 = m.predict_f32(testing.astype(np.float32))
+    o32x = m.predict_f32(testing.astype(np.float32), fast=False)
+    ref32 = dict(zip(("mu", "var", "deriv"), orc.predict(inputs, theta, invQ, invQt, testing.astype(np.float32).astype(np.float64))))
+    pps32 = rate(lambda: m.predict_f32(t32), N, reps=3, warm=1)
+    pps32x = rate(lambda: m.predict_f32(t32, fast=False), N, reps=2, warm=1)
+    tf_peak = bf16_tflops / 2.0 if bf16_tflops else None
+    tf_ach = pps32 * 2 * 1024 * 1024 / 1e12
+    out["cfg3"] = {"workload": "M=1000 D=10 S-model, 1e7 device-resident test points, mu+var+grad",
+                   "fp64": {"points_per_s": pps64, "kernel": m.plan(N), "roofline": tensor_roofline(pps64, flops_per_point(M, D)),
+                            "parity_vs_oracle": par64},
+                   "tf32": {"points_per_s": pps32, "points_per_s_3xtf32": pps32x,
+                            "kernel": "k_predict_tf32_big<DP=12,X3=false> (tcgen05.mma kind::tf32, TMEM accumulators, column passes)",
+                            "roofline": {"bound": "tensor", "achieved": tf_ach, "peak": tf_peak, "unit": "TFLOP/s",
+                                         "frac": (tf_ach / tf_peak) if tf_peak else None,
+                                         "note": "executed TF32 flop (2*Mp^2 per point, Mp=1024) / time; peak = half the measured bf16 "
+                                                 "rate of MEASURED_PEAKS.json (no TF32 figure there); the kernel is bound by the FP32 "
+                                                 "issue rate of K* generation, not by the tensor pipe (DESIGN 4.3c)"},
+                            "error_vs_fp64_oracle": errs(o32, ref32), "error_vs_fp64_oracle_3xtf32": errs(o32x, ref32),
+                            "stated_bound": "variance 2^-11 relative to max|var| (one TF32 pass); reference FP32 pass bar 1e-5 "
+                                            "(tests/benchmark.py:56) met by mean/gradient, and by the variance with the 3x split at M <= 256"}}
+    del t32, m
+
+    # ---- cfg 4: MultivariateEmulator, 20 PCs x 2101 wavelengths, 1e7 test inputs, batched predict + back-projection ----
+    M, D, P, W, N, CH = 250, 10, 20, 2101, 10_000_000, 200_000
+    rs = np.random.RandomState(4)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((P, D + 2)); invQts = rs.random_sample((P, M)); invQs = rs.random_sample((P, M, M))
+    basis = np.linalg.qr(rs.standard_normal((W, P)))[0].T.copy()
+    bank = gpe.DeviceBank(inputs, thetas, invQts, invQs, basis=basis, device=dev_index)
+    tt = rs.random_sample((64, D))
+    models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(P)]
+    fwd_o, mu_o, var_o, grad_o, dfull_o = orc.mv_predict_batch(models, basis, tt, want_deriv_full=True)
+    got = bank.predict(tt, want_var=True, want_deriv=True, project=True, project_deriv=True)
+    par4 = errs(got, {"fwd": fwd_o, "mu": mu_o, "var": var_o, "deriv": grad_o, "deriv_full": dfull_o})
+    t = torch.rand(N, D, dtype=torch.float64, device=dev)
+    lib = _lib_handle()
+    mu_b = torch.empty(CH, P, dtype=torch.float64, device=dev); der_b = torch.empty(CH, P, D, dtype=torch.float64, device=dev)
+    fwd_b = torch.empty(CH, W, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev_index).cuda_stream
+
+    def cfg4_pass(project=True):
+        for c0 in range(0, N, CH):      # the 168 GB of spectra are produced chunk-wise into one 3.4 GB buffer
+            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + CH].data_ptr(), CH, mu_b.data_ptr(), None, der_b.data_ptr(), None,
+                                           fwd_b.data_ptr() if project else None, None, 0x01 | 0x04 | (0x10 if project else 0), st))
+    pps4 = rate(cfg4_pass, N, reps=1, warm=1)
+    pps4_pc = rate(lambda: cfg4_pass(False), N, reps=1, warm=0)
+    proj_s = 1.0 / pps4 - 1.0 / pps4_pc
+    out["cfg4"] = {"workload": "MultivariateEmulator bank P=20 PCs, W=2101 wavelengths, M=250 D=10; 1e7 device-resident test inputs in "
+                               "chunks of 2e5: PC means + PC gradients + back-projected spectra fwd (N, 2101)",
+                   "points_per_s": pps4, "pc_space_only_points_per_s": pps4_pc,
+                   "kernel": "k_predict_mean2<10,false> (bank: blockIdx.y = PC) + k_project<5>",
+                   "roofline": {"bound": "hbm", "achieved": pps4 * W * 8 / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                                "frac": pps4 * W * 8 / 1e9 / hbm_gbs,
+                                "note": "algorithmic bytes = 8 W = 16,808 B of spectrum written per point (SURVEY 8d) over the whole "
+                                        "step (GP kernels + projection); peak = MEASURED_PEAKS.json hbm_gbs",
+                                "projection_only_GBps": W * 8 / proj_s / 1e9 if proj_s > 0 else None},
+                   "parity_vs_oracle": par4}
+    # host-resident: numpy in, PC-space outputs out (1,760 B per point back over PCIe), chunk walk below the C ABI
+    Nh = 2_000_000
+    h_in = torch.rand(Nh, D, dtype=torch.float64).pin_memory().numpy()
+    h_out = {"mu": torch.empty(Nh, P, dtype=torch.float64).pin_memory().numpy(),
+             "deriv": torch.empty(Nh, P, D, dtype=torch.float64).pin_memory().numpy()}
+    bank.predict(h_in, want_var=False, out=h_out)
+    t0 = time.perf_counter()
+    bank.predict(h_in, want_var=False, out=h_out)
+    out["cfg4"]["host_resident_pc_space_points_per_s"] = Nh / (time.perf_counter() - t0)
+    out["cfg4"]["host_resident_note"] = ("pinned numpy in/out through gpe_bank_predict_ex(GPE_HOST_PTRS); %d B per point D2H: the PCIe "
+                                         "link (~55 GB/s) allows %.2e points/s" % (8 * P * (1 + D), 55e9 / (8 * P * (1 + D))))
+    del t, mu_b, der_b, fwd_b, bank, h_in, h_out
+
+    # ---- cfg 5: per-band bank of 64 GPs sharing test inputs, mean + variance + gradient + Hessian --------------------
+    M, D, E, N, CH = 250, 10, 64, 10_000_000, 100_000
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    bank = gpe.DeviceBank(inputs, thetas, invQts, invQs, device=dev_index)
+    tt = rs.random_sample((40, D))
+    models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(E)]
+    mu_o, var_o, grad_o, hess_o = orc.bank_predict(models, tt, do_hess=True)
+    got = bank.predict(tt, want_var=True, want_deriv=True, want_hess=True)
+    par5 = errs(got, {"mu": mu_o, "var": var_o, "deriv": grad_o, "hess": hess_o})
+    t = torch.rand(N, D, dtype=torch.float64, device=dev)
+    ob = {"mu": torch.empty(CH, E, dtype=torch.float64, device=dev), "var": torch.empty(CH, E, dtype=torch.float64, device=dev),
+          "deriv": torch.empty(CH, E, D, dtype=torch.float64, device=dev), "hess": torch.empty(CH, E, D, D, dtype=torch.float64, device=dev)}
+
+    def cfg5_pass(n_total):
+        for c0 in range(0, n_total, CH):   # 573 GB of outputs in total: produced chunk-wise into one 5.7 GB set of buffers
+            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + CH].data_ptr(), CH, ob["mu"].data_ptr(), ob["var"].data_ptr(),
+                                           ob["deriv"].data_ptr(), ob["hess"].data_ptr(), None, None, 0x0F, st))
+    cfg5_pass(2 * CH)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); cfg5_pass(N); b.record(); torch.cuda.synchronize()
+    pps5 = N / (a.elapsed_time(b) * 1e-3)
+    out["cfg5"] = {"workload": "bank of 64 S-model GPs sharing 1e7 device-resident test inputs (chunks of 1e5), M=250 D=10 FP64, "
+                               "mu+var+grad+Hessian = 112 doubles per point per emulator",
+                   "points_per_s": pps5, "emulator_points_per_s": pps5 * E,
+                   "kernel": "64 x k_predict_full<4,8,2,4,10,1,2,true,false,true> (fused Hessian, phase C) per chunk",
+                   "roofline": tensor_roofline(pps5 * E, flops_per_point(M, D, hess=True)),
+                   "output_GBps": pps5 * E * 112 * 8 / 1e9, "parity_vs_oracle": par5}
+    del ob
+    # 5b: the same bank consumed on the fly (cost + gradient per point), device- and host-resident
+    Nc = 2_000_000
+    obs_v = mu_o.mean(axis=0)
+    c_o, g_o = orc.bank_cost(models, tt, obs_v)
+    oc = bank.cost(tt, obs_v)
+    obs_d = torch.from_numpy(obs_v).to(dev)
+    pps5b = rate(lambda: bank.cost(t[:Nc], obs_d), Nc, reps=2, warm=1)
+    h_in = torch.rand(Nc, D, dtype=torch.float64).pin_memory().numpy()
+    bank.cost(h_in, obs_v)
+    t0 = time.perf_counter()
+    bank.cost(h_in, obs_v)
+    out["cfg5"]["on_the_fly_cost"] = {"device_resident_points_per_s": pps5b, "host_resident_points_per_s": Nc / (time.perf_counter() - t0),
+                                      "kernel": "k_predict_mean2<10,false> (bank) + k_bank_cost", "bytes_out_per_point": 8 * (1 + D),
+                                      "parity_vs_oracle": {"cost": orc.ref_err(oc["cost"], c_o), "grad": orc.ref_err(oc["grad"], g_o)},
+                                      "note": "gpe_bank_cost / gpe_bank_cost_host: least-squares misfit of the 64 means against one observed "
+                                              "vector + its gradient, reduced on the device (88 B per point instead of 5.6 KB)"}
+    return out
+
+
+def _lib_handle():
+    from gp_emulator_b200 import _lib
+    return _lib.load()
+
+
+def _check(rc):
+    from gp_emulator_b200 import _lib
+    _lib.check(rc)
 
 
 def run_reference(args, rank, world):

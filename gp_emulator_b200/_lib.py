@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpemu.so")
 
 WANT_MU, WANT_VAR, WANT_DERIV, WANT_HESS, HOST_PTRS = 0x01, 0x02, 0x04, 0x08, 0x100
+WANT_FWD, WANT_DERIV_FULL = 0x10, 0x20
 OPT_SYMMETRIC_VARIANCE = 0x1
 F32_FAST_TF32 = 0x200
 F32_FORCE_3X = 0x400
@@ -24,8 +25,10 @@ TRAIN_MAX_M = 1024
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)
 SYMBOLS = (
     "gpe_last_error", "gpe_version", "gpe_device_count", "gpe_model_create", "gpe_model_create_ex", "gpe_model_destroy",
-    "gpe_predict", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_destroy", "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict",
-    "gpe_bank_cost", "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
+    "gpe_predict", "gpe_model_plan", "gpe_predict_f32", "gpe_predict_wrap", "gpe_multi_create", "gpe_multi_predict", "gpe_multi_predict_device",
+    "gpe_multi_destroy", "gpe_multi_bank_create", "gpe_multi_bank_predict", "gpe_multi_bank_cost",
+    "gpe_bank_create", "gpe_bank_destroy", "gpe_bank_predict", "gpe_bank_predict_ex",
+    "gpe_bank_cost", "gpe_bank_cost_host", "gpe_bank_project", "gpe_bank_forward", "gpe_measure_fp64_peaks", "gpe_launch_count",
     "gpe_trainer_create", "gpe_trainer_eval", "gpe_trainer_destroy",
 )
 
@@ -61,6 +64,8 @@ def load():
     lib.gpe_model_destroy.argtypes = [C.c_void_p]
     lib.gpe_predict.restype = C.c_int
     lib.gpe_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint, C.c_void_p]
+    lib.gpe_model_plan.restype = C.c_int
+    lib.gpe_model_plan.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
     lib.gpe_predict_f32.restype = C.c_int
     lib.gpe_predict_f32.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, C.c_uint, C.c_void_p]
     lib.gpe_multi_create.restype = C.c_int
@@ -70,6 +75,20 @@ def load():
     lib.gpe_multi_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, C.c_uint]
     lib.gpe_multi_destroy.restype = C.c_int
     lib.gpe_multi_destroy.argtypes = [C.c_void_p]
+    pp = C.POINTER(C.c_void_p)   # arrays of per-device pointers
+    lib.gpe_multi_predict_device.restype = C.c_int
+    lib.gpe_multi_predict_device.argtypes = [C.c_void_p, pp, C.POINTER(C.c_int64), pp, pp, pp, pp, C.c_uint, pp]
+    lib.gpe_multi_bank_create.restype = C.c_int
+    lib.gpe_multi_bank_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int,
+                                          C.POINTER(C.c_void_p)]
+    lib.gpe_multi_bank_predict.restype = C.c_int
+    lib.gpe_multi_bank_predict.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, dp, dp, C.c_uint]
+    lib.gpe_multi_bank_cost.restype = C.c_int
+    lib.gpe_multi_bank_cost.argtypes = [C.c_void_p, dp, C.c_int64, dp, C.c_int64, dp, dp, dp]
+    lib.gpe_bank_predict_ex.restype = C.c_int
+    lib.gpe_bank_predict_ex.argtypes = [C.c_void_p, dp, C.c_int64, dp, dp, dp, dp, dp, dp, C.c_uint, C.c_void_p]
+    lib.gpe_bank_cost_host.restype = C.c_int
+    lib.gpe_bank_cost_host.argtypes = [C.c_void_p, dp, C.c_int64, dp, C.c_int64, dp, dp, dp]
     lib.gpe_predict_wrap.restype = C.c_int
     lib.gpe_predict_wrap.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.gpe_bank_create.restype = C.c_int

@@ -6,6 +6,8 @@
 // stream test points through a two-slot pinned pipeline (replaces the Python chunk loop of
 // GaussianProcess.gpu_predict / get_gpu_block, gp_emulator/GaussianProcess.py:253-323).
 #include <cuda_runtime.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -27,6 +29,7 @@
 #include "launch.h"
 #include "gpe_math.cuh"
 #include "host_common.h"
+#include "host_stream.h"
 
 using namespace gpe;
 
@@ -52,10 +55,6 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr uint32_t kSmemMax = 232448;  // 227 KB opt-in limit per CTA on sm_100
-constexpr int64_t kPipeChunk = 1 << 18;  // points per host-streaming chunk
-constexpr int64_t kZeroCopyMax = 16384;  // host calls of up to this many points run on mapped page-locked buffers
-                                         // (tools/zero_copy_probe.py: 1000 points 71 -> 58 us, 16000 points 470 -> 300 us)
-
 inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 constexpr int kHessFusedMaxDp = 16;   // predict_full_inst.cu instantiates the HESS variants up to this DP
@@ -84,19 +83,6 @@ struct MeanPlan {
     uint32_t off_xc = 0, off_ts = 0, off_out = 0, smem = 0, smem_hess = 0;
 };
 
-struct Slot {
-    cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
-    double* d_in = nullptr;
-    double* d_out = nullptr;   // mu | var | deriv | hess, sized for the flags of the first use
-    double* h_in = nullptr;    // pinned staging (pageable callers only)
-    double* h_out = nullptr;
-    size_t d_in_cap = 0, d_out_cap = 0, h_in_cap = 0, h_out_cap = 0;
-    // pending copy-out for the staging path
-    bool pending = false;
-    int64_t pend_n0 = 0, pend_n = 0;
-};
-
 }  // namespace
 
 struct gpe_model {
@@ -117,6 +103,7 @@ struct gpe_model {
     int64_t large_chunk = 0;             // points per sub-batch = capacity of the K* scratch
     double* d_kscratch = nullptr;        // [large_chunk / 16][large_kblk][16][4], pads stay zero
     cudaEvent_t scratch_free = nullptr;  // the scratch is shared by every stream that predicts with this model
+    std::mutex scratch_mu;               // wait -> launches -> record on the scratch is one critical section per caller
     double centre[32];
     bool hess_fused_ok = false;
     double* d_xchunks_mean = nullptr;
@@ -130,26 +117,28 @@ struct gpe_model {
     Slot slots[3];               // host-streaming pipeline: the direct (pinned caller) path uses two, the staged path three
 };
 
-struct gpe_multi {
-    std::vector<gpe_model*> models;   // one resident copy of the GP per device
-};
-
 struct gpe_bank {
     int device = 0, E = 0, M = 0, D = 0, W = 0;
     std::vector<gpe_model*> models;
     MeanBankEntry* d_entries = nullptr;  // per-emulator phase-A data for the one-launch bank mean / Hessian kernel
-    double* d_basis = nullptr;   // basis pre-tiled as [ceil(E/4)][Wp][4], Wp = W rounded up to 256
+    double* d_basis = nullptr;   // basis pre-tiled as [ks][Wp][4] per slice of 32 emulators, Wp = W rounded up to 128
     int Wp = 0;
-    // gpe_bank_forward (host in, host out, one synchronisation): stream + staging buffers, grown on demand
-    std::mutex fwd_mu;
-    cudaStream_t fwd_st = nullptr;
-    double *fwd_h = nullptr, *fwd_d = nullptr;
-    size_t fwd_h_cap = 0, fwd_d_cap = 0;
+    // host-pointer calls (GPE_HOST_PTRS, gpe_bank_forward): the bank's own streaming slots, one call at a time
+    std::mutex host_mu;
+    Slot slots[3];
+    double* d_aux = nullptr;     // shared observation vector + weights of a host-pointer gpe_bank_cost call
+    size_t aux_cap = 0;
     // gpe_bank_cost: per-chunk mu / deriv scratch, shared by every stream that reduces with this bank
     std::mutex cost_mu;
     double* cost_d = nullptr;
     size_t cost_cap = 0;
     cudaEvent_t cost_free = nullptr;
+};
+
+struct gpe_multi {
+    std::vector<int> devices;
+    std::vector<gpe_model*> models;   // one resident copy of the GP per device (single-GP handle) ...
+    std::vector<gpe_bank*> banks;     // ... or of the bank (bank handle)
 };
 
 namespace {
@@ -324,16 +313,6 @@ int check_device(int device, int* sms) {
     return GPE_OK;
 }
 
-void free_slot(Slot& s) {
-    if (s.d_in) cudaFree(s.d_in);
-    if (s.d_out) cudaFree(s.d_out);
-    if (s.h_in) cudaFreeHost(s.h_in);
-    if (s.h_out) cudaFreeHost(s.h_out);
-    if (s.done) cudaEventDestroy(s.done);
-    if (s.st) cudaStreamDestroy(s.st);
-    s = Slot();
-}
-
 // Operand of the fused Hessian (predict_full.cuh, phase C): p_tiled[kb][col][c] = b alpha_j x'_jd x'_je for
 // j = 4 kb + c, col = index of (d <= e) in the row-major upper triangle, x' = sqrt(w) x - centre (mid-range).
 // The expansion sum k a (x'_d - t'_d)(x'_e - t'_e) = S2 - t'_d g_e - t'_e g_d - t'_d t'_e S0 loses about
@@ -391,6 +370,9 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     if (var != nullptr && m->has_invQ && !m->full.valid && m->large_valid) {
         // 1024 < M <= GPE_MAX_TRAIN: per sub-batch, K* + mean + gradient (k_predict_mean2<DP, true>) into the scratch,
         // then the column-pass contraction (k_var_large).  The scratch is per model: streams take turns.
+        // (two threads on different streams must not both pass the wait before either records: hold the model's
+        // scratch mutex from the wait to the record, as gpe_bank_cost does for its scratch)
+        std::lock_guard<std::mutex> scratch_lock(m->scratch_mu);
         CUDA_TRY(cudaStreamWaitEvent(st, m->scratch_free, 0));
         for (int64_t n0 = 0; n0 < N; n0 += m->large_chunk) {
             const int64_t n = std::min(m->large_chunk, N - n0);
@@ -474,336 +456,83 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     return GPE_OK;
 }
 
-bool is_pinned_or_null(const void* p) {
-    if (p == nullptr) return true;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
+struct IoList {
+    IoSpec v[kMaxIo];
+    int n = 0;
+    int add(const void* host, int64_t width) {
+        if (n >= kMaxIo) return -1;
+        v[n].host = const_cast<void*>(host);
+        v[n].width = width;
+        return n++;
     }
-    return a.type == cudaMemoryTypeHost;
-}
-
-int ensure(double** ptr, size_t* cap, size_t need, bool host) {
-    if (*cap >= need) return GPE_OK;
-    if (*ptr) {
-        if (host) cudaFreeHost(*ptr); else cudaFree(*ptr);
-        *ptr = nullptr; *cap = 0;
-    }
-    if (host) CUDA_TRY(cudaMallocHost((void**)ptr, need));
-    else CUDA_TRY(cudaMalloc((void**)ptr, need));
-    *cap = need;
-    return GPE_OK;
-}
-
-// Staging copies for pageable callers.  One core moves ~14 GB/s on the GPU boxes, eight ~50 GB/s, and the PCIe link
-// 55 GB/s each way, so copies of 1 MB and more are split into >= 256 KB pieces over a small persistent pool (created on first use;
-// the submitting thread takes a share of the pieces itself).  Several threads may submit at once: the staged pipeline
-// copies results out on its own thread while the caller's thread stages the next inputs.
-class CopyPool {
-public:
-    static CopyPool& get() {
-        static CopyPool pool;
-        return pool;
-    }
-    void copy(void* dst, const void* src, size_t bytes) {
-        constexpr size_t kPiece = 256u << 10;   // waking a worker costs tens of microseconds: not worth it below 1 MB
-        const size_t want = bytes >= 4 * kPiece ? bytes / kPiece : 1;
-        const unsigned np = (unsigned)std::min<size_t>(workers_.size() + 1, std::max<size_t>(want, 1));
-        if (np <= 1) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        const size_t part = (bytes / np + 63) & ~(size_t)63;
-        Batch batch;
-        unsigned queued = 0;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            for (unsigned i = 1; i < np; ++i) {
-                const size_t off = (size_t)i * part;
-                if (off >= bytes) break;
-                q_.push_back(Task{(char*)dst + off, (const char*)src + off, std::min(part, bytes - off), &batch});
-                ++queued;
-            }
-            batch.remaining = (int)queued;
-        }
-        cv_.notify_all();
-        memcpy(dst, src, std::min(part, bytes));
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return batch.remaining == 0; });
-    }
-
-private:
-    struct Batch { int remaining = 0; };
-    struct Task { char* dst; const char* src; size_t len; Batch* batch; };
-    CopyPool() {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const unsigned n = std::min(7u, std::max(1u, hw / 2) - (hw >= 4 ? 1u : 0u));
-        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    void run() {
-        std::unique_lock<std::mutex> lk(mu_);
-        for (;;) {
-            cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
-            if (stop_) return;
-            Task t = q_.front();
-            q_.pop_front();
-            lk.unlock();
-            memcpy(t.dst, t.src, t.len);
-            lk.lock();
-            if (--t.batch->remaining == 0) done_cv_.notify_all();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::deque<Task> q_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    bool stop_ = false;
 };
 
-void par_memcpy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
+// Pin the calling thread to the CPUs that are local to `device` (sysfs local_cpulist of its PCI function), so that the
+// staging copies and first touches of a per-device pipeline thread stay on the GPU's NUMA node.  Best effort.
+void bind_thread_near_device(int device) {
+    char bdf[32];
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return;
+    char line[4096];
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    if (fgets(line, sizeof(line), f)) {
+        char* save = nullptr;
+        for (char* tok = strtok_r(line, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
+            int a = 0, b = 0;
+            if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET(i, &set); ++count; } }
+            else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) { CPU_SET(a, &set); ++count; }
+        }
+    }
+    fclose(f);
+    if (count > 0) pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+}
 
-// Host-resident caller: stream chunks through a few slots so the H2D copy of chunk i+1, the kernels of chunk i and
-// the D2H copy of chunk i-1 overlap.
-//   pinned caller buffers   : DMA'd directly, two slots, 2^18-point chunks;
-//   pageable caller buffers : staged through page-locked slot buffers -- inputs and outputs independently, so a
-//                             caller with pageable inputs and page-locked result arrays only pays for the copy-in.  The caller's thread stages inputs and
-//                             enqueues (copy-in -> H2D -> kernels -> D2H -> event), a second thread waits for each
-//                             chunk's event and copies its results out, both copying through the CopyPool; three
-//                             slots keep the GPU busy while either side is late.  Chunks are about a quarter of the
-//                             call (whole waves of 64-point tiles, at most 2^18 points) so that mid-sized calls
-//                             (1e5 points) overlap too.
-// T = double (FP64 path) or float (single-precision path); `launch(d_in, n, d_mu, d_var, d_deriv, d_hess, stream)`
-// enqueues the kernels for one chunk.
-template <typename T, typename Launch>
-int predict_host_t(gpe_model* m, const T* testing, int64_t N, T* mu, T* var, T* deriv, T* hess, Launch launch) {
-    constexpr size_t ES = sizeof(T);
-    const int D = m->D;
-    const int64_t per_out = (mu ? 1 : 0) + (var ? 1 : 0) + (deriv ? D : 0) + (hess ? (int64_t)D * D : 0);
-    // inputs and outputs are staged independently: page-locked caller memory is DMA'd directly on either side
-    // (a pointer query on pageable memory costs ~10 us: a small call with pageable inputs does not ask about its
-    // outputs -- staging a few KB is cheaper than finding out)
-    const bool in_direct = is_pinned_or_null(testing);
-    const bool tiny = N <= 3 * 64 * (int64_t)m->sms;
-    const bool out_direct = (in_direct || !tiny) && is_pinned_or_null(mu) && is_pinned_or_null(var) &&
-                            is_pinned_or_null(deriv) && is_pinned_or_null(hess);
-    const bool direct = in_direct && out_direct;
-    int64_t CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(N, 1));
-    if (!direct) {
-        const int64_t wave = 64 * (int64_t)m->sms;
-        CH = std::min<int64_t>(kPipeChunk, std::max<int64_t>(2 * wave, ((N + 3) / 4 + wave - 1) / wave * wave));
-        if (N <= 3 * wave) CH = std::max<int64_t>(N, 1);   // too small to be worth a second thread
-    }
-    const int ns = direct ? 2 : 3;
-    for (int i = 0; i < ns; ++i) {
-        Slot& s = m->slots[i];
-        if (!s.st) CUDA_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        int rc = ensure(&s.d_in, &s.d_in_cap, (size_t)CH * D * ES, false);
-        if (rc) return rc;
-        rc = ensure(&s.d_out, &s.d_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, false);
-        if (rc) return rc;
-        if (!in_direct) {
-            rc = ensure(&s.h_in, &s.h_in_cap, (size_t)CH * D * ES, true);
-            if (rc) return rc;
-        }
-        if (!out_direct) {
-            rc = ensure(&s.h_out, &s.h_out_cap, (size_t)CH * std::max<int64_t>(per_out, 1) * ES, true);
-            if (rc) return rc;
-        }
-        s.pending = false;
-    }
-    struct Outs { T *mu, *var, *der, *hes; };
-    auto carve = [&](Slot& s, int64_t n) {
-        T* o = reinterpret_cast<T*>(s.d_out);
-        Outs r;
-        r.mu = mu ? o : nullptr;    if (mu) o += n;
-        r.var = var ? o : nullptr;  if (var) o += n;
-        r.der = deriv ? o : nullptr; if (deriv) o += n * D;
-        r.hes = hess ? o : nullptr;
-        return r;
-    };
-    auto d2h_direct = [&](Slot& s, const Outs& o, int64_t n0, int64_t n) -> int {
-        if (mu) CUDA_TRY(cudaMemcpyAsync(mu + n0, o.mu, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-        if (var) CUDA_TRY(cudaMemcpyAsync(var + n0, o.var, (size_t)n * ES, cudaMemcpyDeviceToHost, s.st));
-        if (deriv) CUDA_TRY(cudaMemcpyAsync(deriv + n0 * D, o.der, (size_t)n * D * ES, cudaMemcpyDeviceToHost, s.st));
-        if (hess) CUDA_TRY(cudaMemcpyAsync(hess + n0 * D * D, o.hes, (size_t)n * D * D * ES, cudaMemcpyDeviceToHost, s.st));
-        return GPE_OK;
-    };
-    if (direct) {
-        int which = 0;
-        for (int64_t n0 = 0; n0 < N; n0 += CH, which ^= 1) {
-            Slot& s = m->slots[which];
-            const int64_t n = std::min(CH, N - n0);
-            T* const d_in = reinterpret_cast<T*>(s.d_in);
-            const Outs o = carve(s, n);
-            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
-            int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
-            if (rc) return rc;
-            rc = d2h_direct(s, o, n0, n);
-            if (rc) return rc;
-        }
-        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(m->slots[i].st));
-        return GPE_OK;
-    }
-
-    // ---- staged path (inputs and / or outputs in pageable memory) -------------------------------------------
-    static const bool pipe_trace = getenv("GPE_PIPE_TRACE") != nullptr;   // dev aid: host-side time split of a call
-    double t_wait = 0, t_out = 0, t_in = 0, t_block = 0;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    auto copy_out = [&](Slot& s) -> cudaError_t {   // wait for the slot's chunk, then scatter its results to the caller
-        double t0 = now();
-        cudaError_t e = cudaEventSynchronize(s.done);
-        if (e != cudaSuccess) return e;
-        t_wait += now() - t0; t0 = now();
-        if (out_direct) return cudaSuccess;          // the D2H copies went straight into the caller's arrays
-        const int64_t n0 = s.pend_n0, n = s.pend_n;
-        const T* src = reinterpret_cast<const T*>(s.h_out);
-        if (mu) { par_memcpy(mu + n0, src, (size_t)n * ES); src += n; }
-        if (var) { par_memcpy(var + n0, src, (size_t)n * ES); src += n; }
-        if (deriv) { par_memcpy(deriv + n0 * D, src, (size_t)n * D * ES); src += n * D; }
-        if (hess) { par_memcpy(hess + n0 * D * D, src, (size_t)n * D * D * ES); }
-        t_out += now() - t0;
-        return cudaSuccess;
-    };
-    auto stage_in = [&](Slot& s, int64_t n0, int64_t n) -> int {   // copy-in + enqueue of one chunk on the slot
-        T* const d_in = reinterpret_cast<T*>(s.d_in);
-        const Outs o = carve(s, n);
-        if (in_direct) {
-            CUDA_TRY(cudaMemcpyAsync(d_in, testing + n0 * D, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
-        } else {
-            double t0 = now();
-            par_memcpy(s.h_in, testing + n0 * D, (size_t)n * D * ES);
-            t_in += now() - t0;
-            CUDA_TRY(cudaMemcpyAsync(d_in, s.h_in, (size_t)n * D * ES, cudaMemcpyHostToDevice, s.st));
-        }
-        int rc = launch(d_in, n, o.mu, o.var, o.der, o.hes, s.st);
-        if (rc) return rc;
-        if (out_direct) {
-            rc = d2h_direct(s, o, n0, n);
-            if (rc) return rc;
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * per_out * ES, cudaMemcpyDeviceToHost, s.st));
-        }
-        CUDA_TRY(cudaEventRecord(s.done, s.st));
-        s.pend_n0 = n0; s.pend_n = n;
-        return GPE_OK;
-    };
-    const int64_t nchunks = (N + CH - 1) / CH;
-    int rc = GPE_OK;
-    static const bool no_zero_copy = getenv("GPE_NO_ZERO_COPY") != nullptr;   // dev aid: time the copy-based small path
-    static const int64_t zc_max = getenv("GPE_ZERO_COPY_MAX") ? atoll(getenv("GPE_ZERO_COPY_MAX")) : kZeroCopyMax;   // dev aid
-    if (N <= zc_max && !in_direct && !out_direct && !no_zero_copy) {
-        // Small calls (the reference is typically called with ONE point): the two cudaMemcpyAsync of the staged
-        // path cost more than the kernel.  The staging buffers are page-locked, hence mapped into the device's address
-        // space (UVA): the kernels read the test rows from and write the results to host memory directly -- one launch
-        // and one synchronisation instead of copy, launch, copy, synchronise.
-        Slot& s = m->slots[0];
-        double t0 = now();
-        memcpy(s.h_in, testing, (size_t)N * D * ES);
-        t_in += now() - t0;
-        T* o = reinterpret_cast<T*>(s.h_out);
-        T* const z_mu = mu ? o : nullptr;    if (mu) o += N;
-        T* const z_var = var ? o : nullptr;  if (var) o += N;
-        T* const z_der = deriv ? o : nullptr; if (deriv) o += N * D;
-        T* const z_hes = hess ? o : nullptr;
-        rc = launch(reinterpret_cast<T*>(s.h_in), N, z_mu, z_var, z_der, z_hes, s.st);
-        if (rc) return rc;
-        t0 = now();
-        CUDA_TRY(cudaStreamSynchronize(s.st));
-        t_wait += now() - t0; t0 = now();
-        if (mu) memcpy(mu, z_mu, (size_t)N * ES);
-        if (var) memcpy(var, z_var, (size_t)N * ES);
-        if (deriv) memcpy(deriv, z_der, (size_t)N * D * ES);
-        if (hess) memcpy(hess, z_hes, (size_t)N * D * D * ES);
-        t_out += now() - t0;
-    } else if (nchunks == 1) {
-        rc = stage_in(m->slots[0], 0, N);
-        if (rc) return rc;
-        CUDA_TRY(copy_out(m->slots[0]));
-    } else if (out_direct) {
-        // only the inputs are staged: no second thread, a slot is reused once its previous chunk has finished
-        for (int64_t c = 0; c < nchunks; ++c) {
-            Slot& s = m->slots[c % 3];
-            if (c >= 3) {
-                const double t0 = now();
-                CUDA_TRY(cudaEventSynchronize(s.done));
-                t_block += now() - t0;
-            }
-            const int64_t n0 = c * CH;
-            rc = stage_in(s, n0, std::min(CH, N - n0));
-            if (rc) { cudaDeviceSynchronize(); return rc; }
-        }
-        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(m->slots[i].st));
-    } else {
-        // chunk c lives in slot c % 3.  `staged` / `drained` count chunks handed to / finished by the output thread.
-        std::mutex mx;
-        std::condition_variable cv;
-        int64_t staged = 0, drained = 0;
-        bool abort = false;
-        cudaError_t out_err = cudaSuccess;
-        const int device = m->device;
-        std::thread out_thread([&] {
-            cudaSetDevice(device);
-            for (int64_t c = 0; c < nchunks; ++c) {
-                {
-                    std::unique_lock<std::mutex> lk(mx);
-                    cv.wait(lk, [&] { return staged > c || abort; });
-                    if (staged <= c) return;
-                }
-                const cudaError_t e = copy_out(m->slots[c % 3]);
-                std::lock_guard<std::mutex> lk(mx);
-                if (e != cudaSuccess) { out_err = e; abort = true; cv.notify_all(); return; }
-                drained = c + 1;
-                cv.notify_all();
-            }
+// Run fn(g) for g in [0, G) on one host thread per device and fold the statuses (worker error texts are thread-local:
+// carry them out).
+template <typename Fn>
+int run_per_device(int G, const int* devices, Fn fn) {
+    std::vector<int> rcs(G, GPE_OK);
+    std::vector<std::string> msgs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g)
+        th.emplace_back([&, g] {
+            bind_thread_near_device(devices[g]);
+            if (cudaSetDevice(devices[g]) != cudaSuccess) rcs[g] = fail(GPE_ERR_CUDA, "cudaSetDevice(%d) failed", devices[g]);
+            else rcs[g] = fn(g);
+            if (rcs[g]) msgs[g] = gpe_last_error();
         });
-        for (int64_t c = 0; c < nchunks && rc == GPE_OK; ++c) {
-            {
-                const double t0 = now();
-                std::unique_lock<std::mutex> lk(mx);
-                cv.wait(lk, [&] { return drained + 3 > c || abort; });   // the slot's previous chunk has left it
-                if (abort) break;
-                t_block += now() - t0;
-            }
-            const int64_t n0 = c * CH;
-            rc = stage_in(m->slots[c % 3], n0, std::min(CH, N - n0));
-            std::lock_guard<std::mutex> lk(mx);
-            if (rc == GPE_OK) staged = c + 1; else abort = true;
-            cv.notify_all();
-        }
-        out_thread.join();
-        if (rc) {                     // stage_in failed: the error text is already set on this thread
-            cudaDeviceSynchronize();
-            return rc;
-        }
-        if (out_err != cudaSuccess) return fail(GPE_ERR_CUDA, "result copy-out failed: %s", cudaGetErrorString(out_err));
-    }
-    if (pipe_trace)
-        fprintf(stderr, "[gpemu pipe] N=%lld in %lld chunks of %lld (in %s, out %s): out-thread wait %.3f ms, copy-out %.3f ms | "
-                        "copy-in %.3f ms, caller blocked on a slot %.3f ms\n",
-                (long long)N, (long long)nchunks, (long long)CH, in_direct ? "direct" : "staged",
-                out_direct ? "direct" : "staged", t_wait * 1e3, t_out * 1e3, t_in * 1e3, t_block * 1e3);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device %d: %s", devices[g], msgs[g].c_str());
     return GPE_OK;
 }
 
-// call_N: size of the user's call when this is one device's share of it (gpe_multi_predict), else N
-int predict_host(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
-                 double* hess, int64_t call_N = -1) {
+// Host-resident FP64 predict of one model: its share of a call of call_N points (the whole call unless `shared`
+// hands out the chunks of a multi-device call).  Caller holds m->host_mu.
+int model_stream(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                 const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
     const int64_t D = m->D;
-    if (call_N < 0) call_N = N;
-    return predict_host_t<double>(m, testing, N, mu, var, deriv, hess,
-                                  [&](double* d_in, int64_t n, double* a, double* b, double* c, double* h, cudaStream_t st) {
-                                      return predict_device(m, d_in, n, a, b, c, h, 1, 1, D, D * D, st, call_N);
-                                  });
+    IoList in, out;
+    in.add(testing, D);
+    const int i_mu = mu ? out.add(mu, 1) : -1, i_var = var ? out.add(var, 1) : -1, i_der = deriv ? out.add(deriv, D) : -1,
+              i_hes = hess ? out.add(hess, D * D) : -1;
+    StreamPlan pl = shared_plan ? *shared_plan : plan_stream(in.v, in.n, out.v, out.n, N, 8, 64 * (int64_t)m->sms, 1, true);
+    int rc = prepare_slots(m->slots, pl, in.v, in.n, out.v, out.n, 8);
+    if (rc) return rc;
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src = shared ? *shared : ChunkSource{&cursor, N, pl.CH};
+    const int64_t call_N = src.N;   // plan choices that change the summation order follow the size of the API call
+    return stream_host(m->slots, m->device, pl, src, 8, in.v, in.n, out.v, out.n,
+                       [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
+                           auto at = [&](int i) { return i >= 0 ? (double*)dout[i] : nullptr; };
+                           return predict_device(m, (const double*)di[0], n, at(i_mu), at(i_var), at(i_der), at(i_hes), 1, 1,
+                                                 D, D * D, st, call_N);
+                       });
 }
 
 // ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
@@ -822,7 +551,7 @@ constexpr int kProjPitch = 40;  // doubles; = 8 (mod 16) so a quarter-warp's 16-
 template <int KS>   // k-steps of 4: E <= 4 KS
 __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
                                                              int64_t lde, int64_t ldd, const double* __restrict__ b_tiled,
-                                                             int E, int W, int Wp, double* __restrict__ out) {
+                                                             int E, int W, int Wp, double* __restrict__ out, int accumulate) {
     extern __shared__ __align__(128) unsigned char psm[];
     uint64_t* full = reinterpret_cast<uint64_t*>(psm);          // [2]
     double* stage = reinterpret_cast<double*>(psm + 128);       // [2][KS][128][4]
@@ -897,7 +626,10 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
             if (w < W) {
 #pragma unroll 4
                 for (int rr = 0; rr < 16; ++rr)
-                    if (16 * half + rr < nrow) o[(int64_t)(16 * half + rr) * W] = ct[rr * kProjPitch + lane];
+                    if (16 * half + rr < nrow) {
+                        double* q = o + (int64_t)(16 * half + rr) * W;
+                        *q = accumulate ? *q + ct[rr * kProjPitch + lane] : ct[rr * kProjPitch + lane];   // (slices of E > 32)
+                    }
             }
         }
         __syncthreads();   // every warp is done with this stage: refill it with group g + 2
@@ -907,12 +639,12 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
 
 template <int KS>
 cudaError_t launch_project(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd,
-                           const double* b_tiled, int E, int W, int Wp, double* out, cudaStream_t st) {
+                           const double* b_tiled, int E, int W, int Wp, double* out, int accumulate, cudaStream_t st) {
     const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 8 * 16 * kProjPitch * 8;
     cudaError_t e = cudaFuncSetAttribute(k_project<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     if (e != cudaSuccess) return e;
     k_project<KS><<<(unsigned)((R + kProjRows - 1) / kProjRows), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd,
-                                                                                          b_tiled, E, W, Wp, out);
+                                                                                          b_tiled, E, W, Wp, out, accumulate);
     return cudaGetLastError();
 }
 
@@ -1175,6 +907,30 @@ int gpe_model_destroy(gpe_model* m) {
     return GPE_OK;
 }
 
+// Which kernel(s) a mean + variance + gradient call of N points runs on this model (bench.py reports it beside the
+// roofline instead of a hard-coded name).  Returns the number of characters written.
+int gpe_model_plan(gpe_model* m, int64_t N, char* buf, int len) {
+    if (!m || !buf || len <= 0) return 0;
+    auto full_name = [&](const FullPlan& f, char* out, int n) {
+        // template arguments as instantiated in predict_full_inst.cu: <MT, NT, WR, WC, DP, MINB, KB, FULLNT, SYM, HESS>
+        static const int MT[5] = {4, 4, 2, 4, 4}, WR[5] = {2, 1, 1, 1, 2}, WC[5] = {4, 8, 8, 4, 8}, MINB[5] = {1, 1, 1, 2, 1},
+                         KB[5] = {2, 1, 1, 1, 1};
+        const int nt_inst = f.cfg == 0 ? f.nt_act : (f.cfg == 1 ? (f.nt_act >= 5 && f.nt_act <= 7 ? f.nt_act : 8)
+                                                  : (f.cfg == 2 ? (f.nt_act >= 9 && f.nt_act <= 15 ? f.nt_act : 16) : (f.cfg == 3 ? 8 : 4)));
+        return snprintf(out, n, "k_predict_full<%d,%d,%d,%d,%d,%d,%d,%s,%s,false> (cfg %d: %d-point tiles, Mp=%d, %d-stage TMA ring, %u B smem)",
+                        MT[f.cfg], nt_inst, WR[f.cfg], WC[f.cfg], m->DP, MINB[f.cfg], KB[f.cfg], nt_inst == f.nt_act ? "true" : "false",
+                        m->symmetric ? "true" : "false", f.cfg, f.TN, f.Mp, f.nstage, f.smem);
+    };
+    if (m->full.valid) {
+        const bool small = m->full_small.valid && N <= 3 * 16 * (int64_t)m->sms;
+        return full_name(small ? m->full_small : m->full, buf, len);
+    }
+    if (m->large_valid)
+        return snprintf(buf, len, "k_predict_mean2<%d,true> + k_var_large (Mp=%d, %d k-blocks, %d-stage ring)", m->DP, m->large_Mp,
+                        m->large_kblk, m->large_nstage);
+    return snprintf(buf, len, "k_predict_mean2<%d,false> (no invQ: mean + gradient only)", m->DP);
+}
+
 int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
                 unsigned flags, void* stream) {
     NvtxRange nvtx_range("gpe_predict");
@@ -1194,7 +950,7 @@ int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, doub
     CUDA_TRY(cudaSetDevice(m->device));
     if (flags & GPE_HOST_PTRS) {
         std::lock_guard<std::mutex> lock(m->host_mu);
-        return predict_host(m, testing, N, mu, var, deriv, hess);
+        return model_stream(m, testing, N, mu, var, deriv, hess);
     }
     return predict_device(m, testing, N, mu, var, deriv, hess, 1, 1, m->D, (int64_t)m->D * m->D,
                           (cudaStream_t)stream);
@@ -1222,10 +978,19 @@ int gpe_predict_f32(gpe_model* m, const float* testing, int64_t N, float* mu, fl
     std::lock_guard<std::mutex> lock(m->host_mu);   // also covers the lazy packing of the FP32 operands
     if (!(flags & GPE_HOST_PTRS)) return predict_device_f32(m, testing, N, mu, var, deriv, fast, (cudaStream_t)stream);
     // host pointers: the same overlapped pipeline as the FP64 path
-    return predict_host_t<float>(m, testing, N, mu, var, deriv, (float*)nullptr,
-                                 [&](float* d_in, int64_t n, float* a, float* b, float* c, float*, cudaStream_t st) {
-                                     return predict_device_f32(m, d_in, n, a, b, c, fast, st);
-                                 });
+    const int64_t D = m->D;
+    IoList in, out;
+    in.add(testing, D);
+    const int i_mu = mu ? out.add(mu, 1) : -1, i_var = var ? out.add(var, 1) : -1, i_der = deriv ? out.add(deriv, D) : -1;
+    const StreamPlan pl = plan_stream(in.v, in.n, out.v, out.n, N, 4, 64 * (int64_t)m->sms, 1, true);
+    int rc = prepare_slots(m->slots, pl, in.v, in.n, out.v, out.n, 4);
+    if (rc) return rc;
+    std::atomic<int64_t> cursor{0};
+    return stream_host(m->slots, m->device, pl, ChunkSource{&cursor, N, pl.CH}, 4, in.v, in.n, out.v, out.n,
+                       [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
+                           auto at = [&](int i) { return i >= 0 ? (float*)dout[i] : nullptr; };
+                           return predict_device_f32(m, (const float*)di[0], n, at(i_mu), at(i_var), at(i_der), fast, st);
+                       });
 }
 
 int gpe_predict_wrap(const double* expX, const double* inputs, const double* invQt, const double* invQ,
@@ -1258,137 +1023,14 @@ int gpe_predict_wrap(const double* expX, const double* inputs, const double* inv
     return GPE_OK;
 }
 
-// ---- one call, G devices: host-resident test points are split into contiguous ranges, one host thread per
-// device drives that device's streaming pipeline (no steady-state exchange) ------------
-int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
-                     const double* invQt, const double* invQ, unsigned options, gpe_multi** out) {
-    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
-    gpe_multi* mm = new gpe_multi();
-    for (int i = 0; i < n_devices; ++i) {
-        gpe_model* m = nullptr;
-        int rc = gpe_model_create_ex(devices[i], M, D, inputs, expX, invQt, invQ, options, &m);
-        if (rc) { gpe_multi_destroy(mm); return rc; }
-        mm->models.push_back(m);
-    }
-    *out = mm;
-    return GPE_OK;
-}
+}  // extern "C"
 
-int gpe_multi_destroy(gpe_multi* mm) {
-    if (!mm) return GPE_OK;
-    for (gpe_model* m : mm->models) gpe_model_destroy(m);
-    delete mm;
-    return GPE_OK;
-}
+// ---- banks: E GPs sharing training inputs and test points -------------------------------------------------------
+namespace {
 
-int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
-                      double* hess, unsigned flags) {
-    if (!mm) return fail(GPE_ERR_INVALID, "handle is NULL");
-    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
-    if (N == 0) return GPE_OK;
-    const int G = (int)mm->models.size();
-    const int64_t D = mm->models[0]->D;
-    std::vector<int> rcs(G, GPE_OK);
-    std::vector<std::string> msgs(G);
-    std::vector<std::thread> th;
-    const int64_t base = N / G, rem = N % G;
-    for (int g = 0; g < G; ++g) {
-        const int64_t lo = g * base + std::min<int64_t>(g, rem), n = base + (g < rem ? 1 : 0);
-        if (n == 0) continue;
-        th.emplace_back([=, &rcs, &msgs] {
-            gpe_model* m = mm->models[g];
-            const bool w_mu = flags & GPE_WANT_MU, w_var = flags & GPE_WANT_VAR, w_der = flags & GPE_WANT_DERIV,
-                       w_hes = flags & GPE_WANT_HESS;
-            if ((w_mu && !mu) || (w_var && !var) || (w_der && !deriv) || (w_hes && !hess) ||
-                !(w_mu || w_var || w_der || w_hes) || !testing) {
-                rcs[g] = fail(GPE_ERR_INVALID, "output flag set with a NULL array, or nothing requested");
-            } else if (cudaSetDevice(m->device) != cudaSuccess) {
-                rcs[g] = fail(GPE_ERR_CUDA, "cudaSetDevice(%d) failed", m->device);
-            } else {
-                // the plan (tile size) follows the size of the whole call, so G devices reproduce one device bit for bit
-                std::lock_guard<std::mutex> lock(m->host_mu);
-                rcs[g] = predict_host(m, testing + lo * D, n, w_mu ? mu + lo : nullptr, w_var ? var + lo : nullptr,
-                                      w_der ? deriv + lo * D : nullptr, w_hes ? hess + lo * D * D : nullptr, N);
-            }
-            if (rcs[g]) msgs[g] = gpe_last_error();   // thread-local in the worker: carry it out
-        });
-    }
-    for (auto& t : th) t.join();
-    for (int g = 0; g < G; ++g)
-        if (rcs[g]) return fail(rcs[g], "device %d: %s", mm->models[g]->device, msgs[g].c_str());
-    return GPE_OK;
-}
-
-int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const double* expX, const double* invQt,
-                    const double* invQ, const double* basis, int W, gpe_bank** out) {
-    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    if (E < 1) return fail(GPE_ERR_INVALID, "E must be >= 1");
-    if (basis && W < 1) return fail(GPE_ERR_INVALID, "basis given but W < 1");
-    gpe_bank* b = new gpe_bank();
-    b->device = device; b->E = E; b->M = M; b->D = D; b->W = basis ? W : 0;
-    for (int e = 0; e < E; ++e) {
-        gpe_model* m = nullptr;
-        int rc = gpe_model_create(device, M, D, inputs, expX + (size_t)e * (D + 1), invQt + (size_t)e * M,
-                                  invQ ? invQ + (size_t)e * M * M : nullptr, &m);
-        if (rc) { gpe_bank_destroy(b); return rc; }
-        b->models.push_back(m);
-    }
-    {
-        std::vector<MeanBankEntry> ent(E);
-        for (int e2 = 0; e2 < E; ++e2) {
-            ent[e2].xchunks = b->models[e2]->d_xchunks_mean;
-            memcpy(ent[e2].sqrt_w, b->models[e2]->sqrt_w, sizeof(ent[e2].sqrt_w));
-        }
-        cudaError_t e = cudaMalloc((void**)&b->d_entries, sizeof(MeanBankEntry) * E);
-        if (e == cudaSuccess) e = cudaMemcpy(b->d_entries, ent.data(), sizeof(MeanBankEntry) * E, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "bank upload failed: %s", cudaGetErrorString(e)); }
-    }
-    if (basis) {
-        const int ks_e = (E + 3) / 4;
-        const int ks_n = ks_e <= 3 ? 3 : (ks_e <= 5 ? 5 : 8);   // the k-step count of the kernel instantiation used
-        b->Wp = (W + kProjCols - 1) / kProjCols * kProjCols;
-        std::vector<double> bt((size_t)ks_n * b->Wp * 4, 0.0);
-        for (int e2 = 0; e2 < E; ++e2)
-            for (int w = 0; w < W; ++w) bt[((size_t)(e2 >> 2) * b->Wp + w) * 4 + (e2 & 3)] = basis[(size_t)e2 * W + w];
-        cudaError_t e = cudaMalloc((void**)&b->d_basis, bt.size() * 8);
-        if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "basis upload failed: %s", cudaGetErrorString(e)); }
-    }
-    *out = b;
-    return GPE_OK;
-}
-
-int gpe_bank_destroy(gpe_bank* b) {
-    if (!b) return GPE_OK;
-    for (gpe_model* m : b->models) gpe_model_destroy(m);
-    if (b->d_basis) { cudaSetDevice(b->device); cudaFree(b->d_basis); }
-    if (b->d_entries) { cudaSetDevice(b->device); cudaFree(b->d_entries); }
-    if (b->fwd_h) cudaFreeHost(b->fwd_h);
-    if (b->fwd_d) { cudaSetDevice(b->device); cudaFree(b->fwd_d); }
-    if (b->fwd_st) cudaStreamDestroy(b->fwd_st);
-    if (b->cost_d) { cudaSetDevice(b->device); cudaFree(b->cost_d); }
-    if (b->cost_free) cudaEventDestroy(b->cost_free);
-    delete b;
-    return GPE_OK;
-}
-
-int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv,
-                     double* hess, unsigned flags, void* stream) {
-    NvtxRange nvtx_range("gpe_bank_predict");
-    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
-    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
-    if (N == 0) return GPE_OK;
-    if (flags & GPE_HOST_PTRS) return fail(GPE_ERR_UNSUPPORTED, "gpe_bank_predict takes device pointers");
-    if (!testing) return fail(GPE_ERR_INVALID, "testing is NULL");
-    if (!(flags & GPE_WANT_MU)) mu = nullptr;
-    if (!(flags & GPE_WANT_VAR)) var = nullptr;
-    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
-    if (!(flags & GPE_WANT_HESS)) hess = nullptr;
-    if (!mu && !var && !deriv && !hess) return fail(GPE_ERR_INVALID, "no output requested");
-    CUDA_TRY(cudaSetDevice(b->device));
+// Device-resident bank prediction on `st`; outputs point-major: mu (N, E), var (N, E), deriv (N, E, D), hess (N, E, D, D).
+int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                        cudaStream_t stream) {
     const int64_t E = b->E, D = b->D;
     const bool with_var = var != nullptr;
     if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient,
@@ -1397,7 +1039,7 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
         for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok;
         for (int64_t e = 0; e < E; ++e) {
             int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var + e, deriv ? deriv + e * D : nullptr,
-                                    fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, (cudaStream_t)stream);
+                                    fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream);
             if (rc) return rc;
         }
         if (fuse_hess) hess = nullptr;
@@ -1409,7 +1051,7 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
         if (fuse_hess) {
             for (int64_t e = 0; e < E; ++e) {
                 int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, nullptr, deriv ? deriv + e * D : nullptr,
-                                        hess + e * D * D, E, E, E * D, E * D * D, (cudaStream_t)stream);
+                                        hess + e * D * D, E, E, E * D, E * D * D, stream);
                 if (rc) return rc;
             }
             return GPE_OK;
@@ -1434,8 +1076,32 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
         const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
         const int gx = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)m0->sms * 8 / E));
         const size_t smem = do_hess ? m0->mean.smem_hess : m0->mean.smem;
-        CUDA_TRY(launch_mean(m0->DP, do_hess, p, dim3(gx, (unsigned)E), smem, (cudaStream_t)stream));
+        CUDA_TRY(launch_mean(m0->DP, do_hess, p, dim3(gx, (unsigned)E), smem, stream));
     }
+    return GPE_OK;
+}
+
+// fwd (N, W) = mu (N, E) . basis, deriv_full (N, D, W) = sum_e deriv[n, e, d] basis[e, w]; banks of more than 32
+// emulators run in slices of 32 that accumulate into the output (the reference has no limit on the number of PCs).
+int bank_project_device(gpe_bank* b, const double* mu, const double* deriv, int64_t N, double* fwd, double* deriv_full,
+                        cudaStream_t st) {
+    const int E = b->E, D = b->D, W = b->W;
+    auto run = [&](const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, double* o) -> cudaError_t {
+        for (int e0 = 0; e0 < E; e0 += 32) {
+            const int Es = std::min(32, E - e0), ks = (Es + 3) / 4, acc = e0 > 0;
+            const double* As = A + (int64_t)e0 * lde;
+            const double* bt = b->d_basis + (size_t)(e0 / 4) * b->Wp * 4;
+            g_launches.fetch_add(1);
+            cudaError_t e;
+            if (ks <= 3) e = launch_project<3>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
+            else if (ks <= 5) e = launch_project<5>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
+            else e = launch_project<8>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    if (fwd) CUDA_TRY(run(mu, N, 1, E, 1, 0, fwd));
+    if (deriv_full) CUDA_TRY(run(deriv, N * D, D, (int64_t)E * D, D, 1, deriv_full));
     return GPE_OK;
 }
 
@@ -1470,22 +1136,13 @@ __global__ void __launch_bounds__(128) k_bank_cost(const double* __restrict__ mu
     }
 }
 
-int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
-                  double* cost, double* grad, void* stream) {
-    NvtxRange nvtx_range("gpe_bank_cost");
-    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
-    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
-    if (N == 0) return GPE_OK;
-    if (!testing || !obs) return fail(GPE_ERR_INVALID, "testing / obs is NULL");
-    if (!cost && !grad) return fail(GPE_ERR_INVALID, "no output requested");
-    if (obs_ld != 0 && obs_ld < b->E) return fail(GPE_ERR_INVALID, "obs_ld must be 0 (one observation vector) or >= E");
-    CUDA_TRY(cudaSetDevice(b->device));
+int bank_cost_device(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
+                     double* cost, double* grad, cudaStream_t st) {
     const int64_t E = b->E, D = b->D;
     const int64_t per_point = E * (1 + (grad ? D : 0));
     // points per chunk: whole waves of 64-point tiles, scratch bounded by 256 MB
     int64_t chunk = std::max<int64_t>(64, (((int64_t)256 << 20) / (per_point * 8)) / 64 * 64);
     chunk = std::min(chunk, (N + 63) / 64 * 64);
-    cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lock(b->cost_mu);
     if (!b->cost_free) CUDA_TRY(cudaEventCreateWithFlags(&b->cost_free, cudaEventDisableTiming));
     // the scratch may still be read by a reduction enqueued on another stream
@@ -1501,11 +1158,10 @@ int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* o
     }
     double* d_mu = b->cost_d;
     double* d_der = grad ? b->cost_d + chunk * E : nullptr;
-    int sms = b->models[0]->sms;
+    const int sms = b->models[0]->sms;
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
         const int64_t n = std::min(chunk, N - n0);
-        int rc = gpe_bank_predict(b, testing + n0 * D, n, d_mu, nullptr, d_der, nullptr,
-                                  GPE_WANT_MU | (grad ? GPE_WANT_DERIV : 0u), stream);
+        int rc = bank_predict_device(b, testing + n0 * D, n, d_mu, nullptr, d_der, nullptr, st);
         if (rc) return rc;
         const int grid = (int)std::min<int64_t>((n + 3) / 4, (int64_t)sms * 16);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1518,87 +1174,386 @@ int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* o
     return GPE_OK;
 }
 
+// Host-resident bank call through the streaming pipeline: any of the point-major bank outputs plus the back-projected
+// spectra / Jacobians; the PC means / gradients a projection consumes stay on the device as chunk intermediates when
+// the caller did not ask for them.  Caller holds b->host_mu.
+int bank_stream(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                double* fwd, double* deriv_full, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
+    const int64_t E = b->E, D = b->D, W = b->W;
+    IoList in, out;
+    in.add(testing, D);
+    const int i_mu = (mu || fwd) ? out.add(mu, E) : -1;
+    const int i_var = var ? out.add(var, E) : -1;
+    const int i_der = (deriv || deriv_full) ? out.add(deriv, E * D) : -1;
+    const int i_hes = hess ? out.add(hess, E * D * D) : -1;
+    const int i_fwd = fwd ? out.add(fwd, W) : -1;
+    const int i_dfl = deriv_full ? out.add(deriv_full, D * W) : -1;
+    const int sms = b->models[0]->sms;
+    StreamPlan pl = shared_plan ? *shared_plan : plan_stream(in.v, in.n, out.v, out.n, N, 8, 64 * (int64_t)sms, 1, true);
+    int rc = prepare_slots(b->slots, pl, in.v, in.n, out.v, out.n, 8);
+    if (rc) return rc;
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src = shared ? *shared : ChunkSource{&cursor, N, pl.CH};
+    return stream_host(b->slots, b->device, pl, src, 8, in.v, in.n, out.v, out.n,
+                       [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
+                           auto at = [&](int i) { return i >= 0 ? (double*)dout[i] : nullptr; };
+                           int r = bank_predict_device(b, (const double*)di[0], n, at(i_mu), at(i_var), at(i_der), at(i_hes), st);
+                           if (r == GPE_OK && (i_fwd >= 0 || i_dfl >= 0))
+                               r = bank_project_device(b, at(i_mu), at(i_der), n, at(i_fwd), at(i_dfl), st);
+                           return r;
+                       });
+}
+
+// Host-resident gpe_bank_cost: test points (and per-point observations) stream in, cost / gradient stream out.
+int bank_cost_stream(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
+                     double* cost, double* grad, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
+    const int64_t E = b->E, D = b->D;
+    if (obs_ld != 0 && obs_ld != E) return fail(GPE_ERR_INVALID, "host observations must be contiguous: obs_ld = E or 0");
+    // the shared observation vector and the weights are small: one upload per call
+    const size_t aux_n = (size_t)(obs_ld == 0 ? E : 0) + (weights ? E : 0);
+    double *d_obs1 = nullptr, *d_w = nullptr;
+    if (aux_n > 0) {
+        int rc = ensure_buf((void**)&b->d_aux, &b->aux_cap, aux_n * 8, false);
+        if (rc) return rc;
+        double* p = b->d_aux;
+        if (obs_ld == 0) { CUDA_TRY(cudaMemcpy(p, obs, (size_t)E * 8, cudaMemcpyHostToDevice)); d_obs1 = p; p += E; }
+        if (weights) { CUDA_TRY(cudaMemcpy(p, weights, (size_t)E * 8, cudaMemcpyHostToDevice)); d_w = p; }
+    }
+    IoList in, out;
+    in.add(testing, D);
+    const int i_obs = obs_ld != 0 ? in.add(obs, E) : -1;
+    const int i_cost = cost ? out.add(cost, 1) : -1, i_grad = grad ? out.add(grad, D) : -1;
+    const int sms = b->models[0]->sms;
+    StreamPlan pl = shared_plan ? *shared_plan : plan_stream(in.v, in.n, out.v, out.n, N, 8, 64 * (int64_t)sms, 1, true);
+    int rc = prepare_slots(b->slots, pl, in.v, in.n, out.v, out.n, 8);
+    if (rc) return rc;
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src = shared ? *shared : ChunkSource{&cursor, N, pl.CH};
+    return stream_host(b->slots, b->device, pl, src, 8, in.v, in.n, out.v, out.n,
+                       [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
+                           return bank_cost_device(b, (const double*)di[0], n, i_obs >= 0 ? (const double*)di[i_obs] : d_obs1,
+                                                   i_obs >= 0 ? E : 0, d_w, i_cost >= 0 ? (double*)dout[i_cost] : nullptr,
+                                                   i_grad >= 0 ? (double*)dout[i_grad] : nullptr, st);
+                       });
+}
+
+int bank_check_outputs(gpe_bank* b, int64_t N, const double* testing, double*& mu, double*& var, double*& deriv, double*& hess,
+                       double*& fwd, double*& deriv_full, unsigned flags) {
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N > 0 && !testing) return fail(GPE_ERR_INVALID, "testing is NULL");
+    if (!(flags & GPE_WANT_MU)) mu = nullptr;
+    if (!(flags & GPE_WANT_VAR)) var = nullptr;
+    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
+    if (!(flags & GPE_WANT_HESS)) hess = nullptr;
+    if (!(flags & GPE_WANT_FWD)) fwd = nullptr;
+    if (!(flags & GPE_WANT_DERIV_FULL)) deriv_full = nullptr;
+    if (((flags & GPE_WANT_MU) && !mu) || ((flags & GPE_WANT_VAR) && !var) || ((flags & GPE_WANT_DERIV) && !deriv) ||
+        ((flags & GPE_WANT_HESS) && !hess) || ((flags & GPE_WANT_FWD) && !fwd) || ((flags & GPE_WANT_DERIV_FULL) && !deriv_full))
+        return fail(GPE_ERR_INVALID, "an output flag is set but its array is NULL");
+    if (!mu && !var && !deriv && !hess && !fwd && !deriv_full) return fail(GPE_ERR_INVALID, "no output requested");
+    if (var && !b->models[0]->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the bank was created without invQ");
+    if ((fwd || deriv_full) && !b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
+    return GPE_OK;
+}
+
+// Chunk plan of a call that G pipelines share.
+StreamPlan plan_shared(const IoList& in, const IoList& out, int64_t N, int sms, int G) {
+    return plan_stream(in.v, in.n, out.v, out.n, N, 8, 64 * (int64_t)sms, G, false);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const double* expX, const double* invQt,
+                    const double* invQ, const double* basis, int W, gpe_bank** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (E < 1) return fail(GPE_ERR_INVALID, "E must be >= 1");
+    if (basis && W < 1) return fail(GPE_ERR_INVALID, "basis given but W < 1");
+    gpe_bank* b = new gpe_bank();
+    b->device = device; b->E = E; b->M = M; b->D = D; b->W = basis ? W : 0;
+    for (int e = 0; e < E; ++e) {
+        gpe_model* m = nullptr;
+        int rc = gpe_model_create(device, M, D, inputs, expX + (size_t)e * (D + 1), invQt + (size_t)e * M,
+                                  invQ ? invQ + (size_t)e * M * M : nullptr, &m);
+        if (rc) { gpe_bank_destroy(b); return rc; }
+        b->models.push_back(m);
+    }
+    {
+        std::vector<MeanBankEntry> ent(E);
+        for (int e2 = 0; e2 < E; ++e2) {
+            ent[e2].xchunks = b->models[e2]->d_xchunks_mean;
+            memcpy(ent[e2].sqrt_w, b->models[e2]->sqrt_w, sizeof(ent[e2].sqrt_w));
+        }
+        cudaError_t e = cudaMalloc((void**)&b->d_entries, sizeof(MeanBankEntry) * E);
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_entries, ent.data(), sizeof(MeanBankEntry) * E, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "bank upload failed: %s", cudaGetErrorString(e)); }
+    }
+    if (basis) {
+        // k-steps of 4 emulators; the projection runs in slices of 32 emulators = 8 k-steps, and the instantiation used for
+        // a slice (3, 5 or 8 k-steps) may read up to 8 k-steps from the slice's start: size the image for whole slices
+        const int ks_alloc = (E + 31) / 32 * 8;
+        b->Wp = (W + kProjCols - 1) / kProjCols * kProjCols;
+        std::vector<double> bt((size_t)ks_alloc * b->Wp * 4, 0.0);
+        for (int e2 = 0; e2 < E; ++e2)
+            for (int w = 0; w < W; ++w) bt[((size_t)(e2 >> 2) * b->Wp + w) * 4 + (e2 & 3)] = basis[(size_t)e2 * W + w];
+        cudaError_t e = cudaMalloc((void**)&b->d_basis, bt.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_basis, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "basis upload failed: %s", cudaGetErrorString(e)); }
+    }
+    *out = b;
+    return GPE_OK;
+}
+
+int gpe_bank_destroy(gpe_bank* b) {
+    if (!b) return GPE_OK;
+    cudaSetDevice(b->device);
+    for (gpe_model* m : b->models) gpe_model_destroy(m);
+    for (auto& s : b->slots) free_slot(s);
+    if (b->d_basis) cudaFree(b->d_basis);
+    if (b->d_entries) cudaFree(b->d_entries);
+    if (b->d_aux) cudaFree(b->d_aux);
+    if (b->cost_d) cudaFree(b->cost_d);
+    if (b->cost_free) cudaEventDestroy(b->cost_free);
+    delete b;
+    return GPE_OK;
+}
+
+int gpe_bank_predict_ex(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                        double* fwd, double* deriv_full, unsigned flags, void* stream) {
+    NvtxRange nvtx_range("gpe_bank_predict");
+    int rc = bank_check_outputs(b, N, testing, mu, var, deriv, hess, fwd, deriv_full, flags);
+    if (rc) return rc;
+    if (N == 0) return GPE_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (flags & GPE_HOST_PTRS) {
+        std::lock_guard<std::mutex> lock(b->host_mu);
+        return bank_stream(b, testing, N, mu, var, deriv, hess, fwd, deriv_full);
+    }
+    // device pointers: a projection needs the PC means / gradients materialised by the caller
+    if (fwd && !mu) return fail(GPE_ERR_INVALID, "device-pointer projection: GPE_WANT_FWD needs GPE_WANT_MU (the PC means) too");
+    if (deriv_full && !deriv) return fail(GPE_ERR_INVALID, "device-pointer projection: GPE_WANT_DERIV_FULL needs GPE_WANT_DERIV too");
+    rc = bank_predict_device(b, testing, N, mu, var, deriv, hess, (cudaStream_t)stream);
+    if (rc == GPE_OK && (fwd || deriv_full)) rc = bank_project_device(b, mu, deriv, N, fwd, deriv_full, (cudaStream_t)stream);
+    return rc;
+}
+
+int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                     double* hess, unsigned flags, void* stream) {
+    return gpe_bank_predict_ex(b, testing, N, mu, var, deriv, hess, nullptr, nullptr,
+                               flags & ~(unsigned)(GPE_WANT_FWD | GPE_WANT_DERIV_FULL), stream);
+}
+
+int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
+                  double* cost, double* grad, void* stream) {
+    NvtxRange nvtx_range("gpe_bank_cost");
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing || !obs) return fail(GPE_ERR_INVALID, "testing / obs is NULL");
+    if (!cost && !grad) return fail(GPE_ERR_INVALID, "no output requested");
+    if (obs_ld != 0 && obs_ld < b->E) return fail(GPE_ERR_INVALID, "obs_ld must be 0 (one observation vector) or >= E");
+    CUDA_TRY(cudaSetDevice(b->device));
+    return bank_cost_device(b, testing, N, obs, obs_ld, weights, cost, grad, (cudaStream_t)stream);
+}
+
+int gpe_bank_cost_host(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
+                       const double* weights, double* cost, double* grad) {
+    NvtxRange nvtx_range("gpe_bank_cost_host");
+    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing || !obs) return fail(GPE_ERR_INVALID, "testing / obs is NULL");
+    if (!cost && !grad) return fail(GPE_ERR_INVALID, "no output requested");
+    CUDA_TRY(cudaSetDevice(b->device));
+    std::lock_guard<std::mutex> lock(b->host_mu);
+    return bank_cost_stream(b, testing, N, obs, obs_ld, weights, cost, grad);
+}
+
 int gpe_bank_project(gpe_bank* b, const double* mu, const double* deriv, int64_t N, double* fwd, double* deriv_full,
                      void* stream) {
     if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
     if (!b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
     if (N <= 0) return N == 0 ? GPE_OK : fail(GPE_ERR_INVALID, "N must be >= 0");
-    if (b->E > 32) return fail(GPE_ERR_UNSUPPORTED, "back-projection supports E <= 32 (got %d)", b->E);
+    if (fwd && !mu) return fail(GPE_ERR_INVALID, "fwd requested but mu is NULL");
+    if (deriv_full && !deriv) return fail(GPE_ERR_INVALID, "deriv_full requested but deriv is NULL");
     CUDA_TRY(cudaSetDevice(b->device));
-    const int E = b->E, D = b->D, W = b->W;
-    cudaStream_t st = (cudaStream_t)stream;
-    auto run = [&](const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, double* o) {
-        g_launches.fetch_add(1);
-        const int ks = (E + 3) / 4;
-        if (ks <= 3) return launch_project<3>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
-        if (ks <= 5) return launch_project<5>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
-        return launch_project<8>(A, R, RD, ldn, lde, ldd, b->d_basis, E, W, b->Wp, o, st);
-    };
-    if (fwd) {
-        if (!mu) return fail(GPE_ERR_INVALID, "fwd requested but mu is NULL");
-        CUDA_TRY(run(mu, N, 1, E, 1, 0, fwd));
-    }
-    if (deriv_full) {
-        if (!deriv) return fail(GPE_ERR_INVALID, "deriv_full requested but deriv is NULL");
-        CUDA_TRY(run(deriv, N * D, D, (int64_t)E * D, D, 1, deriv_full));
-    }
-    return GPE_OK;
+    return bank_project_device(b, mu, deriv, N, fwd, deriv_full, (cudaStream_t)stream);
 }
 
 int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd, double* deriv_full) {
     NvtxRange nvtx_range("gpe_bank_forward");
-    if (!b) return fail(GPE_ERR_INVALID, "bank is NULL");
-    if (!b->d_basis) return fail(GPE_ERR_INVALID, "bank was created without basis functions");
+    if (!fwd) return fail(GPE_ERR_INVALID, "testing / fwd is NULL");
+    return gpe_bank_predict_ex(b, testing, N, nullptr, nullptr, nullptr, nullptr, fwd, deriv_full,
+                               GPE_WANT_FWD | (deriv_full ? GPE_WANT_DERIV_FULL : 0u) | GPE_HOST_PTRS, nullptr);
+}
+
+// ---- one call, G devices ---------------------------------------------------------------------------------------
+// The model (or bank) is resident on every listed device.  A host-resident batch is cut into chunks that the devices'
+// pipelines -- one host thread each -- pull from one shared cursor (test points are
+// independent, no steady-state exchange), so a GPU behind a slower PCIe path takes fewer chunks instead of holding the
+// call back: on the 8-GPU boxes GPUs 0-3 sustain 8.0 GB/s per direction against 11.3 for GPUs 4-7 with all eight
+// active (profiles/r01_pcie_8ranks.txt).
+int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
+                     const double* invQt, const double* invQ, unsigned options, gpe_multi** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
+    gpe_multi* mm = new gpe_multi();
+    for (int i = 0; i < n_devices; ++i) {
+        gpe_model* m = nullptr;
+        int rc = gpe_model_create_ex(devices[i], M, D, inputs, expX, invQt, invQ, options, &m);
+        if (rc) { gpe_multi_destroy(mm); return rc; }
+        mm->models.push_back(m);
+        mm->devices.push_back(devices[i]);
+    }
+    *out = mm;
+    return GPE_OK;
+}
+
+int gpe_multi_bank_create(int n_devices, const int* devices, int E, int M, int D, const double* inputs, const double* expX,
+                          const double* invQt, const double* invQ, const double* basis, int W, gpe_multi** out) {
+    if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
+    gpe_multi* mm = new gpe_multi();
+    for (int i = 0; i < n_devices; ++i) {
+        gpe_bank* b = nullptr;
+        int rc = gpe_bank_create(devices[i], E, M, D, inputs, expX, invQt, invQ, basis, W, &b);
+        if (rc) { gpe_multi_destroy(mm); return rc; }
+        mm->banks.push_back(b);
+        mm->devices.push_back(devices[i]);
+    }
+    *out = mm;
+    return GPE_OK;
+}
+
+int gpe_multi_destroy(gpe_multi* mm) {
+    if (!mm) return GPE_OK;
+    for (gpe_model* m : mm->models) gpe_model_destroy(m);
+    for (gpe_bank* b : mm->banks) gpe_bank_destroy(b);
+    delete mm;
+    return GPE_OK;
+}
+
+int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                      double* hess, unsigned flags) {
+    NvtxRange nvtx_range("gpe_multi_predict");
+    if (!mm || mm->models.empty()) return fail(GPE_ERR_INVALID, "handle is NULL or not a single-GP handle");
     if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
     if (N == 0) return GPE_OK;
-    if (!testing || !fwd) return fail(GPE_ERR_INVALID, "testing / fwd is NULL");
-    std::lock_guard<std::mutex> lock(b->fwd_mu);
-    CUDA_TRY(cudaSetDevice(b->device));
-    if (!b->fwd_st) CUDA_TRY(cudaStreamCreateWithFlags(&b->fwd_st, cudaStreamNonBlocking));
-    const int64_t E = b->E, D = b->D, W = b->W;
-    // per point: testing D | mu E | deriv E*D stay on the device; fwd W [| deriv_full D*W] come back
-    const int64_t out_pp = W + (deriv_full ? D * W : 0);
-    const int64_t dev_pp = D + E + E * D + out_pp;
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)(64u << 20) / (8 * out_pp)));
-    int rc = ensure(&b->fwd_d, &b->fwd_d_cap, (size_t)chunk * dev_pp * 8, false);
-    if (rc) return rc;
-    rc = ensure(&b->fwd_h, &b->fwd_h_cap, (size_t)chunk * (D + out_pp) * 8, true);
-    if (rc) return rc;
-    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
-        const int64_t n = std::min(chunk, N - n0);
-        double* d_t = b->fwd_d;
-        double* d_mu = d_t + n * D;
-        double* d_der = d_mu + n * E;
-        double* d_out = d_der + n * E * D;          // fwd (n, W) | deriv_full (n, D, W)
-        double* h_t = b->fwd_h;
-        double* h_out = h_t + n * D;
-        par_memcpy(h_t, testing + n0 * D, (size_t)n * D * 8);
-        static const bool no_zero_copy = getenv("GPE_NO_ZERO_COPY") != nullptr;
-        if (n <= kZeroCopyMax && (size_t)n * out_pp * 8 <= ((size_t)1 << 20) && !no_zero_copy) {
-            // a few points (the reference's call is one): the kernels read the test rows from and write the spectra to
-            // the page-locked staging buffer itself (mapped, UVA) -- no copy calls around the two launches
-            d_t = h_t;
-            d_out = h_out;
-            rc = gpe_bank_predict(b, d_t, n, d_mu, nullptr, deriv_full ? d_der : nullptr, nullptr,
-                                  GPE_WANT_MU | (deriv_full ? GPE_WANT_DERIV : 0u), b->fwd_st);
-            if (rc) return rc;
-            rc = gpe_bank_project(b, d_mu, deriv_full ? d_der : nullptr, n, d_out, deriv_full ? d_out + n * W : nullptr, b->fwd_st);
-            if (rc) return rc;
-            CUDA_TRY(cudaStreamSynchronize(b->fwd_st));
-        } else {
-        CUDA_TRY(cudaMemcpyAsync(d_t, h_t, (size_t)n * D * 8, cudaMemcpyHostToDevice, b->fwd_st));
-        rc = gpe_bank_predict(b, d_t, n, d_mu, nullptr, deriv_full ? d_der : nullptr, nullptr,
-                              GPE_WANT_MU | (deriv_full ? GPE_WANT_DERIV : 0u), b->fwd_st);
+    if (!(flags & GPE_WANT_MU)) mu = nullptr;
+    if (!(flags & GPE_WANT_VAR)) var = nullptr;
+    if (!(flags & GPE_WANT_DERIV)) deriv = nullptr;
+    if (!(flags & GPE_WANT_HESS)) hess = nullptr;
+    if (((flags & GPE_WANT_MU) && !mu) || ((flags & GPE_WANT_VAR) && !var) || ((flags & GPE_WANT_DERIV) && !deriv) ||
+        ((flags & GPE_WANT_HESS) && !hess) || !(mu || var || deriv || hess) || !testing)
+        return fail(GPE_ERR_INVALID, "output flag set with a NULL array, or nothing requested");
+    const int G = (int)mm->models.size();
+    gpe_model* m0 = mm->models[0];
+    const int64_t D = m0->D;
+    IoList in, out;
+    in.add(testing, D);
+    if (mu) out.add(mu, 1);
+    if (var) out.add(var, 1);
+    if (deriv) out.add(deriv, D);
+    if (hess) out.add(hess, D * D);
+    const StreamPlan pl = plan_shared(in, out, N, m0->sms, G);
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src{&cursor, N, pl.CH};
+    // the kernel plan (tile size) follows the size of the whole call, so G devices reproduce one device bit for bit
+    return run_per_device(G, mm->devices.data(), [&](int g) {
+        gpe_model* m = mm->models[g];
+        std::lock_guard<std::mutex> lock(m->host_mu);
+        return model_stream(m, testing, N, mu, var, deriv, hess, &pl, &src);
+    });
+}
+
+int gpe_multi_predict_device(gpe_multi* mm, const double* const* testing, const int64_t* N, double* const* mu,
+                             double* const* var, double* const* deriv, double* const* hess, unsigned flags,
+                             void* const* streams) {
+    NvtxRange nvtx_range("gpe_multi_predict_device");
+    if (!mm || mm->models.empty()) return fail(GPE_ERR_INVALID, "handle is NULL or not a single-GP handle");
+    if (!testing || !N) return fail(GPE_ERR_INVALID, "testing / N is NULL");
+    const int G = (int)mm->models.size();
+    int64_t call_N = 0;
+    for (int g = 0; g < G; ++g) {
+        if (N[g] < 0) return fail(GPE_ERR_INVALID, "N[%d] must be >= 0", g);
+        call_N += N[g];
+    }
+    for (int g = 0; g < G; ++g) {
+        if (N[g] == 0) continue;
+        gpe_model* m = mm->models[g];
+        double* o_mu = (flags & GPE_WANT_MU) && mu ? mu[g] : nullptr;
+        double* o_var = (flags & GPE_WANT_VAR) && var ? var[g] : nullptr;
+        double* o_der = (flags & GPE_WANT_DERIV) && deriv ? deriv[g] : nullptr;
+        double* o_hes = (flags & GPE_WANT_HESS) && hess ? hess[g] : nullptr;
+        if (!testing[g]) return fail(GPE_ERR_INVALID, "testing[%d] is NULL", g);
+        if (((flags & GPE_WANT_MU) && !o_mu) || ((flags & GPE_WANT_VAR) && !o_var) || ((flags & GPE_WANT_DERIV) && !o_der) ||
+            ((flags & GPE_WANT_HESS) && !o_hes) || !(o_mu || o_var || o_der || o_hes))
+            return fail(GPE_ERR_INVALID, "device %d: output flag set with a NULL array, or nothing requested", mm->devices[g]);
+        CUDA_TRY(cudaSetDevice(m->device));
+        int rc = predict_device(m, testing[g], N[g], o_mu, o_var, o_der, o_hes, 1, 1, m->D, (int64_t)m->D * m->D,
+                                streams ? (cudaStream_t)streams[g] : nullptr, call_N);
         if (rc) return rc;
-        rc = gpe_bank_project(b, d_mu, deriv_full ? d_der : nullptr, n, d_out, deriv_full ? d_out + n * W : nullptr, b->fwd_st);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_out, d_out, (size_t)n * out_pp * 8, cudaMemcpyDeviceToHost, b->fwd_st));
-        CUDA_TRY(cudaStreamSynchronize(b->fwd_st));
-        }
-        par_memcpy(fwd + n0 * W, h_out, (size_t)n * W * 8);
-        if (deriv_full) par_memcpy(deriv_full + n0 * D * W, h_out + n * W, (size_t)n * D * W * 8);
     }
     return GPE_OK;
+}
+
+int gpe_multi_bank_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                           double* hess, double* fwd, double* deriv_full, unsigned flags) {
+    NvtxRange nvtx_range("gpe_multi_bank_predict");
+    if (!mm || mm->banks.empty()) return fail(GPE_ERR_INVALID, "handle is NULL or not a bank handle");
+    gpe_bank* b0 = mm->banks[0];
+    int rc = bank_check_outputs(b0, N, testing, mu, var, deriv, hess, fwd, deriv_full, flags);
+    if (rc) return rc;
+    if (N == 0) return GPE_OK;
+    const int G = (int)mm->banks.size();
+    const int64_t E = b0->E, D = b0->D, W = b0->W;
+    IoList in, out;   // same arrays, same order as bank_stream builds them: the plan only needs widths and pinned-ness
+    in.add(testing, D);
+    if (mu || fwd) out.add(mu, E);
+    if (var) out.add(var, E);
+    if (deriv || deriv_full) out.add(deriv, E * D);
+    if (hess) out.add(hess, E * D * D);
+    if (fwd) out.add(fwd, W);
+    if (deriv_full) out.add(deriv_full, D * W);
+    const StreamPlan pl = plan_shared(in, out, N, b0->models[0]->sms, G);
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src{&cursor, N, pl.CH};
+    return run_per_device(G, mm->devices.data(), [&](int g) {
+        gpe_bank* b = mm->banks[g];
+        std::lock_guard<std::mutex> lock(b->host_mu);
+        return bank_stream(b, testing, N, mu, var, deriv, hess, fwd, deriv_full, &pl, &src);
+    });
+}
+
+int gpe_multi_bank_cost(gpe_multi* mm, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
+                        const double* weights, double* cost, double* grad) {
+    NvtxRange nvtx_range("gpe_multi_bank_cost");
+    if (!mm || mm->banks.empty()) return fail(GPE_ERR_INVALID, "handle is NULL or not a bank handle");
+    if (N < 0) return fail(GPE_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return GPE_OK;
+    if (!testing || !obs) return fail(GPE_ERR_INVALID, "testing / obs is NULL");
+    if (!cost && !grad) return fail(GPE_ERR_INVALID, "no output requested");
+    gpe_bank* b0 = mm->banks[0];
+    const int G = (int)mm->banks.size();
+    const int64_t E = b0->E, D = b0->D;
+    IoList in, out;
+    in.add(testing, D);
+    if (obs_ld != 0) in.add(obs, E);
+    if (cost) out.add(cost, 1);
+    if (grad) out.add(grad, D);
+    const StreamPlan pl = plan_shared(in, out, N, b0->models[0]->sms, G);
+    std::atomic<int64_t> cursor{0};
+    ChunkSource src{&cursor, N, pl.CH};
+    return run_per_device(G, mm->devices.data(), [&](int g) {
+        gpe_bank* b = mm->banks[g];
+        std::lock_guard<std::mutex> lock(b->host_mu);
+        return bank_cost_stream(b, testing, N, obs, obs_ld, weights, cost, grad, &pl, &src);
+    });
 }
 
 }  // extern "C"

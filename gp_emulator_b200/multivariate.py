@@ -13,7 +13,7 @@ import shutil
 
 import numpy as np
 
-from .engine import DeviceBank
+from .engine import DeviceBank, resolve_devices
 from .gaussian_process import GaussianProcess
 
 
@@ -21,7 +21,8 @@ class MultivariateEmulator(object):
     def __init__(self, dump=None, X=None, y=None, hyperparams=None, thresh=0.98, n_tries=5, device=0,
                  batched_training=False, basis_functions=None, n_pcs=None):
         """See reference multivariate_gp.py:40-121.  ``X`` (N_train, N_full) model outputs, ``y``
-        (N_train, N_params) the parameters that produced them, ``hyperparams`` (N_params + 2, n_pcs)."""
+        (N_train, N_params) the parameters that produced them, ``hyperparams`` (N_params + 2, n_pcs).
+        ``device``: GPU index, list of indices or ``"all"`` (host batches are then spread over all of them per call)."""
         if basis_functions is not None and n_pcs is None:      # (EmulatorStorage hands a stored basis back in)
             n_pcs = basis_functions.shape[0]
         if dump is not None:
@@ -62,7 +63,7 @@ class MultivariateEmulator(object):
         self.basis_functions = basis_functions
         if hyperparams is not None:
             assert (y.shape[1] + 2 == hyperparams.shape[0]) and (self.n_pcs == hyperparams.shape[1])
-        self._bank = None
+        self._bank, self._bank_key = None, None
         self.train_emulators(X, y, hyperparams=hyperparams, n_tries=n_tries, batched=batched_training)
 
     def dump_emulator(self, fname):
@@ -97,7 +98,7 @@ class MultivariateEmulator(object):
             D = y.shape[1]
             # the same random draws, in the same order, as n_pcs sequential learn_hyperparameters calls
             starts = [(i, th) for i in range(self.n_pcs) for th in 5.0 * (np.random.rand(n_tries, D + 2) - 0.5)]
-            trainer = DeviceTrainer(np.atleast_2d(y), train_data, device=self.device)
+            trainer = DeviceTrainer(np.atleast_2d(y), train_data, device=resolve_devices(self.device)[0])
             try:
                 fits, self.training_stats = minimise_batched(trainer.evaluate, starts)
             finally:
@@ -116,19 +117,32 @@ class MultivariateEmulator(object):
                     self.hyperparams[:, i] = hyperparams[:, i]
                     gp._set_params(hyperparams[:, i])
         self.emulators = gps
-        self._bank = None
+        self.invalidate_device()
 
     def compress(self, X):
         """Project full-rank vectors onto the PC basis (reference multivariate_gp.py:191-193)."""
         return X.dot(self.basis_functions.T).T
 
     def _device_bank(self):
-        if self._bank is None:
+        """Device copy of the per-PC GPs and the basis, rebuilt when any emulator's state is rebound (each
+        ``GaussianProcess`` counts assignments to inputs / theta / invQ / invQt, so ``emulators[i]._set_params(...)``
+        is seen) or the basis is replaced.  In-place edits of an emulator's arrays need ``invalidate_device()``."""
+        key = (tuple((id(g), g._version) for g in self.emulators), id(self.basis_functions), self.n_pcs, str(self.device))
+        if self._bank is None or key != self._bank_key:
+            if self._bank is not None:
+                self._bank.close()
             gps = self.emulators
             self._bank = DeviceBank(np.atleast_2d(self.y_train), np.stack([g.theta for g in gps]),
                                     np.stack([g.invQt for g in gps]), np.stack([g.invQ for g in gps]),
                                     basis=self.basis_functions[: self.n_pcs], device=self.device)
+            self._bank_key = key
         return self._bank
+
+    def invalidate_device(self):
+        """Drop the device copy of the emulator bank (the next predict re-uploads it)."""
+        if self._bank is not None:
+            self._bank.close()
+        self._bank, self._bank_key = None, None
 
     def predict(self, y, do_deriv=True, is_gpu=True):
         """Reconstruct the full output (and its Jacobian) at parameter vector(s) ``y``.

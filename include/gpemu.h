@@ -39,6 +39,8 @@ typedef enum gpe_status {
 #define GPE_WANT_VAR    0x02u  /* needs invQ at model creation */
 #define GPE_WANT_DERIV  0x04u
 #define GPE_WANT_HESS   0x08u
+#define GPE_WANT_FWD    0x10u  /* banks with a basis: back-projected output fwd (N, W) */
+#define GPE_WANT_DERIV_FULL 0x20u /* banks with a basis: back-projected Jacobian deriv_full (N, D, W) */
 #define GPE_HOST_PTRS   0x100u /* testing/outputs are host pointers: the library streams them */
 #define GPE_F32_FAST_TF32 0x200u /* gpe_predict_f32 only: one TF32 pass for the variance instead of the 3xTF32 split */
 #define GPE_F32_FORCE_3X  0x400u /* gpe_predict_f32 only: 3xTF32 split also for M > 256 (default there: one pass) */
@@ -89,6 +91,10 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
 int gpe_predict(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                 double* hess, unsigned flags, void* stream);
 
+/* Diagnostic: name and tile plan of the kernel(s) a mean + variance + gradient call of N points runs on this model,
+ * written to buf (NUL-terminated, at most len bytes); returns the length.  bench.py reports it beside the roofline. */
+int gpe_model_plan(gpe_model* m, int64_t N, char* buf, int len);
+
 /* Single-precision variant on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in TMEM):
  * what the reference's FP32 build of gpuPredict computes (`real` = float, gp_emulator/gpu/gpu_predict.h:20-34;
  * Python side precision=np.float32, gp_emulator/GaussianProcess.py:289-316).  Same handle, float32 I/O
@@ -112,15 +118,24 @@ int gpe_predict_wrap(const double* expX, const double* inputs, const double* inv
                      const double* testing, double* result, double* error, double* deriv,
                      int Npredict, int Ntrain, int Ninputs, int theta_size);
 
-/* One call, several devices: the GP is uploaded to every listed device and a host-resident batch is split into
- * contiguous row ranges, one per device, each streamed by its own host thread (test points are independent:
+/* One call, several devices: the GP is uploaded to every listed device and a host-resident batch is cut into chunks
+ * that the devices' pipelines -- one host thread each inside the library -- pull from one shared cursor, so a GPU
+ * behind a slower PCIe path takes fewer chunks instead of holding the call back (test points are independent:
  * gp_emulator/GaussianProcess.py:228-249; the reference has no multi-device code, doc/report.md:48,95 lists it as
- * future work).  Host pointers only; results are bit-identical to the single-device call. */
+ * future work).  Results are bit-identical to the single-device call.  This is what the drop-in classes run on with
+ * `device="all"`: the reference API has no notion of ranks (gp_emulator/GaussianProcess.py:327), so the fan-out lives
+ * below it. */
 typedef struct gpe_multi gpe_multi;
 int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
                      const double* invQt, const double* invQ, unsigned options, gpe_multi** out);
+/* host pointers */
 int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                       double* hess, unsigned flags);
+/* device pointers: arrays of n_devices entries, testing[g] (N[g], D) etc. resident on device g of the handle;
+ * asynchronous on streams[g] (streams == NULL: the legacy default stream of each device).  N[g] may be 0. */
+int gpe_multi_predict_device(gpe_multi* mm, const double* const* testing, const int64_t* N, double* const* mu,
+                             double* const* var, double* const* deriv, double* const* hess, unsigned flags,
+                             void* const* streams);
 int gpe_multi_destroy(gpe_multi* mm);
 
 /* Bank of E GPs that share the training inputs (M, D) and the test points, each with its own
@@ -139,6 +154,15 @@ int gpe_bank_destroy(gpe_bank* b);
 int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var,
                      double* deriv, double* hess, unsigned flags, void* stream);
 
+/* Same, plus the back-projected outputs in the same call: fwd (N, W) with GPE_WANT_FWD, deriv_full (N, D, W) with
+ * GPE_WANT_DERIV_FULL (gp_emulator/multivariate_gp.py:216,218).  With GPE_HOST_PTRS every array is a host array and
+ * the library streams chunks through its pinned pipeline -- the chunk walk of GaussianProcess.gpu_predict
+ * (gp_emulator/GaussianProcess.py:297-321) below the C ABI, for banks; the PC means / gradients a projection consumes
+ * stay on the device unless they are requested too.  With device pointers a projection needs GPE_WANT_MU (and
+ * GPE_WANT_DERIV for the Jacobian) as well.  Banks of more than 32 emulators project in slices of 32. */
+int gpe_bank_predict_ex(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                        double* hess, double* fwd, double* deriv_full, unsigned flags, void* stream);
+
 /* Least-squares cost of the bank's means against observations and its input gradient, reduced over the E emulators
  * on the fly so the (N, E) means and (N, E, D) gradients never leave the device (they exist for one chunk at a time):
  *   cost_n = 1/2 sum_e w_e (mu_ne - obs_ne)^2        grad_nd = sum_e w_e (mu_ne - obs_ne) deriv_ned
@@ -149,6 +173,20 @@ int gpe_bank_predict(gpe_bank* b, const double* testing, int64_t N, double* mu, 
  *   cost (N) or NULL; grad (N, D) or NULL.  Device pointers, asynchronous on `stream`. */
 int gpe_bank_cost(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
                   const double* weights, double* cost, double* grad, void* stream);
+/* The same reduction for host arrays (obs_ld = E or 0), streamed in chunks; synchronous. */
+int gpe_bank_cost_host(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
+                       const double* weights, double* cost, double* grad);
+
+/* Banks on several devices, host arrays, one call: the bank counterpart of gpe_multi_create / gpe_multi_predict
+ * (same handle type; destroy with gpe_multi_destroy).  Arguments as gpe_bank_create / gpe_bank_predict_ex /
+ * gpe_bank_cost_host. */
+int gpe_multi_bank_create(int n_devices, const int* devices, int E, int M, int D, const double* inputs,
+                          const double* expX, const double* invQt, const double* invQ, const double* basis, int W,
+                          gpe_multi** out);
+int gpe_multi_bank_predict(gpe_multi* mm, const double* testing, int64_t N, double* mu, double* var, double* deriv,
+                           double* hess, double* fwd, double* deriv_full, unsigned flags);
+int gpe_multi_bank_cost(gpe_multi* mm, const double* testing, int64_t N, const double* obs, int64_t obs_ld,
+                        const double* weights, double* cost, double* grad);
 
 /* PCA back-projection of bank means: fwd (N, W) = mu (N, E) @ basis (E, W)
  * (the accumulation `fwd += pred_mu * basis_functions[i]`, gp_emulator/multivariate_gp.py:216, batched

@@ -16,6 +16,9 @@ goldens is therefore the reference's own numpy/scipy code:
   MultivariateEmulator (dump=...) .predict gp_emulator/multivariate_gp.py:40-121, 195-222
   GaussianProcess.loglikelihood / partial_devs  gp_emulator/GaussianProcess.py:78-125
   lhd                                     gp_emulator/lhd.py:11-269
+  GaussianProcess.get_gpu_block           gp_emulator/GaussianProcess.py:253-270
+  per-band bank pattern (E x predict + hessian on shared inputs)   tests/test_perband_emulator.py:22-47
+  MultivariateEmulator(X=, y=, hyperparams=) with 20 PCs x 2101 wavelengths (BASELINE config 4)
 
     python tests/golden/make_golden.py [--only S1500]
 """
@@ -40,6 +43,11 @@ def py2to3(src):
     src = re.sub(r"^(\s*)print (.*?),?\s*$", r"\1print(\2)", src, flags=re.M)
     src = re.sub(r"raise ValueError, (\".*?\")", r"raise ValueError(\1)", src)
     src = src.replace("from GaussianProcess import GaussianProcess", "")
+    # py2 `range` is a list the reference assigns into (get_gpu_block, GaussianProcess.py:259,266)
+    src = re.sub(r"^(\s*\w+ = )range\((.*)\)\s*$", r"\1list(range(\2))", src, flags=re.M)
+    # numpy of the reference's era let a boolean mask be shorter than the axis it indexes (multivariate_gp.py:159:
+    # 250 singular values against the 2101 rows of the full V); current numpy raises, so make the truncation explicit
+    src = src.replace("V [ pcnt_var_explained <= thresh ]", "V [ :s.size ][ pcnt_var_explained <= thresh ]")
     return src
 
 
@@ -117,6 +125,65 @@ def main():
         np.random.seed(9); out["space"] = lhd_mod.lhd(dist=(d0, d1, d2, d3), size=12, form="spacefilling", iterations=7)
         np.savez_compressed(os.path.join(HERE, "golden_U.npz"), **out)
         print("U   single", out["single"].ravel())
+    # ---- B: block boundaries of the reference's host chunker (GaussianProcess.get_gpu_block, :253-270) --------------
+    if not only or only == "B":
+        gp = RefGP(np.zeros((3, 2)), [])
+        cases = [(10, 4), (12345, 1000), (100000, 200000), (900000, 100000), (200001, 200000), (7, 7), (8, 7), (1, 5)]
+        out = {"cases": np.array(cases)}
+        for i, (size, block) in enumerate(cases):
+            a, b = gp.get_gpu_block(size, block)
+            out["start_%d" % i] = np.asarray(a, dtype=np.int64); out["end_%d" % i] = np.asarray(b, dtype=np.int64)
+        np.savez_compressed(os.path.join(HERE, "golden_B.npz"), **out)
+        print("B   ", [(out["start_0"].tolist(), out["end_0"].tolist())])
+    # ---- K: per-band bank -- E GaussianProcess objects on the same inputs, own theta / targets, each predicted and
+    # differentiated twice separately (the loop of tests/test_perband_emulator.py:22-47) -------------------------------
+    if not only or only == "K":
+        rs = np.random.RandomState(31)
+        M, D, E, N = 60, 4, 5, 40
+        inputs = rs.random_sample((M, D)); testing = rs.random_sample((N, D))
+        thetas = rs.random_sample((E, D + 2)) - 0.5
+        targets = np.sin(inputs.sum(axis=1))[None, :] * (1.0 + rs.random_sample((E, 1))) + 0.1 * rs.standard_normal((E, M))
+        mu = np.empty((N, E)); var = np.empty((N, E)); deriv = np.empty((N, E, D)); hess = np.empty((N, E, D, D))
+        invQ = np.empty((E, M, M)); invQt = np.empty((E, M))
+        for e in range(E):
+            gp = RefGP(inputs, targets[e])
+            gp._set_params(np.r_[thetas[e, :D + 1], -4.0])
+            invQ[e], invQt[e] = gp.invQ, gp.invQt
+            mu[:, e], var[:, e], deriv[:, e, :] = gp.predict(testing)
+            hess[:, e] = gp.hessian(testing)
+        thetas[:, D + 1] = -4.0
+        np.savez_compressed(os.path.join(HERE, "golden_K.npz"), inputs=inputs, testing=testing, thetas=thetas, invQ=invQ,
+                            invQt=invQt, mu=mu, var=var, deriv=deriv, hess=hess)
+        print("K    mu[0]", mu[0])
+    # ---- M20: BASELINE config 4 -- MultivariateEmulator with 2101 wavelengths compressed to 20 PCs, built by the
+    # reference's own constructor (SVD + per-PC _set_params), single-point predicts (all the reference supports) ------
+    if not only or only == "M20":
+        rs = np.random.RandomState(41)
+        M, D, W = 250, 10, 2101
+        y = rs.random_sample((M, D))
+        lam = np.linspace(0.0, 1.0, W)
+        # smooth synthetic spectra: a few dozen parameter-dependent bumps, so the singular values decay slowly enough
+        X = np.zeros((M, W))
+        for k in range(40):
+            a = rs.standard_normal(D)
+            X += np.cos(y @ a + k)[:, None] * np.exp(-0.5 * ((lam - rs.random_sample()) / (0.02 + 0.1 * rs.random_sample())) ** 2)[None, :]
+        s = np.linalg.svd(X, compute_uv=False)
+        frac = s.cumsum() / s.sum()
+        thresh = 0.5 * (frac[19] + frac[20])                      # exactly 20 components pass `<= thresh`
+        hyper = np.tile(np.r_[[-0.5] * D, 0.0, -6.0][:, None], (1, 20)) + 0.3 * rs.standard_normal((D + 2, 20))
+        hyper[D + 1] = -6.0
+        mv = RefMV(X=X, y=y, hyperparams=hyper, thresh=thresh)
+        assert mv.n_pcs == 20, mv.n_pcs
+        pts = np.vstack([y[3], rs.random_sample((3, D))])
+        wsub = np.arange(0, W, 5)
+        fwd = np.empty((4, W)); dsub = np.empty((4, D, wsub.size))
+        for k in range(4):
+            f, d = mv.predict(pts[k])
+            fwd[k] = f; dsub[k] = np.asarray(d)[:, wsub]
+        np.savez_compressed(os.path.join(HERE, "golden_M20.npz"), y=y, hyperparams=hyper, thresh=thresh,
+                            basis_functions=mv.basis_functions, n_pcs=20, train_data=mv.compress(X),
+                            invQt=np.stack([g.invQt for g in mv.emulators]), points=pts, fwd=fwd, wsub=wsub, deriv_sub=dsub)
+        print("M20  n_pcs", mv.n_pcs, "fwd[0,:3]", fwd[0, :3])
     if only and only not in ("T", "P"):
         return
     # ---- T: genuinely conditioned model through the reference's own _set_params ---------------------

@@ -157,9 +157,11 @@ def test_pageable_and_pinned_host_paths_multi_chunk(gpemu):
     assert orc.ref_err(a["deriv"][idx], deriv) < TOL
 
 
-def test_bank_host_batches_are_chunked(gpemu):
-    """numpy callers of a bank get their batch walked in device-memory-bounded chunks (fwd / deriv_full are W and
-    D*W doubles per point): same values as the one-shot call, every output key, ragged last chunk."""
+def test_bank_host_batches_are_chunked(gpemu, monkeypatch):
+    """numpy callers of a bank get their batch walked in chunks BELOW the C ABI (gpe_bank_predict_ex with host pointers:
+    H2D / kernels / D2H overlapped, chunk size bounded by the width of the outputs): same values as the device-pointer
+    call, every output key, ragged last chunk, pageable and page-locked result arrays."""
+    import torch
     rs = np.random.RandomState(12)
     M, D, E, W, N = 60, 4, 5, 300, 1037
     inputs = rs.random_sample((M, D))
@@ -168,14 +170,23 @@ def test_bank_host_batches_are_chunked(gpemu):
     bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
     t = rs.random_sample((N, D))
     kw = dict(want_var=True, want_deriv=True, want_hess=True, project=True, project_deriv=True)
-    ref = bank.predict(t, **kw)
-    bank.host_chunk_bytes = 8 * 100 * (E * (2 + D + D * D) + W + D * W)     # 100 points per chunk
-    got = bank.predict(t, **kw)
-    assert set(got) == set(ref)
+    ref = {k: v.cpu().numpy() for k, v in bank.predict(torch.from_numpy(t).cuda(), **kw).items()}
+    one = bank.predict(t, **kw)                                            # one chunk
+    monkeypatch.setenv("GPE_SLOT_OUT_BYTES", str(8 * 100 * (E * (2 + D + D * D) + W + D * W)))   # 100 points per chunk
+    got = bank.predict(t, **kw)                                            # 11 chunks, staged (pageable) path
+    pin = bank.predict(torch.from_numpy(t).pin_memory().numpy(), pinned=True, **kw)   # 11 chunks, direct DMA path
+    assert set(got) == set(ref) == set(one) == set(pin)
     for k in ref:
-        assert got[k].shape == ref[k].shape and np.array_equal(got[k], ref[k]), k
-    fwd = bank.predict(t, want_var=False, want_deriv=False, project=True)["fwd"]
-    assert np.array_equal(fwd, ref["fwd"])
+        for name, r in (("one", one), ("chunked", got), ("pinned", pin)):
+            assert r[k].shape == ref[k].shape and np.array_equal(r[k], ref[k]), (name, k)
+    fwd = bank.predict(t, want_var=False, want_deriv=False, want_mu=False, project=True)
+    assert set(fwd) == {"fwd"} and np.array_equal(fwd["fwd"], ref["fwd"])  # PC means stay on the device
+    f2, d2 = bank.forward(t)
+    assert np.array_equal(f2, ref["fwd"]) and np.array_equal(d2, ref["deriv_full"])
+    monkeypatch.delenv("GPE_SLOT_OUT_BYTES")
+    models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
+    mu_o, var_o, grad_o, hess_o = orc.bank_predict(models, t[:200], do_hess=True)
+    assert orc.ref_err(got["mu"][:200], mu_o) < TOL and orc.ref_err(got["hess"][:200], hess_o) < TOL
 
 
 @pytest.mark.parametrize("M,D,E,N", [(60, 4, 5, 1037), (250, 10, 64, 3000), (33, 1, 1, 7), (40, 32, 3, 129)])
@@ -732,16 +743,65 @@ def test_fused_hessian_offset_inputs(gpemu):
     assert orc.ref_err(out["hess"], orc.hessian(inputs, theta, invQt, testing)) < 1e-10
 
 
-def test_inplace_edit_needs_invalidate(gpemu):
-    inputs, theta, invQ, invQt, testing = orc.make_S_model(64, 4, 50, seed=2)
-    gp = gpemu.GaussianProcess(inputs, [])
+def test_inplace_edits_are_seen_without_invalidate(gpemu):
+    """The reference re-reads inputs / theta / invQ / invQt on every predict (GaussianProcess.py:228-240).  Here the
+    device copy is checked bitwise against the arrays (one memcmp) whenever that is cheap next to the call -- always at
+    M = 250, and for >= 1000 points at any M -- so an in-place edit of ONE entry gives the new result with no hook."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 10_000, seed=2)
+    gp = gpemu.GaussianProcess(inputs.copy(), [])
     gp.theta, gp.invQ, gp.invQt = theta, invQ.copy(), invQt
     _, v0, _ = gp.predict(testing)
-    gp.invQ[1, 2] += 0.5                                  # in-place edit of one entry
-    gp.invalidate_device()
+    gp.invQ[101, 7] += 0.5                                # one entry, in place, not on the sampled grid
     _, v1, _ = gp.predict(testing)
     _, var, _ = orc.predict(inputs, theta, gp.invQ, invQt, testing)
     assert orc.ref_err(v1, var) < TOL and not np.array_equal(v0, v1)
+    gp.inputs[17, 3] += 0.25                              # the other matrix; a one-point call this time
+    m1, v2, d1 = gp.predict(testing[:1])
+    mu, var, der = orc.predict(gp.inputs, theta, gp.invQ, invQt, testing[:1])
+    assert orc.ref_err(m1, mu) < TOL and orc.ref_err(v2, var) < TOL and orc.ref_err(d1, der) < TOL
+    # a large model: tiny calls use the sampled fingerprint (documented), calls of >= 1000 points the full comparison
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(600, 4, 1200, seed=3)
+    gp = gpemu.GaussianProcess(inputs, [])
+    gp.theta, gp.invQ, gp.invQt = theta, invQ.copy(), invQt
+    gp.predict(testing[:5])
+    gp.invQ[301, 11] -= 0.75
+    _, v3, _ = gp.predict(testing)
+    assert orc.ref_err(v3, orc.predict(inputs, theta, gp.invQ, invQt, testing)[1]) < TOL
+    gp.cache_check = "full"
+    gp.invQ[5, 501] += 0.3
+    _, v4, _ = gp.predict(testing[:3])
+    assert orc.ref_err(v4, orc.predict(inputs, theta, gp.invQ, invQt, testing[:3])[1]) < TOL
+    gp.invalidate_device()
+    assert gp._dev_model is None
+
+
+def test_closed_handles_raise(gpemu):
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(20, 3, 10, seed=4)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    m.predict(testing)
+    m.close()
+    with pytest.raises(gpemu.GpemuError):
+        m.predict(testing)
+    b = gpemu.DeviceBank(inputs, theta[None, :], invQt[None, :], invQ[None, :, :])
+    b.close()
+    with pytest.raises(gpemu.GpemuError):
+        b.predict(testing)
+
+
+def test_reference_method_aliases(gpemu):
+    """cpu_predict / gpu_predict / get_gpu_block exist under the reference's names (GaussianProcess.py:211, 253, 273)."""
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(64, 4, 50, seed=2)
+    gp = gpemu.GaussianProcess(inputs, [])
+    gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    a = gp.cpu_predict(testing)
+    assert len(a) == 3 and orc.ref_err(a[0], mu) < TOL and orc.ref_err(a[1], var) < TOL and orc.ref_err(a[2], deriv) < TOL
+    b = gp.cpu_predict(testing, do_unc=False)
+    assert len(b) == 2 and orc.ref_err(b[0], mu) < TOL and orc.ref_err(b[1], deriv) < TOL    # (mean-only kernel)
+    c = gp.gpu_predict(testing)
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))
+    s, e = gp.get_gpu_block(10, 4)
+    assert list(s) == [0, 4, 7] and list(e) == [4, 7, 10]
 
 
 def test_one_call_multi_device_fanout(lib, gpemu):
@@ -800,3 +860,314 @@ def test_single_precision_host_streaming_multi_chunk(gpemu):
     torch.cuda.synchronize()
     for k in ("mu", "var", "deriv"):
         assert np.array_equal(a[k], b[k].cpu().numpy()), k
+
+
+# ---- round 2: BASELINE configs 4 and 5 under pytest, banks through the host pipeline, one call / all GPUs, guards ----
+@pytest.mark.parametrize("M,D,E,N", [(250, 10, 64, 150), (37, 3, 5, 131), (60, 13, 3, 70)])
+def test_bank_hessian_against_oracle(gpemu, M, D, E, N):
+    """BASELINE config 5: a per-band bank (E GPs, shared inputs and test points) with mean, variance, gradient AND
+    Hessian against E separate oracle predict + hessian calls -- the reference pattern of
+    tests/test_perband_emulator.py:22-37 + GaussianProcess.hessian (:345-366); point-major strided outputs
+    (ld_hess = E*D*D), device and host callers."""
+    import torch
+    rs = np.random.RandomState(100 + E)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+    t = rs.random_sample((N, D))
+    models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
+    mu_o, var_o, grad_o, hess_o = orc.bank_predict(models, t, do_hess=True)
+    host = bank.predict(t, want_var=True, want_deriv=True, want_hess=True)
+    dev = bank.predict(torch.from_numpy(t).cuda(), want_var=True, want_deriv=True, want_hess=True)
+    for name, got in (("host", host), ("device", {k: v.cpu().numpy() for k, v in dev.items()})):
+        assert got["hess"].shape == (N, E, D, D) and got["deriv"].shape == (N, E, D)
+        assert orc.ref_err(got["mu"], mu_o) < TOL, name
+        assert orc.ref_err(got["var"], var_o) < TOL, name
+        assert orc.ref_err(got["deriv"], grad_o) < TOL, name
+        assert orc.ref_err(got["hess"], hess_o) < TOL, name
+    # Hessian without the variance (one launch for all emulators, or per-emulator fused launches on big batches)
+    h_only = bank.predict(t, want_var=False, want_deriv=False, want_hess=True)
+    assert orc.ref_err(h_only["hess"], hess_o) < TOL and orc.ref_err(h_only["mu"], mu_o) < TOL
+
+
+def test_golden_perband_bank_with_hessian(gpemu):
+    """The same pattern against outputs frozen from the reference itself (golden_K: trained per-band GPs)."""
+    g = golden("K")
+    bank = gpemu.DeviceBank(g["inputs"], g["thetas"], g["invQt"], g["invQ"])
+    got = bank.predict(g["testing"], want_var=True, want_deriv=True, want_hess=True)
+    assert orc.ref_err(got["mu"], g["mu"]) < TOL and orc.ref_err(got["deriv"], g["deriv"]) < TOL
+    assert orc.ref_err(got["hess"], g["hess"]) < TOL
+    for e in range(g["thetas"].shape[0]):
+        assert orc.var_cond_err(got["var"][:, e], g["var"][:, e], g["inputs"], g["thetas"][e], g["invQ"][e], g["testing"]) < TOL
+
+
+def test_cfg4_20_components_2101_wavelengths(gpemu):
+    """BASELINE config 4: P = 20 PCs, W = 2101 wavelengths, synthetic orthonormal basis; PC-space outputs, spectra and
+    full Jacobians against the oracle's batched MultivariateEmulator.predict (multivariate_gp.py:195-222), host and
+    device callers."""
+    import torch
+    M, D, P, W, N = 250, 10, 20, 2101, 96
+    rs = np.random.RandomState(4)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((P, D + 2)); invQts = rs.random_sample((P, M)); invQs = rs.random_sample((P, M, M))
+    basis = np.linalg.qr(rs.standard_normal((W, P)))[0].T.copy()
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
+    tt = rs.random_sample((N, D))
+    models = [(inputs, thetas[i], invQs[i], invQts[i]) for i in range(P)]
+    fwd, mu_o, var_o, grad_o, dfull = orc.mv_predict_batch(models, basis, tt, want_deriv_full=True)
+    kw = dict(want_var=True, want_deriv=True, project=True, project_deriv=True)
+    host = bank.predict(tt, **kw)
+    dev = {k: v.cpu().numpy() for k, v in bank.predict(torch.from_numpy(tt).cuda(), **kw).items()}
+    for name, got in (("host", host), ("device", dev)):
+        assert got["fwd"].shape == (N, W) and got["deriv_full"].shape == (N, D, W)
+        for k, ref in (("fwd", fwd), ("mu", mu_o), ("var", var_o), ("deriv", grad_o), ("deriv_full", dfull)):
+            assert orc.ref_err(got[k], ref) < TOL, (name, k)
+    f2, d2 = bank.forward(tt)           # (no variance: the one-launch bank mean kernel instead of P fused launches)
+    assert orc.ref_err(f2, fwd) < TOL and orc.ref_err(d2, dfull) < TOL
+
+
+def test_golden_cfg4_multivariate_emulator_20pcs(gpemu):
+    """The drop-in MultivariateEmulator on a model the REFERENCE built with 20 PCs x 2101 wavelengths (golden_M20):
+    single-point predicts as the reference makes them, and the batch call."""
+    g = golden("M20")
+    B = g["basis_functions"]
+    X = g["train_data"].T @ B            # rank-20 stand-in whose compression reproduces train_data
+    mv = gpemu.MultivariateEmulator(X=X, y=g["y"], hyperparams=g["hyperparams"], basis_functions=B, n_pcs=20)
+    models = [(gp.inputs, gp.theta, gp.invQ, gp.invQt) for gp in mv.emulators]
+    for k in range(4):
+        fwd, d = mv.predict(g["points"][k])
+        assert fwd.shape == (2101,) and d.shape == (10, 2101)
+        assert orc.ref_err(fwd, g["fwd"][k]) < 1e-7        # invQ re-derived on this host (cond(Q) ~ 1e6)
+        assert orc.ref_err(d[:, g["wsub"]], g["deriv_sub"][k]) < 1e-7
+        ofwd, od = orc.mv_predict_point(models, B, g["points"][k])     # same invQ on both sides: the 1e-10 bar
+        assert orc.ref_err(fwd, ofwd) < TOL and orc.ref_err(d, od) < TOL
+    fb, db = mv.predict(g["points"])
+    assert fb.shape == (4, 2101) and db.shape == (4, 10, 2101)
+    ofwd, _, _, _, odf = orc.mv_predict_batch(models, B, g["points"], want_deriv_full=True)
+    assert orc.ref_err(fb, ofwd) < TOL and orc.ref_err(db, odf) < TOL
+    # re-binding one emulator's state re-uploads the bank; in-place edits need invalidate_device()
+    mv.emulators[3]._set_params(mv.emulators[3].theta + 0.01)
+    models[3] = (mv.emulators[3].inputs, mv.emulators[3].theta, mv.emulators[3].invQ, mv.emulators[3].invQt)
+    f2 = mv.predict(g["points"][1], do_deriv=False)
+    assert orc.ref_err(f2, orc.mv_predict_point(models, B, g["points"][1])[0]) < TOL and not np.array_equal(f2, fb[1])
+
+
+@pytest.mark.parametrize("E", [33, 70])
+def test_bank_with_more_than_32_emulators_and_a_basis(gpemu, E):
+    """The reference has no limit on the number of PCs: banks beyond 32 emulators project in slices of 32 that
+    accumulate into the output (E > 32 with a basis used to overflow the packed basis image)."""
+    import torch
+    M, D, W, N = 40, 3, 300, 203
+    rs = np.random.RandomState(E)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)) - 0.5
+    basis = rs.standard_normal((E, W))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, None, basis=basis)
+    t = rs.random_sample((N, D))
+    models = [(inputs, thetas[e], None, invQts[e]) for e in range(E)]
+    mu = np.empty((N, E)); grad = np.empty((N, E, D))
+    for e in range(E):
+        mu[:, e], _, grad[:, e, :] = orc.predict(inputs, thetas[e], None, invQts[e], t, do_unc=False)
+    fwd = mu @ basis
+    dfull = np.einsum("ned,ew->ndw", grad, basis)
+    host = bank.predict(t, want_var=False, want_deriv=True, project=True, project_deriv=True)
+    dev = {k: v.cpu().numpy() for k, v in bank.predict(torch.from_numpy(t).cuda(), want_var=False, want_deriv=True,
+                                                        project=True, project_deriv=True).items()}
+    for name, got in (("host", host), ("device", dev)):
+        assert orc.ref_err(got["mu"], mu) < TOL and orc.ref_err(got["deriv"], grad) < TOL, name
+        assert orc.ref_err(got["fwd"], fwd) < TOL and orc.ref_err(got["deriv_full"], dfull) < TOL, name
+
+
+def test_bank_cost_host_streaming_seams(gpemu, monkeypatch):
+    """gpe_bank_cost_host: test points and per-point observations stream in, cost + gradient stream out, in chunks."""
+    rs = np.random.RandomState(77)
+    M, D, E, N = 60, 4, 6, 2500
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts)          # (mean + gradient only: the bank needs no invQ)
+    t = rs.random_sample((N, D))
+    models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
+    obsN = rs.random_sample((N, E)); w = rs.random_sample(E) + 0.5
+    c_o, g_o = orc.bank_cost(models, t, obsN, w)
+    one = bank.cost(t, obsN, w)
+    monkeypatch.setenv("GPE_SLOT_OUT_BYTES", str(8 * (1 + D) * 300))     # 300 points per chunk
+    many = bank.cost(t, obsN, w)
+    shared = bank.cost(t, obsN[0], None)
+    monkeypatch.delenv("GPE_SLOT_OUT_BYTES")
+    assert orc.ref_err(one["cost"], c_o) < TOL and orc.ref_err(one["grad"], g_o) < TOL
+    assert np.array_equal(one["cost"], many["cost"]) and np.array_equal(one["grad"], many["grad"])
+    c1, g1 = orc.bank_cost(models, t, obsN[0], None)
+    assert orc.ref_err(shared["cost"], c1) < TOL and orc.ref_err(shared["grad"], g1) < TOL
+
+
+def test_drop_in_classes_spread_one_call_over_all_devices(lib, gpemu):
+    """GaussianProcess / MultivariateEmulator / DeviceBank with device="all" (or a list): ONE predict call, every GPU of
+    the list -- the reference API has no notion of ranks (GaussianProcess.py:327).  The devices' pipelines pull chunks
+    from one cursor; results are bit-identical to one GPU.  With one visible GPU the list [0, 0] runs the same code with
+    two resident copies."""
+    import torch
+    ndev = lib.gpe_device_count()
+    devices = "all" if ndev > 1 else [0, 0]
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 300_001, seed=12)
+    gp1 = gpemu.GaussianProcess(inputs, [], device=0)
+    gpn = gpemu.GaussianProcess(inputs, [], device=devices)
+    for gp in (gp1, gpn):
+        gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt
+    a = gp1.predict(testing); b = gpn.predict(testing)
+    assert isinstance(gpn._device_model(), gpemu.MultiDeviceModel)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    pin = torch.from_numpy(testing).pin_memory().numpy()
+    out = {k: torch.empty(s, dtype=torch.float64).pin_memory().numpy() for k, s in
+           (("mu", (300_001,)), ("var", (300_001,)), ("deriv", (300_001, 10)))}
+    c = gpn.predict(pin, out=out)                                     # page-locked in and out: direct DMA path
+    for x, y in zip(a, c):
+        assert np.array_equal(x, y)
+    assert np.array_equal(gpn.hessian(testing[:500]), gp1.hessian(testing[:500]))
+    mu1 = gpn.predict(testing[:1], do_unc=False, do_deriv=False)
+    assert mu1.shape == (1,) and mu1[0] == a[0][0]
+    # device-resident data on several devices: one tensor per device
+    mm = gpn._device_model()
+    parts = [torch.from_numpy(testing[i * 1000:(i + 1) * 1000]).to("cuda:%d" % d) for i, d in enumerate(mm.devices)]
+    res = mm.predict(parts)
+    for d in set(mm.devices):
+        torch.cuda.synchronize(d)
+    for i, r in enumerate(res):
+        assert np.array_equal(r["var"].cpu().numpy(), gp1.predict(testing[i * 1000:(i + 1) * 1000])[1])
+    one = mm.predict(parts[-1])
+    assert np.array_equal(one["mu"].cpu().numpy(), res[-1]["mu"].cpu().numpy())
+    with pytest.raises(ValueError):
+        mm.predict(testing, out={"mu": np.empty(3)})                  # wrong shape is refused, not written past
+    with pytest.raises(ValueError):
+        mm.predict(testing, out={"mu": np.empty(300_001, dtype=np.float32)})
+    # single precision on a multi-device handle is served by one device
+    m32 = gpn.predict(testing[:2000], precision=np.float32)
+    assert m32[0].dtype == np.float32 and orc.ref_err(m32[0], a[0][:2000]) < 1e-5
+    # banks
+    rs = np.random.RandomState(5)
+    M, D, E, W, N = 60, 4, 5, 300, 40_000
+    binp = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+    basis = rs.standard_normal((E, W))
+    t = rs.random_sample((N, D))
+    b1 = gpemu.DeviceBank(binp, thetas, invQts, invQs, basis=basis, device=0)
+    bn = gpemu.DeviceBank(binp, thetas, invQts, invQs, basis=basis, device=devices)
+    kw = dict(want_var=True, want_deriv=True, want_hess=True, project=True)
+    r1 = b1.predict(t, **kw); rn = bn.predict(t, **kw)
+    for k in r1:
+        assert np.array_equal(r1[k], rn[k]), k
+    obs = rs.random_sample((N, E))
+    c1 = b1.cost(t, obs); cn = bn.cost(t, obs)
+    assert np.array_equal(c1["cost"], cn["cost"]) and np.array_equal(c1["grad"], cn["grad"])
+    with pytest.raises(ValueError):
+        bn.predict(torch.from_numpy(t).cuda())
+
+
+def test_large_m_scratch_shared_by_threads_and_streams(gpemu):
+    """1024 < M: the per-model K* scratch is handed between streams through an event; wait -> launches -> record is
+    one critical section (two threads could both pass the wait before either recorded)."""
+    import threading
+    import torch
+    M, D, N = 1100, 4, 6000
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=8)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    ref = orc.predict(inputs, theta, invQ, invQt, testing)
+    td = torch.from_numpy(testing).cuda()
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    out = m.predict(td)
+            st.synchronize()
+            results[i] = {k: v.cpu().numpy() for k, v in out.items()}
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for th in threads: th.start()
+    for th in threads: th.join()
+    assert not errors
+    for i in range(4):
+        assert orc.ref_err(results[i]["mu"], ref[0]) < TOL and orc.ref_err(results[i]["var"], ref[1]) < TOL
+        assert orc.ref_err(results[i]["deriv"], ref[2]) < TOL
+
+
+def _guarded(shape, guard=4096):
+    """CUDA tensor of `shape` carved out of a buffer with NaN-pattern guard bands on both sides."""
+    import torch
+    n = int(np.prod(shape)) if len(shape) else 1
+    big = torch.full((guard + n + guard,), float("nan"), dtype=torch.float64, device="cuda")
+    return big, big[guard:guard + n].view(*shape)
+
+
+def _guards_intact(big, n, guard=4096):
+    import torch
+    return bool(torch.isnan(big[:guard]).all()) and bool(torch.isnan(big[guard + n:]).all())
+
+
+def test_red_zones_around_every_output(gpemu):
+    """Stand-in for compute-sanitizer (closed on this pool): every output lives between NaN guard bands; after a sweep
+    over all plans (cfg 0/1/2, small-batch plan, symmetric fold, fused / direct Hessian, large M, single precision,
+    bank strides, projection slices) the guards must be untouched and every result element written."""
+    import torch
+    rs = np.random.RandomState(9)
+    shapes = [(1, 1, 1), (5, 2, 3), (64, 4, 129), (100, 7, 257), (250, 10, 1000), (250, 10, 7105), (256, 16, 65),
+              (300, 6, 200), (512, 10, 97), (700, 12, 50), (1000, 10, 130), (1024, 24, 33), (1100, 3, 500), (96, 32, 70)]
+    for (M, D, N) in shapes:
+        inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
+        td = torch.from_numpy(testing).cuda()
+        for sym in ((False, True) if M <= 1024 else (False,)):
+            m = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=sym)
+            for hess in (False, True):
+                bufs = {k: _guarded(s) for k, s in (("mu", (N,)), ("var", (N,)), ("deriv", (N, D)), ("hess", (N, D, D)))
+                        if hess or k != "hess"}
+                for b, v in bufs.values():
+                    v.fill_(float("inf"))
+                m.predict(td, want_hess=hess, out={k: v for k, (b, v) in bufs.items()})
+                torch.cuda.synchronize()
+                for k, (b, v) in bufs.items():
+                    assert _guards_intact(b, v.numel()), (M, D, N, sym, hess, k)
+                    assert bool(torch.isfinite(v).all()), (M, D, N, sym, hess, k)
+            m.close()
+    # single precision (float32 outputs: guard with a float32 NaN pattern)
+    for (M, D, N) in [(250, 10, 300), (100, 3, 129), (600, 10, 200), (1024, 16, 70)]:
+        inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M)
+        m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+        lib = gpemu._lib.load()
+        t32 = torch.from_numpy(testing.astype(np.float32)).cuda()
+        G = 4096
+        bufs = {k: torch.full((G + n + G,), float("nan"), dtype=torch.float32, device="cuda")
+                for k, n in (("mu", N), ("var", N), ("deriv", N * D))}
+        for fast in (0, gpemu._lib.F32_FAST_TF32):
+            for b in bufs.values():
+                b[G:-G] = float("inf")
+            gpemu._lib.check(lib.gpe_predict_f32(m._h, t32.data_ptr(), N, bufs["mu"][G:].data_ptr(), bufs["var"][G:].data_ptr(),
+                                                 bufs["deriv"][G:].data_ptr(), 7 | fast,
+                                                 torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            for k, b in bufs.items():
+                assert bool(torch.isnan(b[:G]).all()) and bool(torch.isnan(b[-G:]).all()), (M, D, N, fast, k)
+                assert bool(torch.isfinite(b[G:-G]).all()), (M, D, N, fast, k)
+        m.close()
+    # bank: strided point-major outputs, Hessian, projection (incl. a slice boundary at E = 33 and odd W)
+    for (M, D, E, W, N) in [(60, 4, 5, 301, 150), (40, 3, 33, 77, 90), (250, 10, 3, 2101, 70)]:
+        inputs = rs.random_sample((M, D))
+        thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
+        basis = rs.standard_normal((E, W))
+        bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs, basis=basis)
+        td = torch.from_numpy(rs.random_sample((N, D))).cuda()
+        lib = gpemu._lib.load()
+        bufs = {k: _guarded(s) for k, s in (("mu", (N, E)), ("var", (N, E)), ("deriv", (N, E, D)), ("hess", (N, E, D, D)),
+                                            ("fwd", (N, W)), ("deriv_full", (N, D, W)))}
+        for b, v in bufs.values():
+            v.fill_(float("inf"))
+        gpemu._lib.check(lib.gpe_bank_predict_ex(bank._h, td.data_ptr(), N, *[bufs[k][1].data_ptr() for k in
+                                                 ("mu", "var", "deriv", "hess", "fwd", "deriv_full")], 0x3F,
+                                                 torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        for k, (b, v) in bufs.items():
+            assert _guards_intact(b, v.numel()), (M, D, E, W, N, k)
+            assert bool(torch.isfinite(v).all()), (M, D, E, W, N, k)
+        bank.close()

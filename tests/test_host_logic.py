@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 
+import gp_emulator_b200 as gpe
 from gp_emulator_b200 import GaussianProcess, MultivariateEmulator, k_fold_cross_validation
 from gp_emulator_b200.sharding import shard_range
 from oracle import gp_oracle as orc
@@ -122,3 +123,37 @@ def test_argument_checks_that_need_no_device():
         gp.predict([[0.0, 0.0]])                           # the reference indexes testing.shape: arrays only
     with pytest.raises(AssertionError):
         gp.predict(np.zeros((3, 5)))                       # wrong number of columns (reference :229 asserts)
+
+
+def test_get_gpu_block_matches_reference_chunker():
+    """GaussianProcess.get_gpu_block against block boundaries frozen from the reference (GaussianProcess.py:253-270)."""
+    g = golden("B")
+    gp = gpe.GaussianProcess(np.zeros((3, 2)), [])
+    for i, (size, block) in enumerate(g["cases"]):
+        a, b = gp.get_gpu_block(int(size), int(block))
+        assert np.array_equal(a, g["start_%d" % i]) and np.array_equal(b, g["end_%d" % i]), (size, block)
+
+
+def test_model_attribute_rebinding_is_counted():
+    """MultivariateEmulator keys its device bank on each emulator's assignment counter."""
+    gp = gpe.GaussianProcess(np.zeros((3, 2)), [])
+    v0 = gp._version
+    gp.theta = np.zeros(4)
+    gp.invQt = np.zeros(3)
+    assert gp._version == v0 + 2
+    gp.targets = [1]                     # not a predict-relevant attribute
+    assert gp._version == v0 + 2
+
+
+def test_resolve_devices_and_closed_handles():
+    from gp_emulator_b200 import engine
+    assert engine.resolve_devices(3) == [3] and engine.resolve_devices([1, 0]) == [1, 0]
+    with pytest.raises(ValueError):
+        engine.resolve_devices("some")
+    with pytest.raises(ValueError):
+        engine.resolve_devices([])
+    h = engine._Handle()
+    h._own(None, lambda _h: None)
+    h.close()
+    with pytest.raises(gpe.GpemuError):
+        h._h

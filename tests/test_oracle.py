@@ -86,3 +86,33 @@ def test_longdouble_oracle_agrees_on_well_conditioned_inputs():
     lmu, lvar, lderiv, lh = orc.predict_longdouble(inputs, theta, invQ, invQt, testing, do_hess=True)
     assert orc.ref_err(mu, lmu) < 1e-14 and orc.ref_err(var, lvar) < 1e-14 and orc.ref_err(deriv, lderiv) < 1e-14
     assert orc.ref_err(orc.hessian(inputs, theta, invQt, testing), lh) < 1e-13
+
+
+def test_oracle_matches_reference_perband_bank():
+    """BASELINE config 5 pattern: E GPs on shared inputs, each predicted and differentiated twice by the reference's own
+    predict / hessian (tests/test_perband_emulator.py:22-47) -- golden_K."""
+    g = golden("K")
+    E = g["thetas"].shape[0]
+    models = [(g["inputs"], g["thetas"][e], g["invQ"][e], g["invQt"][e]) for e in range(E)]
+    mu, var, deriv, hess = orc.bank_predict(models, g["testing"], do_hess=True)
+    assert orc.ref_err(mu, g["mu"]) < TOL and orc.ref_err(deriv, g["deriv"]) < TOL and orc.ref_err(hess, g["hess"]) < TOL
+    for e in range(E):
+        assert orc.var_cond_err(var[:, e], g["var"][:, e], g["inputs"], g["thetas"][e], g["invQ"][e], g["testing"]) < 1e-14
+
+
+def test_oracle_matches_reference_cfg4_20pcs():
+    """BASELINE config 4 shape: 2101 wavelengths compressed to 20 PCs by the reference's own constructor -- golden_M20."""
+    g = golden("M20")
+    y, hyp, B = g["y"], g["hyperparams"], g["basis_functions"]
+    assert int(g["n_pcs"]) == 20 and B.shape == (20, 2101)
+    models = []
+    for i in range(20):
+        invQ, invQt = orc.prepare_likelihood(y, g["train_data"][i], hyp[:, i])
+        assert orc.ref_err(invQt, g["invQt"][i]) < 1e-6
+        models.append((y, hyp[:, i], invQ, g["invQt"][i]))
+    for k in range(4):
+        fwd, d = orc.mv_predict_point(models, B, g["points"][k])
+        assert orc.ref_err(fwd, g["fwd"][k]) < TOL
+        assert orc.ref_err(d[:, g["wsub"]], g["deriv_sub"][k]) < TOL
+    fwd_b, _, _, _, dfull = orc.mv_predict_batch(models, B, g["points"], want_deriv_full=True)
+    assert orc.ref_err(fwd_b, g["fwd"]) < 1e-11 and orc.ref_err(dfull[:, :, g["wsub"]], g["deriv_sub"]) < 1e-11
