@@ -411,6 +411,7 @@ def main():
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=dev)
+            host_group = dist.new_group(backend="gloo")   # CPU-side barrier for the phase where rank 0 drives every GPU
             model = sharding.broadcast_model(model, src=0, device=dev)   # the only collective on the path
             dist.barrier()
             torch.cuda.synchronize()
@@ -456,9 +457,35 @@ def main():
     total_ms = evs[0].elapsed_time(evs[-1])
     if world > 1:
         total_ms = sharding.max_over_ranks(total_ms, device=dev)
-    # cheap correctness tripwire inside the bench: the prefix against the oracle
-    mu_head = out["mu"][:512].cpu().numpy(); var_head = out["var"][:512].cpu().numpy()
-    t_head = testing[:512].cpu().numpy()
+    # correctness tripwire inside the bench (cfg 2): a prefix and a random subset of the step's points
+    # against the oracle, all three outputs (rank 0)
+    trip = None
+    if rank == 0:
+        nt = min(int(args.tripwire), N)
+        idx = torch.cat([torch.arange(nt, device=dev),
+                         torch.randint(0, N, (nt,), device=dev, generator=torch.Generator(device=dev).manual_seed(7))])
+        trip = {"t": testing[idx].cpu().numpy(), "mu": out["mu"][idx].cpu().numpy(), "var": out["var"][idx].cpu().numpy(),
+                "deriv": out["deriv"][idx].cpu().numpy(), "n_prefix": nt, "n_random": nt}
+    # ---- configs[1] as written: 1e8 points IN TOTAL, N/G per GPU (strong scaling) ---------------------------------
+    strong = None
+    Ns = int(round(1e8)) // world
+    if Ns <= N:
+        ts = testing[:Ns]
+        dm.predict(ts)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            dm.predict(ts)
+        e1.record()
+        barrier()
+        s_ms = e0.elapsed_time(e1)
+        if world > 1:
+            s_ms = sharding.max_over_ranks(s_ms, device=dev)
+        strong = {"total_points_per_step": Ns * world, "points_per_gpu_per_step": Ns, "value": Ns * world * args.steps / (s_ms * 1e-3),
+                  "unit": "points/s", "ms_per_step": s_ms / args.steps, "scaling": "strong",
+                  "note": "BASELINE configs[1] literally: 1e8 test points sharded N/G per GPU, device-resident, max over ranks"}
+        del ts
     del out
     torch.cuda.empty_cache()
 
@@ -481,6 +508,37 @@ def main():
     e2e_s = time.perf_counter() - t0
     if world > 1:
         e2e_s = sharding.max_over_ranks(e2e_s, device=dev)
+    ranks_e2e = Ne * world * args.steps / e2e_s
+    # ---- N > 1: the drop-in call itself -- ONE process, ONE GaussianProcess.predict over all N GPUs (gpe_multi_*) ----
+    one_proc = None
+    if world > 1:
+        del host_in, host_out, mu_h, var_h, der_h
+        dist.barrier(group=host_group)
+        if rank == 0:
+            Nm = int(args.multi_points) * world
+            gpm = gpe.GaussianProcess(model["inputs"], [], device=list(range(world)))
+            gpm.theta, gpm.invQ, gpm.invQt = model["theta"], model["invQ"], model["invQt"]
+            m_in = torch.rand(Nm, D, dtype=torch.float64).pin_memory().numpy()
+            m_out = {"mu": torch.empty(Nm, dtype=torch.float64).pin_memory().numpy(),
+                     "var": torch.empty(Nm, dtype=torch.float64).pin_memory().numpy(),
+                     "deriv": torch.empty(Nm, D, dtype=torch.float64).pin_memory().numpy()}
+            gpm.predict(m_in, out=m_out)
+            l0 = lib.gpe_launch_count()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                mu_m, var_m, der_m = gpm.predict(m_in, out=m_out)
+                _ = float(mu_m[-1]) + float(der_m[-1, -1])
+            one_s = time.perf_counter() - t0
+            # the fan-out must reproduce one GPU bit for bit: check a slice against this rank's single-device model
+            chk = dm.predict(torch.from_numpy(m_in[:100000]).to(dev))
+            same = all(bool(np.array_equal(chk[k].cpu().numpy(), m_out[k][:100000])) for k in ("mu", "var", "deriv"))
+            one_proc = {"value": Nm * args.steps / one_s, "unit": "points/s", "points_per_step": Nm,
+                        "h2d_bytes_per_step": Nm * D * 8, "d2h_bytes_per_step": Nm * (2 + D) * 8,
+                        "launches": int(lib.gpe_launch_count() - l0), "bit_identical_to_one_gpu": same,
+                        "api": "ONE process: GaussianProcess(inputs, targets, device=[0..%d]).predict(pinned numpy in, pinned out) -> "
+                               "gpe_multi_predict: one pipeline thread per GPU pulling chunks from a shared cursor" % (world - 1)}
+            del m_in, m_out, gpm
+        dist.barrier(group=host_group)
     # the same call the way a reference user makes it: plain (pageable) numpy in, fresh numpy arrays out
     pageable_rate = None
     if world == 1:
@@ -493,6 +551,7 @@ def main():
             mu_p, var_p, der_p = gp.predict(plain_in)
         pageable_rate = 3 * Np / (time.perf_counter() - t0)
         del plain_in, mu_p, var_p, der_p
+        del host_in, host_out
 
     # ---- opt-in variants of the same workload, reported beside the headline (short, outside every timed region) --
     variants = None
@@ -543,18 +602,25 @@ def main():
         trainer.close()
     if rank == 0:
         from oracle import gp_oracle as orc
-        mu_o, var_o, _ = orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], t_head)
-        parity = {"mu": orc.ref_err(mu_head, mu_o), "var": orc.ref_err(var_head, var_o)}
+        _use_all_host_threads()
+        mu_o, var_o, der_o = orc.predict(model["inputs"], model["theta"], model["invQ"], model["invQt"], trip["t"], chunk=100000)
+        parity = {"mu": orc.ref_err(trip["mu"], mu_o), "var": orc.ref_err(trip["var"], var_o),
+                  "deriv": orc.ref_err(trip["deriv"], der_o), "points_checked": int(trip["t"].shape[0]),
+                  "what": "%d-point prefix + %d random indices of rank 0's %d points of the last timed step, metric "
+                          "max|x - ref| / max|ref| (tests/benchmark.py:51-53), bar 1e-10" % (trip["n_prefix"], trip["n_random"], N)}
         value = N * world * args.steps / (total_ms * 1e-3)
         kern_ms = float(np.mean(step_ms))
         achieved = N * F_PER_POINT / (kern_ms * 1e-3) / 1e12
         peak = peaks["dmma_tflops"]
-        traffic = None
+        # DRAM traffic cannot be observed without a profiler attached: it is IMPORTED from the committed ncu capture of
+        # this kernel (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per point) and scaled to N
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
                 traffic = tj["dram_bytes_per_point"] * N
+                traffic_src = "imported, not measured in this run: %s" % tj.get("source", "profiles/traffic.json")
             except Exception:
                 traffic = None
         line = {
@@ -563,16 +629,17 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(N),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "note": "FP64: achieved = N*139011 flop / mean launch time (CUDA events, one launch per step); "
                                  "peak = DMMA.8x8x4 rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 "
                                  "figure); DFMA peak %.1f, SM %.0f MHz under FP64 load" %
                                  (peaks["dfma_tflops"], peaks["sm_mhz_fp64_load"]),
-                         "kernel": "k_predict_full<4,8,2,4,10>", "kernel_ms": kern_ms,
+                         "kernel": dm.plan(N), "kernel_ms": kern_ms,
                          "hbm_GBps": N * BYTES_PER_POINT / (kern_ms * 1e-3) / 1e9},
-            "e2e": {"value": Ne * world * args.steps / e2e_s, "unit": "points/s",
+            "e2e": {"value": ranks_e2e, "unit": "points/s",
                     "h2d_bytes_per_step": Ne * D * 8, "d2h_bytes_per_step": Ne * (2 + D) * 8,
-                    "points_per_gpu_per_step": Ne,
+                    "points_per_gpu_per_step": Ne, "mode": "torchrun ranks" if world > 1 else "one process, one GPU",
+                    "torchrun_ranks_points_per_s": ranks_e2e, "one_process_all_gpus": one_proc,
                     "pageable_numpy_points_per_s": pageable_rate,   # pageable inputs, fresh result arrays per call (steady state)
                     "host_numa_binding": ("rank pinned to the %d CPUs local to its GPU" % len(numa_cpus)) if numa_cpus else None,
                     "api": "GaussianProcess.predict(numpy pinned in, preallocated pinned out) -> libgpemu two-slot stream pipeline"},
@@ -581,8 +648,24 @@ def main():
             "parity_vs_oracle": parity,
             "variants": variants,
         }
+        if one_proc is not None and one_proc["value"] > ranks_e2e:
+            # the headline e2e is the call a drop-in user makes: one process, one predict over all N GPUs
+            line["e2e"].update({"value": one_proc["value"], "mode": "one process, gpe_multi (GaussianProcess(device=[0..N-1]))",
+                                "h2d_bytes_per_step": one_proc["h2d_bytes_per_step"],
+                                "d2h_bytes_per_step": one_proc["d2h_bytes_per_step"]})
+        line["strong_scaling"] = strong
         if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
             line["cpu_baseline"] = cpu_baseline(model, int(args.cpu_points))
+        if not args.no_configs and world == 1:
+            del testing
+            torch.cuda.empty_cache()
+            hbm = bf16 = None
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                hbm, bf16 = float(mp["hbm_gbs"]), float(mp.get("bf16_tflops_sustained", mp.get("bf16_tflops")))
+            except Exception:
+                hbm = 6550.0     # the figure B200_PROFILING.md quotes for this pool when the file is absent
+            line["configs"] = run_configs(torch, gpe, orc, local_rank, peaks, hbm, bf16)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -1,4 +1,4 @@
-// Thin inline-PTX wrappers: mbarrier, TMA bulk copies (cp.async.bulk -> SASS UBLKCP), cluster helpers.
+// Thin inline-PTX wrappers: mbarrier, TMA bulk copies (cp.async.bulk -> SASS UBLKCP).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -60,32 +60,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
         : "memory");
 }
 
-// Same, multicast to the CTAs of the cluster named in cta_mask (same smem offset and mbarrier offset in each).
-__device__ __forceinline__ void tma_bulk_g2s_mcast(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                                   uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], "
-        "%4;\n" ::"r"(smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
-        : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
+// Kernel-entry guard (always on; a handful of integer instructions per CTA): the shared-memory carve-up computed on the
+// host -- byte offsets travelling in the kernel parameters -- must fit the dynamic shared memory this launch was actually
+// given.  A mismatch traps (the launch fails with an error the host reports) instead of silently corrupting a
+// neighbouring buffer.  compute-sanitizer is not available on the GPU pool; this and the red-zone test
+// (tests/test_gpu_parity.py::test_red_zones_around_every_output) stand in for it.
+__device__ __forceinline__ uint32_t dynamic_smem_size() {
     uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;\n" : "=r"(r));
     return r;
 }
-
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+__device__ __forceinline__ void smem_guard(uint32_t extent) {
+    if (threadIdx.x == 0 && extent > dynamic_smem_size()) __trap();
 }
-
-// Arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
-}
+__device__ __forceinline__ uint32_t umax2(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 }  // namespace gpe

@@ -61,7 +61,7 @@ constexpr int kHessFusedMaxDp = 16;   // predict_full_inst.cu instantiates the H
 
 struct FullPlan {
     bool valid = false;
-    int cfg = 0, TN = 0, WC = 0, GH = 1, alias_x = 0, ctas_per_sm = 1;
+    int cfg = 0, TN = 0, WC = 0, GH = 1, ctas_per_sm = 1;
     int Mp = 0, nt_act = 0, kblk = 0, kbps = 0, nit = 0, nstage = 0, JC = 0, nchunks = 0;
     uint32_t off_bar = 0, off_sqw = 0, off_ks = 0, off_bst = 0, off_xc = 0, off_ts = 0, off_pa = 0, off_vred = 0;
     uint32_t stage_bytes = 0, smem = 0, ts_bytes = 0;
@@ -139,6 +139,12 @@ struct gpe_multi {
     std::vector<int> devices;
     std::vector<gpe_model*> models;   // one resident copy of the GP per device (single-GP handle) ...
     std::vector<gpe_bank*> banks;     // ... or of the bank (bank handle)
+    // PCIe routing of host-resident calls: relays[g].partner >= 0 sends device g's host traffic through that device's
+    // link over NVLink (decided once per handle from a measured link rate, multi_route)
+    std::mutex route_mu;
+    bool routed = false;
+    std::vector<Relay> relays;
+    std::vector<double> link_gbs;     // measured per-device rate (GB/s per direction, all devices copying both ways at once)
 };
 
 namespace {
@@ -182,27 +188,21 @@ cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_
 }
 
 // Decide tile shape, pipeline depth and the shared-memory carve-up of the fused kernel for (M, D).
-//   cfg 3: Mp <= 256 -> TN = 32, 4 warps, TWO CTAs per SM: DFMA (phase A) and DMMA (phase B) share one FP64 pipe,
-//          so two co-resident CTAs whose phases drift apart keep it busy (ncu: 77% -> see profiles/).  To fit
-//          2 x ~100 KB the phase-A chunk buffer overlays the B-operand ring (alias_x).
-//   cfg 0: same Mp range, TN = 64, 8 warps, 1 CTA/SM (kept selectable with GPE_FULL_CFG=0 for comparison)
-//   cfg 1 / 2: Mp <= 512 / 1024, TN = 32 / 16, 8 warps, 1 CTA/SM
+//   cfg 0: Mp <= 256 -> TN = 64, 8 warps as 2 x 4, 1 CTA/SM
+//   cfg 1 / 2: Mp <= 512 / 1024, TN = 32 / 16, 8 warps as 1 x 8, 1 CTA/SM
+// (Two more configurations were measured and dropped in round 1: two co-resident 4-warp CTAs per SM -- slower, mixing
+// DFMA and DMMA warps costs pipe efficiency and per-tile overheads double -- and 16 warps at 128 registers, which spills.)
 // small_Mp > 0: the low-latency plan for small batches -- 16-point tiles (cfg 2) on the padded width of the main
 // plan, so that both share s_tiled / xchunks.
 FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     FullPlan f;
     const int m32 = (M + 31) / 32 * 32, m64 = (M + 63) / 64 * 64;
-    int force = -1;
-    if (const char* e = getenv("GPE_FULL_CFG")) force = atoi(e);
     // the kernels also hold static shared memory (exp table 512 B; HESS variants a 1 KB index table + 256 B): leave room
-    uint32_t smem_cap = kSmemMax - 2048;
+    const uint32_t smem_cap = kSmemMax - 2048;
     if (small_Mp > 0) {
         f.cfg = 2; f.TN = 16; f.WC = 8; f.GH = 4; f.Mp = small_Mp; f.nt_act = small_Mp / 64;
     } else if (m32 <= 256) {
-        f.Mp = m32; f.nt_act = m32 / 32;
-        if (force == 3) { f.cfg = 3; f.TN = 32; f.WC = 4; f.GH = 1; f.alias_x = 1; smem_cap = (233472 - 2 * 1024) / 2; }
-        else if (force == 4) { f.cfg = 4; f.TN = 64; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64; }
-        else { f.cfg = 0; f.TN = 64; f.WC = 4; f.GH = 1; }
+        f.cfg = 0; f.TN = 64; f.WC = 4; f.GH = 1; f.Mp = m32; f.nt_act = m32 / 32;
     } else if (m64 <= 512) {
         f.cfg = 1; f.TN = 32; f.WC = 8; f.GH = 2; f.Mp = m64; f.nt_act = m64 / 64;
     } else if (m64 <= 1024) {
@@ -210,7 +210,7 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     } else {
         return f;  // invalid: variance contraction unsupported for this M
     }
-    f.ctas_per_sm = (f.cfg == 3) ? 2 : 1;
+    f.ctas_per_sm = 1;
     f.kblk = (M + 3) / 4;
     f.kbps = (f.cfg == 0) ? 2 : 1;  // k-blocks (32 * Mp bytes each) per ring stage == template KB of the cfg
     f.nit = (f.kblk + f.kbps - 1) / f.kbps;
@@ -224,7 +224,7 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     f.off_ts = off; off += 2 * f.ts_bytes;
     f.off_pa = off; off += (f.GH > 1) ? align_up((uint32_t)f.GH * f.TN * (D + 1) * 8u, 16) : 0;
     f.off_vred = off; off += (uint32_t)f.WC * f.TN * 8u;
-    if (DP <= kHessFusedMaxDp && f.cfg <= 2) {   // room for the centred test rows of the fused Hessian
+    if (DP <= kHessFusedMaxDp) {   // room for the centred test rows of the fused Hessian
         f.off_hts = off; off += align_up((uint32_t)f.TN * D * 8u, 16);
         f.NC = (DP * (DP + 1) / 2 + 7) / 8 * 8;
         f.kbh = (int)(f.stage_bytes / ((uint32_t)f.NC * 32u));
@@ -234,18 +234,6 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     const uint32_t fixed = off;
     const int m4 = (M + 3) / 4 * 4;
     const uint32_t row = (uint32_t)(DP + 1) * 8u;
-    if (f.alias_x) {
-        // ring and chunk buffer share [fixed, fixed + max(ring, chunk))
-        if (fixed + 2 * f.stage_bytes > smem_cap) return f;
-        f.nstage = (fixed + 4 * f.stage_bytes <= smem_cap) ? 4 : 2;
-        const int jc_max = (int)((smem_cap - fixed) / row) / 4 * 4;
-        if (jc_max < 32) return f;
-        f.JC = std::min(jc_max, m4); f.nchunks = (M + f.JC - 1) / f.JC;
-        f.off_bst = fixed; f.off_xc = fixed;
-        f.smem = fixed + std::max((uint32_t)f.nstage * f.stage_bytes, (uint32_t)f.JC * row);
-        f.valid = f.smem <= smem_cap;
-        return f;
-    }
     // resident training set if it fits beside a ring of >= 3 stages, else chunks of <= 256 points; the ring then
     // takes every stage that still fits (at most 8: the barrier arrays)
     {
@@ -261,7 +249,6 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
         f.nstage = (int)std::min<uint32_t>(8, (avail - (uint32_t)f.JC * row) / f.stage_bytes);
         if (f.nstage < 2) return f;
     }
-    if (f.nstage == 0) return f;
     f.off_bst = fixed;
     f.off_xc = fixed + (uint32_t)f.nstage * f.stage_bytes;
     f.smem = f.off_xc + (uint32_t)f.JC * row;
@@ -416,7 +403,8 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
         p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk;
         p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1; p.symmetric = m->symmetric ? 1 : 0;
-        if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1)); p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b; p.alias_x = f.alias_x;
+        if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1));
+        p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
         p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;
         p.stage_bytes = f.stage_bytes; p.ts_bytes = f.ts_bytes;
@@ -429,7 +417,10 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         }
         const int64_t ntiles = (N + f.TN - 1) / f.TN;
         const int grid = (int)std::min<int64_t>(ntiles, (int64_t)m->sms * f.ctas_per_sm);
-        CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem, st));
+        // dev aid for tests/test_gpu_parity.py::test_smem_guard_traps: launch with less dynamic shared memory than the
+        // carve-up needs; the kernel-entry guard must turn that into a launch error
+        static const uint32_t shrink = getenv("GPE_DEBUG_SHRINK_SMEM") ? (uint32_t)atoi(getenv("GPE_DEBUG_SHRINK_SMEM")) : 0u;
+        CUDA_TRY(launch_full(m->DP, f.cfg, p, grid, f.smem - std::min(shrink, f.smem), st));
         mean_done = true;
     }
     const bool need_mean = !mean_done && (mu != nullptr || deriv != nullptr);
@@ -455,6 +446,13 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     }
     return GPE_OK;
 }
+
+// Calls that visit several devices leave the caller's current device as they found it (torch allocates on it).
+struct DeviceRestore {
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; } }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
 
 struct IoList {
     IoSpec v[kMaxIo];
@@ -515,7 +513,7 @@ int run_per_device(int G, const int* devices, Fn fn) {
 // Host-resident FP64 predict of one model: its share of a call of call_N points (the whole call unless `shared`
 // hands out the chunks of a multi-device call).  Caller holds m->host_mu.
 int model_stream(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
-                 const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
+                 const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr, const Relay* relay = nullptr) {
     const int64_t D = m->D;
     IoList in, out;
     in.add(testing, D);
@@ -532,7 +530,7 @@ int model_stream(gpe_model* m, const double* testing, int64_t N, double* mu, dou
                            auto at = [&](int i) { return i >= 0 ? (double*)dout[i] : nullptr; };
                            return predict_device(m, (const double*)di[0], n, at(i_mu), at(i_var), at(i_der), at(i_hes), 1, 1,
                                                  D, D * D, st, call_N);
-                       });
+                       }, relay);
 }
 
 // ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
@@ -558,6 +556,7 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
     double* ctile = stage + 2 * (size_t)KS * kProjCols * 4;     // [8 warps][16][kProjPitch]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = warp >> 2, wc = warp & 3;
+    smem_guard(128u + 2u * KS * kProjCols * 4u * 8u + 8u * 16u * kProjPitch * 8u);
     const int64_t r0 = (int64_t)blockIdx.x * kProjRows + wr * 32;
     const int ngroups = Wp / kProjCols;
     constexpr uint32_t ks_bytes = kProjCols * 4 * 8, stage_doubles = (uint32_t)KS * kProjCols * 4;
@@ -913,10 +912,9 @@ int gpe_model_plan(gpe_model* m, int64_t N, char* buf, int len) {
     if (!m || !buf || len <= 0) return 0;
     auto full_name = [&](const FullPlan& f, char* out, int n) {
         // template arguments as instantiated in predict_full_inst.cu: <MT, NT, WR, WC, DP, MINB, KB, FULLNT, SYM, HESS>
-        static const int MT[5] = {4, 4, 2, 4, 4}, WR[5] = {2, 1, 1, 1, 2}, WC[5] = {4, 8, 8, 4, 8}, MINB[5] = {1, 1, 1, 2, 1},
-                         KB[5] = {2, 1, 1, 1, 1};
+        static const int MT[3] = {4, 4, 2}, WR[3] = {2, 1, 1}, WC[3] = {4, 8, 8}, MINB[3] = {1, 1, 1}, KB[3] = {2, 1, 1};
         const int nt_inst = f.cfg == 0 ? f.nt_act : (f.cfg == 1 ? (f.nt_act >= 5 && f.nt_act <= 7 ? f.nt_act : 8)
-                                                  : (f.cfg == 2 ? (f.nt_act >= 9 && f.nt_act <= 15 ? f.nt_act : 16) : (f.cfg == 3 ? 8 : 4)));
+                                                                  : (f.nt_act >= 9 && f.nt_act <= 15 ? f.nt_act : 16));
         return snprintf(out, n, "k_predict_full<%d,%d,%d,%d,%d,%d,%d,%s,%s,false> (cfg %d: %d-point tiles, Mp=%d, %d-stage TMA ring, %u B smem)",
                         MT[f.cfg], nt_inst, WR[f.cfg], WC[f.cfg], m->DP, MINB[f.cfg], KB[f.cfg], nt_inst == f.nt_act ? "true" : "false",
                         m->symmetric ? "true" : "false", f.cfg, f.TN, f.Mp, f.nstage, f.smem);
@@ -1257,6 +1255,159 @@ int bank_check_outputs(gpe_bank* b, int64_t N, const double* testing, double*& m
     return GPE_OK;
 }
 
+// Per-device PCIe rate with every device of the list copying both ways at once (what a host-resident multi-device
+// call does): 16 MB pinned buffers, ~40 ms.  GB/s per direction.
+std::vector<double> measure_links(const std::vector<int>& devices) {
+    const int G = (int)devices.size();
+    const size_t bytes = (size_t)16 << 20;
+    std::vector<double> rate(G, 0.0);
+    std::vector<void*> h_in(G, nullptr), h_out(G, nullptr), d_in(G, nullptr), d_out(G, nullptr);
+    std::vector<cudaStream_t> s1(G, nullptr), s2(G, nullptr);
+    bool ok = true;
+    for (int g = 0; g < G && ok; ++g) {
+        ok = cudaSetDevice(devices[g]) == cudaSuccess && cudaMallocHost(&h_in[g], bytes) == cudaSuccess &&
+             cudaMallocHost(&h_out[g], bytes) == cudaSuccess && cudaMalloc(&d_in[g], bytes) == cudaSuccess &&
+             cudaMalloc(&d_out[g], bytes) == cudaSuccess && cudaStreamCreateWithFlags(&s1[g], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&s2[g], cudaStreamNonBlocking) == cudaSuccess;
+        if (ok) memset(h_in[g], 0, bytes);
+    }
+    if (ok) {
+        std::atomic<int> ready{0};
+        std::atomic<bool> go{false};
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] {
+                cudaSetDevice(devices[g]);
+                auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+                auto round = [&] {
+                    cudaMemcpyAsync(d_in[g], h_in[g], bytes, cudaMemcpyHostToDevice, s1[g]);
+                    cudaMemcpyAsync(h_out[g], d_out[g], bytes, cudaMemcpyDeviceToHost, s2[g]);
+                };
+                round(); cudaStreamSynchronize(s1[g]); cudaStreamSynchronize(s2[g]);     // warm
+                ready++;
+                while (!go.load()) {}
+                const double t0 = now();
+                int reps = 0;
+                while (now() - t0 < 0.04) { round(); round(); cudaStreamSynchronize(s1[g]); cudaStreamSynchronize(s2[g]); reps += 2; }
+                rate[g] = reps * (double)bytes / (now() - t0) / 1e9;
+            });
+        while (ready.load() < G) {}
+        go = true;
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < G; ++g) {
+        if (cudaSetDevice(devices[g]) != cudaSuccess) continue;
+        if (h_in[g]) cudaFreeHost(h_in[g]);
+        if (h_out[g]) cudaFreeHost(h_out[g]);
+        if (d_in[g]) cudaFree(d_in[g]);
+        if (d_out[g]) cudaFree(d_out[g]);
+        if (s1[g]) cudaStreamDestroy(s1[g]);
+        if (s2[g]) cudaStreamDestroy(s2[g]);
+    }
+    cudaGetLastError();
+    if (!ok) std::fill(rate.begin(), rate.end(), 0.0);
+    return rate;
+}
+
+// Decide, once per handle, which devices send their host traffic through a partner.  GPE_MULTI_RELAY = off | auto
+// (default) | force (first half of the device list relays through the second half: for tests on symmetric boxes).
+// auto: a device whose measured rate is below 0.6 x the best one relays through a fast device -- on the 8-GPU boxes of
+// this pool GPUs 0-3 get 6.2 GB/s per direction against 11.9 for GPUs 4-7 with all eight active, and moving ALL host
+// traffic onto GPUs 4-7 lifts the aggregate from 72 to 94 GB/s per direction (profiles/r02_pcie_probe8_b.txt).
+void multi_route(gpe_multi* mm) {
+    std::lock_guard<std::mutex> lock(mm->route_mu);
+    if (mm->routed) return;
+    mm->routed = true;
+    const int G = (int)mm->devices.size();
+    mm->relays.assign(G, Relay());
+    const char* env = getenv("GPE_MULTI_RELAY");
+    const std::string mode = env ? env : "auto";
+    if (G < 2 || mode == "off" || mode == "0") return;
+    std::vector<int> slow, fast;
+    if (mode == "force") {
+        for (int g = 0; g < G; ++g) (g < G / 2 ? slow : fast).push_back(g);
+    } else {
+        bool distinct = true;
+        for (int g = 0; g < G; ++g) for (int h = 0; h < g; ++h) distinct = distinct && mm->devices[g] != mm->devices[h];
+        if (!distinct) return;
+        mm->link_gbs = measure_links(mm->devices);
+        const double best = *std::max_element(mm->link_gbs.begin(), mm->link_gbs.end());
+        if (!(best > 0)) return;
+        for (int g = 0; g < G; ++g) (mm->link_gbs[g] < 0.6 * best ? slow : fast).push_back(g);
+    }
+    const bool trace = getenv("GPE_PIPE_TRACE") != nullptr;
+    if (trace) {
+        fprintf(stderr, "[gpemu multi] link GB/s per direction (all devices copying both ways):");
+        for (double v : mm->link_gbs) fprintf(stderr, " %.1f", v);
+        fprintf(stderr, " | %zu slow, %zu fast\n", slow.size(), fast.size());
+    }
+    if (slow.empty() || fast.empty()) return;
+    for (size_t i = 0; i < slow.size(); ++i) {
+        const int g = slow[i], p = fast[i % fast.size()];
+        const int dg = mm->devices[g], dp = mm->devices[p];
+        if (dg != dp) {
+            int a = 0, b = 0;
+            if (cudaDeviceCanAccessPeer(&a, dg, dp) != cudaSuccess || cudaDeviceCanAccessPeer(&b, dp, dg) != cudaSuccess || !a || !b) {
+                cudaGetLastError();
+                continue;
+            }
+            cudaSetDevice(dg); cudaDeviceEnablePeerAccess(dp, 0); cudaGetLastError();   // (already enabled is fine)
+            cudaSetDevice(dp); cudaDeviceEnablePeerAccess(dg, 0); cudaGetLastError();
+        }
+        Relay r;
+        r.partner = dp;
+        bool ok = cudaSetDevice(dp) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; ++k)
+            ok = cudaStreamCreateWithFlags(&r.st[k], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&r.ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&r.done[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaSetDevice(dg) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&r.ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) mm->relays[g] = r;
+        else cudaGetLastError();
+    }
+    if (trace) {
+        fprintf(stderr, "[gpemu multi] relays:");
+        for (int g = 0; g < G; ++g) if (mm->relays[g].partner >= 0) fprintf(stderr, " %d->%d", mm->devices[g], mm->relays[g].partner);
+        fprintf(stderr, "\n");
+    }
+}
+
+// The relay of pipeline g for this call (NULL: the device uses its own link), with buffers grown to the plan.
+const Relay* multi_relay(gpe_multi* mm, int g, const StreamPlan& pl, const IoList& in, const IoList& out, int* rc) {
+    *rc = GPE_OK;
+    if (!(pl.in_direct && pl.out_direct)) return nullptr;
+    Relay& r = mm->relays[g];
+    if (r.partner < 0) return nullptr;
+    const size_t in_b = std::max<size_t>(io_bytes(in.v, in.n, pl.CH, 8, false), 256);
+    const size_t out_b = std::max<size_t>(io_bytes(out.v, out.n, pl.CH, 8, true), 256);
+    if (cudaSetDevice(r.partner) != cudaSuccess) { *rc = fail(GPE_ERR_CUDA, "cudaSetDevice(%d) failed", r.partner); return nullptr; }
+    for (int k = 0; k < 2 && *rc == GPE_OK; ++k) {
+        *rc = ensure_buf(&r.r_in[k], &r.in_cap[k], in_b, false);
+        if (*rc == GPE_OK) *rc = ensure_buf(&r.r_out[k], &r.out_cap[k], out_b, false);
+    }
+    cudaSetDevice(mm->devices[g]);
+    return *rc == GPE_OK ? &r : nullptr;
+}
+
+void multi_free_relays(gpe_multi* mm) {
+    for (size_t g = 0; g < mm->relays.size(); ++g) {
+        Relay& r = mm->relays[g];
+        if (r.partner < 0) continue;
+        cudaSetDevice(r.partner);
+        for (int k = 0; k < 2; ++k) {
+            if (r.r_in[k]) cudaFree(r.r_in[k]);
+            if (r.r_out[k]) cudaFree(r.r_out[k]);
+            if (r.st[k]) cudaStreamDestroy(r.st[k]);
+            if (r.ev_in[k]) cudaEventDestroy(r.ev_in[k]);
+            if (r.done[k]) cudaEventDestroy(r.done[k]);
+        }
+        cudaSetDevice(mm->devices[g]);
+        for (int k = 0; k < 2; ++k) if (r.ev_out[k]) cudaEventDestroy(r.ev_out[k]);
+    }
+    mm->relays.clear();
+}
+
 // Chunk plan of a call that G pipelines share.
 StreamPlan plan_shared(const IoList& in, const IoList& out, int64_t N, int sms, int G) {
     return plan_stream(in.v, in.n, out.v, out.n, N, 8, 64 * (int64_t)sms, G, false);
@@ -1398,6 +1549,7 @@ int gpe_bank_forward(gpe_bank* b, const double* testing, int64_t N, double* fwd,
 // active (profiles/r01_pcie_8ranks.txt).
 int gpe_multi_create(int n_devices, const int* devices, int M, int D, const double* inputs, const double* expX,
                      const double* invQt, const double* invQ, unsigned options, gpe_multi** out) {
+    DeviceRestore restore_device;
     if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
@@ -1415,6 +1567,7 @@ int gpe_multi_create(int n_devices, const int* devices, int M, int D, const doub
 
 int gpe_multi_bank_create(int n_devices, const int* devices, int E, int M, int D, const double* inputs, const double* expX,
                           const double* invQt, const double* invQ, const double* basis, int W, gpe_multi** out) {
+    DeviceRestore restore_device;
     if (!out) return fail(GPE_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n_devices < 1 || !devices) return fail(GPE_ERR_INVALID, "need at least one device");
@@ -1431,7 +1584,9 @@ int gpe_multi_bank_create(int n_devices, const int* devices, int E, int M, int D
 }
 
 int gpe_multi_destroy(gpe_multi* mm) {
+    DeviceRestore restore_device;
     if (!mm) return GPE_OK;
+    multi_free_relays(mm);
     for (gpe_model* m : mm->models) gpe_model_destroy(m);
     for (gpe_bank* b : mm->banks) gpe_bank_destroy(b);
     delete mm;
@@ -1463,11 +1618,18 @@ int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* m
     const StreamPlan pl = plan_shared(in, out, N, m0->sms, G);
     std::atomic<int64_t> cursor{0};
     ChunkSource src{&cursor, N, pl.CH};
+    // large page-locked calls: decide (once per handle) whether some devices should send their host traffic through a
+    // partner's PCIe link
+    const bool relay_ok = pl.in_direct && pl.out_direct && N >= 4 * pl.CH;
+    if (relay_ok) multi_route(mm);
     // the kernel plan (tile size) follows the size of the whole call, so G devices reproduce one device bit for bit
     return run_per_device(G, mm->devices.data(), [&](int g) {
         gpe_model* m = mm->models[g];
         std::lock_guard<std::mutex> lock(m->host_mu);
-        return model_stream(m, testing, N, mu, var, deriv, hess, &pl, &src);
+        int rc = GPE_OK;
+        const Relay* relay = (relay_ok && mm->routed && !mm->relays.empty()) ? multi_relay(mm, g, pl, in, out, &rc) : nullptr;
+        if (rc) return rc;
+        return model_stream(m, testing, N, mu, var, deriv, hess, &pl, &src, relay);
     });
 }
 
@@ -1475,6 +1637,7 @@ int gpe_multi_predict_device(gpe_multi* mm, const double* const* testing, const 
                              double* const* var, double* const* deriv, double* const* hess, unsigned flags,
                              void* const* streams) {
     NvtxRange nvtx_range("gpe_multi_predict_device");
+    DeviceRestore restore_device;
     if (!mm || mm->models.empty()) return fail(GPE_ERR_INVALID, "handle is NULL or not a single-GP handle");
     if (!testing || !N) return fail(GPE_ERR_INVALID, "testing / N is NULL");
     const int G = (int)mm->models.size();

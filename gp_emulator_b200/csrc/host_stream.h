@@ -189,6 +189,18 @@ struct ChunkSource {
     }
 };
 
+// NVLink relay of one device's host traffic through a partner device's PCIe link (gpe_multi_*: on some boxes half of
+// the GPUs sit behind a slower PCIe path, profiles/r02_pcie_probe8_*.txt).  Buffers, streams and the in / done events
+// live on the partner; ev_out on the device itself.  Two slots, matching the direct path.
+struct Relay {
+    int partner = -1;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    void* r_in[2] = {nullptr, nullptr};
+    void* r_out[2] = {nullptr, nullptr};
+    size_t in_cap[2] = {0, 0}, out_cap[2] = {0, 0};
+};
+
 struct StreamPlan {
     bool in_direct = false, out_direct = false, zero_copy = false;
     int64_t CH = 1;
@@ -276,7 +288,8 @@ inline int prepare_slots(Slot* slots, const StreamPlan& pl, const IoSpec* ins, i
 //   chunk-local device arrays ((n, width) each, 256-byte aligned; external outputs first, then the intermediates).
 template <typename Launch>
 int stream_host(Slot* slots, int device, const StreamPlan& pl, ChunkSource src, size_t ES, const IoSpec* ins, int nin,
-                const IoSpec* outs, int nout, Launch launch) {
+                const IoSpec* outs, int nout, Launch launch, const Relay* relay = nullptr) {
+    if (relay && !(pl.in_direct && pl.out_direct)) relay = nullptr;   // the staged path copies through its own slots
     if (nin > kMaxIo || nout > kMaxIo) return set_error(GPE_ERR_INVALID, "too many streamed arrays");
     // order of the chunk-local output arrays: external ones first (one contiguous D2H in the staged path)
     int order[kMaxIo], next = 0;
@@ -314,22 +327,60 @@ int stream_host(Slot* slots, int device, const StreamPlan& pl, ChunkSource src, 
     int64_t n0 = 0, n = 0;
 
     if (pl.in_direct && pl.out_direct) {
+        // At most two chunks in flight per pipeline: a slot takes its next chunk only when its previous one has finished,
+        // so that with several pipelines on one cursor a chunk goes to the device that is ready for it (taking chunks at
+        // enqueue speed would hand the whole call to the first thread).
         int which = 0;
         bool used[2] = {false, false};
-        while (src.take(&n0, &n)) {
+        for (;;) {
             Slot& s = slots[which];
+            cudaEvent_t done = relay ? relay->done[which] : s.done;
+            if (used[which]) GPE_CUDA_TRY(cudaEventSynchronize(done));
+            if (!src.take(&n0, &n)) break;
             used[which] = true;
             carve(s.d_in, nullptr, ins, nin, nullptr, nin, n, d_ins);
             carve(s.d_out, nullptr, outs, nout, order, nout, n, d_outs);
-            int rc = h2d(s, d_ins, nullptr, n0, n);
-            if (rc) return rc;
-            rc = launch(n0, n, d_ins, d_outs, s.st);
-            if (rc) return rc;
-            rc = d2h_direct(s, d_outs, n0, n);
-            if (rc) return rc;
+            int rc;
+            if (!relay) {
+                rc = h2d(s, d_ins, nullptr, n0, n);
+                if (rc) return rc;
+                rc = launch(n0, n, d_ins, d_outs, s.st);
+                if (rc) return rc;
+                rc = d2h_direct(s, d_outs, n0, n);
+                if (rc) return rc;
+                GPE_CUDA_TRY(cudaEventRecord(s.done, s.st));
+            } else {
+                // Host traffic of this device rides the partner's PCIe link: host -> partner (H2D on the partner's stream)
+                // -> NVLink peer copy -> kernels here -> NVLink peer copy -> partner -> host.
+                void *r_ins[kMaxIo], *r_outs[kMaxIo];
+                carve(relay->r_in[which], nullptr, ins, nin, nullptr, nin, n, r_ins);
+                carve(relay->r_out[which], nullptr, outs, nout, order, nout, n, r_outs);
+                cudaStream_t rst = relay->st[which];
+                GPE_CUDA_TRY(cudaSetDevice(relay->partner));
+                for (int i = 0; i < nin; ++i)
+                    GPE_CUDA_TRY(cudaMemcpyAsync(r_ins[i], (const char*)ins[i].host + (size_t)n0 * ins[i].width * ES,
+                                                 (size_t)n * ins[i].width * ES, cudaMemcpyHostToDevice, rst));
+                GPE_CUDA_TRY(cudaEventRecord(relay->ev_in[which], rst));
+                GPE_CUDA_TRY(cudaSetDevice(device));
+                GPE_CUDA_TRY(cudaStreamWaitEvent(s.st, relay->ev_in[which], 0));
+                GPE_CUDA_TRY(cudaMemcpyPeerAsync(s.d_in, device, relay->r_in[which], relay->partner, io_bytes(ins, nin, n, ES, false), s.st));
+                rc = launch(n0, n, d_ins, d_outs, s.st);
+                if (rc) return rc;
+                GPE_CUDA_TRY(cudaMemcpyPeerAsync(relay->r_out[which], relay->partner, s.d_out, device, io_bytes(outs, nout, n, ES, true), s.st));
+                GPE_CUDA_TRY(cudaEventRecord(relay->ev_out[which], s.st));
+                GPE_CUDA_TRY(cudaSetDevice(relay->partner));
+                GPE_CUDA_TRY(cudaStreamWaitEvent(rst, relay->ev_out[which], 0));
+                for (int i = 0; i < nout; ++i)
+                    if (outs[i].host)
+                        GPE_CUDA_TRY(cudaMemcpyAsync((char*)outs[i].host + (size_t)n0 * outs[i].width * ES, r_outs[i],
+                                                     (size_t)n * outs[i].width * ES, cudaMemcpyDeviceToHost, rst));
+                GPE_CUDA_TRY(cudaEventRecord(relay->done[which], rst));
+                GPE_CUDA_TRY(cudaSetDevice(device));
+            }
             which ^= 1;
         }
-        for (int i = 0; i < 2; ++i) if (used[i]) GPE_CUDA_TRY(cudaStreamSynchronize(slots[i].st));
+        for (int i = 0; i < 2; ++i)
+            if (used[i]) GPE_CUDA_TRY(cudaEventSynchronize(relay ? relay->done[i] : slots[i].done));
         return GPE_OK;
     }
 

@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "gpe_math.cuh"
 #include "gpe_ptx.cuh"
 
@@ -52,7 +53,6 @@ struct FullParams {
     int nstage;     // ring depth (<= 8)
     int lag;        // refill distance behind the consumer (1 or 2, < nstage)
     int JC;         // training points per phase-A chunk (multiple of 4)
-    int alias_x;    // 1: the chunk buffer overlays the B-operand ring (2-CTA/SM configuration)
     int symmetric;  // 1: s_tiled holds the upper-triangular fold of invQ (opt-in, half the DMMAs)
     int nchunks;
     double b;       // signal variance exp(theta[D])
@@ -71,6 +71,19 @@ struct FullParams {
     double sqrt_w[kMaxD];
     double centre[kMaxD];  // c_d of the centred coordinates (HESS variants)
 };
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for_impl(F& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for_impl<I + 1, N>(f);
+    }
+}
+// f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N - 1>), in order
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F f) {
+    static_for_impl<0, N>(f);
+}
 
 template <int MT, int NT, int WR, int WC, int DP, int MINB, int KB, bool FULLNT, bool SYM, bool HESS>
 __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullParams p) {
@@ -129,11 +142,22 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     // ring iterations per tile: [0, nit_b) stream invQ for phase B, [nit_b, nit_tot) stream P for phase C
     const int nit_b = want_var ? p.nit : 0;
     const int nit_tot = nit_b + (want_hess ? p.nit_h : 0);
-    const bool alias_x = p.alias_x != 0;
     // bulk copies need 16-byte aligned sources; row blocks of full tiles are multiples of 64 bytes
     const bool ts_tma_ok = (reinterpret_cast<uintptr_t>(p.testing) & 15) == 0;
     const uint32_t ts_tile_bytes = (uint32_t)TN * D * 8u;
 
+    {   // every buffer of the carve-up must lie inside the dynamic shared memory of this launch
+        uint32_t ext = umax2(p.off_bar + 192u, p.off_sqw + 256u);
+        ext = umax2(ext, p.off_ks + (uint32_t)TN * (uint32_t)pitch * 8u);
+        ext = umax2(ext, p.off_ts + 2u * p.ts_bytes);
+        ext = umax2(ext, umax2((uint32_t)TN * (uint32_t)DV * 8u, ts_tile_bytes) + p.off_ts + p.ts_bytes);
+        if (GH > 1) ext = umax2(ext, p.off_pa + (uint32_t)GH * TN * (uint32_t)DV * 8u);
+        ext = umax2(ext, p.off_vred + (uint32_t)WC * TN * 8u);
+        if (want_hess) ext = umax2(ext, p.off_hts + (uint32_t)TN * (uint32_t)D * 8u);
+        if (nit_tot > 0) ext = umax2(ext, p.off_bst + (uint32_t)nstage * p.stage_bytes);
+        ext = umax2(ext, p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u);
+        smem_guard(ext);
+    }
     // ---- one-time setup -------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) {
@@ -250,7 +274,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
         GPE_TRACE(0);
         // (16-point tiles keep the B-operand burst here, before the row wait: see kLateChores below)
-        if (!kLateChores && nit_tot > 0 && !alias_x && tid == 0) issue_burst();
+        if (!kLateChores && nit_tot > 0 && tid == 0) issue_burst();
 
         // ---- this tile's test rows: prefetched by TMA during the previous tile, or loaded in-line ------------
         if (rows_prefetched(tile)) {
@@ -287,9 +311,8 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         __syncthreads();  // ts_s is reused as the output staging area below; the other buffer is free for prefetch
         // Two serial chores, ~0.5 k and ~0.3 k cycles each, given to lane 0 of two different warps AFTER the barrier so
         // that nobody waits for them (they overlap the other warps' phase A): the B-operand burst for this tile's
-        // contraction (lands while phase A runs, unless the ring shares its buffer with the chunk), and the TMA
-        // prefetch of the next tile's test rows.
-        if (kLateChores && nit_tot > 0 && !alias_x && tid == 0) issue_burst();
+        // contraction (lands while phase A runs), and the TMA prefetch of the next tile's test rows.
+        if (kLateChores && nit_tot > 0 && tid == 0) issue_burst();
         {
             const int64_t next = tile + gridDim.x;
             if (tid == ((kLateChores && NW > 1) ? 32 : 0) && next < ntiles) prefetch_rows(next, buf ^ 1);
@@ -310,7 +333,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 }
                 mbar_wait(bar_x, xpar);
                 xpar ^= 1;
-                if (p.nchunks == 1 && !alias_x) x_resident = true;
+                if (p.nchunks == 1) x_resident = true;
             }
             const int jn = min(p.JC, M - c * p.JC);
             const double* al = Xc + p.JC * DP;
@@ -367,7 +390,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                     }
                 }
             }
-            if (!x_resident) __syncthreads();  // all reads of Xc done before the next chunk (or the ring) lands
+            if (!x_resident) __syncthreads();  // all reads of Xc done before the next chunk lands
         }
 
         GPE_TRACE(2);
@@ -407,7 +430,6 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         }
 
         GPE_TRACE(3);
-        if (alias_x && nit_tot > 0 && tid == 0) issue_burst();  // chunk buffer is dead: start the ring
         // ---- phase B: variance contraction on the FP64 tensor path --------------------------------------
         if (want_var) {
             double acc[MT][NT][2];
@@ -423,7 +445,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
 
             // KB k-blocks (4 values of the contraction index each) per ring stage, fully unrolled.  The A fragments
             // come from the K* tile, not from the ring, so they are fetched before waiting on the stage barrier.
-            for (int it = 0; it < nit_b; ++it) {
+            // One ring step with this warp's column tiles [JM, NT) (JM = 0: all of them), JM a compile-time constant so
+            // that the tile loop carries no predicate and ptxas hoists the B-fragment loads.
+            auto ring_step = [&](auto jm_c, int it) {
+                constexpr int JM = decltype(jm_c)::value;
                 refill(it);
                 const int kb0 = it * KB;
                 double a[KB][MT];
@@ -437,35 +462,35 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 for (int kk = 0; kk < KB; ++kk) {
                     if (KB == 1 || kb0 + kk < p.kblk) {
                         const double* bk = bs + kk * Mp * 4;
-                        // SYM: the B operand is the upper-triangular fold of invQ, column tile t is all zero for
-                        // k-block kb unless t >= kb / 2; this warp's tile j is t = wcol + WC j
-                        const int jmin = SYM ? ((((kb0 + kk) >> 1) - wcol + WC - 1) / WC) : 0;
-                        if (SYM) {
-                            // descending over this warp's tiles with a real (warp-uniform) exit: a predicated-off
-                            // DMMA still pays its issue stall, so predication alone saves nothing (measured)
 #pragma unroll
-                            for (int j = NT - 1; j >= 0; --j) {
-                                if (j < jmin) break;
-                                if (FULLNT || j < nt_act) {
-                                    const double bf = bk[j * (WC * 32)];
+                        for (int j = JM; j < NT; ++j) {
+                            if (!FULLNT && j >= nt_act) break;   // real exit: predicated-off DMMAs are not free
+                            const double bf = bk[j * (WC * 32)];
 #pragma unroll
-                                    for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                if (!FULLNT && j >= nt_act) break;   // real exit: predicated-off DMMAs are not free
-                                const double bf = bk[j * (WC * 32)];
-#pragma unroll
-                                for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
-                            }
+                            for (int i = 0; i < MT; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[kk][i], bf);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[cs]);
                 if (++cs == nstage) { cs = 0; cpar ^= 1; }
+            };
+            if constexpr (!SYM) {
+                for (int it = 0; it < nit_b; ++it) ring_step(std::integral_constant<int, 0>{}, it);
+            } else {
+                // SYM: the B operand is the upper-triangular fold of invQ: column tile t is all zero for k-block kb unless
+                // t >= kb / 2, and this warp's tile j is t = wcol + WC j.  So its first active tile JM(it) =
+                // ceil((t0 - wcol) / WC), t0 = (it KB) / 2, grows by one every 2 WC / KB ring steps: the loop over the ring
+                // is cut into NT runs, each compiled for its own fixed tile range (the earlier version tested
+                // `j < jmin` inside one unrolled loop and ran at 70 % of the halved work).
+                int it = 0;
+                static_for<NT>([&](auto jm_c) {
+                    constexpr int JM = decltype(jm_c)::value;
+                    const int it_end = min(nit_b, (WC * JM + wcol + 1) * (2 / KB));
+                    for (; it < it_end; ++it) ring_step(jm_c, it);
+                });
+                // past this warp's last tile it only keeps the ring moving (barrier waits, arrivals, its refill turns)
+                for (; it < nit_b; ++it) ring_step(std::integral_constant<int, NT>{}, it);
             }
 
             GPE_TRACE(4);
@@ -585,7 +610,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             }
             GPE_TRACE(7);
         }
-        __syncthreads();  // K*, outs, vred (and the ring, if it doubles as chunk buffer) are free for the next tile
+        __syncthreads();  // K*, outs, vred are free for the next tile
         if (!(HESS && want_hess)) GPE_TRACE(5);
         ++trace_tile;
     }

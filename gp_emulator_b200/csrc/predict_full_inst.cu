@@ -29,7 +29,7 @@ static cudaError_t launch_cfg(const FullParams& p, int grid, size_t smem, cudaSt
                                : k_predict_full<MT, NT, WR, WC, GPE_DP, MINB, KB, false, false, false>;
     }
 #if GPE_DP <= 16
-    // fused Hessian variants (gpemu.cu only asks for them when cfg <= 2 and the model is not symmetric-folded)
+    // fused Hessian variants (gpemu.cu only asks for them when the model is not symmetric-folded)
     if (p.hess != nullptr) {
         if (p.symmetric || MINB != 1 || WR * WC != 8) return cudaErrorInvalidValue;
         if constexpr (MINB == 1 && WR * WC == 8) {
@@ -81,8 +81,6 @@ cudaError_t GPE_CAT(launch_full_dp, GPE_DP)(int cfg, const FullParams& p, int gr
                 case 15: return launch_cfg<2, 15, 1, 8, 1, 1, true>(p, grid, smem, st);
                 default: return launch_cfg<2, 16, 1, 8, 1, 1, false>(p, grid, smem, st);
             }
-        case 3: return launch_cfg<4, 8, 1, 4, 2, 1, false>(p, grid, smem, st);   // TN = 32, Mp <= 256, 4 warps, 2 CTAs/SM
-        case 4: return launch_cfg<4, 4, 2, 8, 1, 1, false>(p, grid, smem, st);   // TN = 64, Mp <= 256, 16 warps, 1 CTA/SM
         default: return cudaErrorInvalidValue;
     }
 }

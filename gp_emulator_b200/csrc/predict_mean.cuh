@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gpe_math.cuh"
+#include "gpe_ptx.cuh"
 
 namespace gpe {
 
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M, DV = D + 1;
+    smem_guard(umax2(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)DV * 8u),
+                     HESS ? p.off_out + (uint32_t)TN * (uint32_t)(D * D) * 8u : 0u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
     exp_tab_load(exp_tab, tid);   // visible after the barrier at the first tile start
     const int g_low = lane & 7, n_a = warp * 8 + (lane >> 3), n_b = n_a + 4;
     const int D = p.D, M = p.M, DV = D + 1;
+    smem_guard(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)DV * 8u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
@@ -375,6 +379,8 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
     exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M;
+    smem_guard(umax2(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)D * 8u),
+                     p.off_out + (uint32_t)TN * HR * (uint32_t)D * 8u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];

@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(kTfThreads, 1) k_predict_tf32_big(const Tf32Bi
     const int npass = (Mp + PW - 1) / PW;
     const int64_t ntiles = (p.N + TN - 1) / TN;
     const bool want_var = p.var != nullptr;
+    // the carve-up is ascending: barriers, TMEM slot, A, B ring, training set, output staging, variance partials
+    smem_guard(umax2(umax2(p.off_vred + 2u * TN * 4u, p.off_out + (uint32_t)TN * (uint32_t)DV * 4u),
+                     umax2(p.off_x + (uint32_t)Mp * (uint32_t)(DP + 1) * 4u, p.off_b + 2u * p.bstage_bytes)));
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {

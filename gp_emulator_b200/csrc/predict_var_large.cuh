@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kVlWarps * 32, 1) k_var_large(const VarLargePa
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nstage = p.nstage;
     const int lag = (nstage >= 3) ? 2 : 1;
+    smem_guard(128u + NW * kVlTN * 8u + (uint32_t)nstage * kVlStageBytes);
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) {
             mbar_init(&bar_full[s], 1);

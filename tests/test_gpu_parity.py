@@ -1171,3 +1171,57 @@ def test_red_zones_around_every_output(gpemu):
             assert _guards_intact(b, v.numel()), (M, D, E, W, N, k)
             assert bool(torch.isfinite(v).all()), (M, D, E, W, N, k)
         bank.close()
+
+
+def test_multi_device_nvlink_relay_of_host_traffic(lib, gpemu, monkeypatch):
+    """gpe_multi_predict can send a device's host traffic through a partner's PCIe link (host -> partner -> NVLink ->
+    device -> NVLink -> partner -> host) when its own link is measured to be much slower; forced here
+    (GPE_MULTI_RELAY=force: first half of the device list relays through the second half).  Bit-identical results."""
+    import torch
+    ndev = lib.gpe_device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    inputs, theta, invQ, invQt, _ = orc.make_S_model(250, 10, 1, seed=21)
+    N = 700_001
+    t = torch.rand(N, 10, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).pin_memory().numpy()
+    out = {k: torch.empty(s, dtype=torch.float64).pin_memory().numpy() for k, s in
+           (("mu", (N,)), ("var", (N,)), ("deriv", (N, 10)))}
+    ref = gpemu.DeviceModel(inputs, theta, invQt, invQ).predict(t)
+    monkeypatch.setenv("GPE_MULTI_RELAY", "force")
+    mm = gpemu.MultiDeviceModel(inputs, theta, invQt, invQ, devices=devices)
+    for _ in range(2):
+        for v in out.values():
+            v.fill(np.nan)
+        got = mm.predict(t, out=out)
+        for k in ("mu", "var", "deriv"):
+            assert np.array_equal(got[k], ref[k]), k
+    mm.close()
+    monkeypatch.setenv("GPE_MULTI_RELAY", "off")
+    mm = gpemu.MultiDeviceModel(inputs, theta, invQt, invQ, devices=devices)
+    got = mm.predict(t, out=out)
+    for k in ("mu", "var", "deriv"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_smem_guard_traps():
+    """Every kernel checks at entry that the host's shared-memory carve-up fits the dynamic shared memory of the launch.
+    Launching the fused kernel with 4 KB less than its plan (dev switch) must fail loudly, not corrupt memory; in a
+    subprocess, because a trapped kernel poisons the CUDA context."""
+    import os
+    import subprocess
+    import sys
+    code = ("import numpy as np, gp_emulator_b200 as g\n"
+            "from oracle import gp_oracle as orc\n"
+            "i, th, Q, a, t = orc.make_S_model(250, 10, 500, seed=1)\n"
+            "m = g.DeviceModel(i, th, a, Q)\n"
+            "try:\n"
+            "    m.predict(t)\n"
+            "    print('NO-ERROR')\n"
+            "except g.GpemuError as e:\n"
+            "    print('TRAPPED', e)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GPE_DEBUG_SHRINK_SMEM="4096", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert "TRAPPED" in r.stdout and "NO-ERROR" not in r.stdout, (r.stdout, r.stderr[-500:])
+    env.pop("GPE_DEBUG_SHRINK_SMEM")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert "NO-ERROR" in r.stdout, (r.stdout, r.stderr[-500:])
