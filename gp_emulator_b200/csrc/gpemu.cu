@@ -314,7 +314,7 @@ int build_hessian_operand(gpe_model* m, const double* inputs, const double* invQ
     memset(m->centre, 0, sizeof(m->centre));
     m->hess_fused_ok = false;
     if (getenv("GPE_HESS_DIRECT") != nullptr) return GPE_OK;   // dev aid: always use the direct Hessian kernels
-    if (!f.valid || f.kbh < 1 || m->symmetric || f.NC > M || f.NC > f.Mp) return GPE_OK;
+    if (!f.valid || f.kbh < 1 || f.NC > M || f.NC > f.Mp) return GPE_OK;
     double r2max = 0.0;
     for (int d = 0; d < D; ++d) {
         double lo = inputs[d], hi = inputs[d];
@@ -353,7 +353,9 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     // the Hessian rides on the fused kernel when the model qualifies (build_hessian_operand); without a variance
     // request that only pays for the 64-point tiles of cfg 0 (measured: 4.6e8 vs 3.6e8 points/s at M = 250, but
     // 0.98e8 vs 1.10e8 at M = 1000), so larger M keeps the direct kernel for Hessian-only calls
-    const bool fuse_hess = hess != nullptr && m->hess_fused_ok && (var != nullptr || m->full.cfg == 0);
+    // (the HESS variants are built on the plain variance operand: with a symmetric-folded model the Hessian only rides
+    // along when no variance is requested -- phase B is then skipped and the fold does not matter)
+    const bool fuse_hess = hess != nullptr && m->hess_fused_ok && (var != nullptr ? !m->symmetric : m->full.cfg == 0);
     if (var != nullptr && m->has_invQ && !m->full.valid && m->large_valid) {
         // 1024 < M <= GPE_MAX_TRAIN: per sub-batch, K* + mean + gradient (k_predict_mean2<DP, true>) into the scratch,
         // then the column-pass contraction (k_var_large).  The scratch is per model: streams take turns.
@@ -402,7 +404,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
         p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
         p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk;
-        p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1; p.symmetric = m->symmetric ? 1 : 0;
+        p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1; p.symmetric = (m->symmetric && var != nullptr) ? 1 : 0;
         if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1));
         p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
@@ -533,119 +535,8 @@ int model_stream(gpe_model* m, const double* testing, int64_t N, double* mu, dou
                        }, relay);
 }
 
-// ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W), A addressed with three strides ------------
-// A skinny FP64 GEMM (K = E <= 32) whose output write is the HBM-bound part (W = 2101 doubles per row) and whose
-// 2 E W flop per row sit right at the FP64 ridge, so it runs on the FP64 tensor path.  CTA = 64 rows, 8 warps as
-// 2 (rows) x 4 (columns); a warp keeps its A fragments (32 rows x E) in registers for the whole sweep over W and
-// produces 32 x 32 output tiles with DMMA.8x8x4.  The basis is pre-tiled at bank creation as [ks][Wp][4]
-// (b_tiled[ks][w][c] = basis[4 ks + c][w], zero padded), the same conflict-free B-fragment image the variance
-// kernel uses, streamed in 128-column groups by TMA bulk copies through a two-stage mbarrier ring.  Output tiles
-// go through a per-warp smem buffer (16 rows x pitch 40 doubles = conflict-free 16-byte fragment stores) so
-// every global store instruction writes 256 contiguous bytes of one output row (rows are only 8-byte aligned:
-// W is odd).  Two CTAs per SM (<= 128 registers, 80 KB smem) so that one CTA's store burst drains -- HBM absorbs
-// ~25 B/clk per SM -- while the other's DMMAs run; ncu showed the single-CTA version lg_throttle-bound.
-constexpr int kProjThreads = 256, kProjRows = 64, kProjCols = 128;
-constexpr int kProjPitch = 40;  // doubles; = 8 (mod 16) so a quarter-warp's 16-byte fragment stores hit 32 banks
-template <int KS>   // k-steps of 4: E <= 4 KS
-__global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
-                                                             int64_t lde, int64_t ldd, const double* __restrict__ b_tiled,
-                                                             int E, int W, int Wp, double* __restrict__ out, int accumulate) {
-    extern __shared__ __align__(128) unsigned char psm[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(psm);          // [2]
-    double* stage = reinterpret_cast<double*>(psm + 128);       // [2][KS][128][4]
-    double* ctile = stage + 2 * (size_t)KS * kProjCols * 4;     // [8 warps][16][kProjPitch]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = warp >> 2, wc = warp & 3;
-    smem_guard(128u + 2u * KS * kProjCols * 4u * 8u + 8u * 16u * kProjPitch * 8u);
-    const int64_t r0 = (int64_t)blockIdx.x * kProjRows + wr * 32;
-    const int ngroups = Wp / kProjCols;
-    constexpr uint32_t ks_bytes = kProjCols * 4 * 8, stage_doubles = (uint32_t)KS * kProjCols * 4;
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto load_group = [&](int g, int st) {   // thread 0
-        mbar_arrive_expect_tx(&full[st], (uint32_t)KS * ks_bytes);
-        for (int ks = 0; ks < KS; ++ks)
-            tma_bulk_g2s(stage + (size_t)st * stage_doubles + (size_t)ks * kProjCols * 4,
-                         b_tiled + ((size_t)ks * Wp + (size_t)g * kProjCols) * 4, ks_bytes, &full[st]);
-    };
-    if (tid == 0) {
-        load_group(0, 0);
-        if (ngroups > 1) load_group(1, 1);
-    }
-    // A fragments: lane holds A[row = 8 i + lane / 4][k = 4 ks + lane % 4]
-    double a[4][KS];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t r = r0 + 8 * i + (lane >> 2);
-        const int64_t base = (r < R) ? (r / RD) * ldn + (r % RD) * ldd : 0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int e = 4 * ks + (lane & 3);
-            a[i][ks] = (r < R && e < E) ? A[base + (int64_t)e * lde] : 0.0;
-        }
-    }
-    const int nrow = (int)max((int64_t)0, min((int64_t)32, R - r0));
-    double* ct = ctile + (size_t)warp * (16 * kProjPitch);
-    uint32_t par = 0;
-    for (int g = 0; g < ngroups; ++g) {
-        const int st = g & 1;
-        mbar_wait(&full[st], (par >> st) & 1u);
-        par ^= 1u << st;
-        const double* bs = stage + (size_t)st * stage_doubles + (size_t)(wc * 32 + (lane >> 2)) * 4 + (lane & 3);
-        double acc[4][4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double bf = bs[(size_t)ks * kProjCols * 4 + j * 32];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i][ks], bf);
-            }
-        }
-        const int w = g * kProjCols + wc * 32 + lane;
-        double* o = out + r0 * W + w;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {   // rows 0..15, then 16..31 of the warp tile
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<double2*>(ct + (8 * i + (lane >> 2)) * kProjPitch + 8 * j + 2 * (lane & 3)) =
-                        make_double2(acc[2 * half + i][j][0], acc[2 * half + i][j][1]);
-            __syncwarp();
-            if (w < W) {
-#pragma unroll 4
-                for (int rr = 0; rr < 16; ++rr)
-                    if (16 * half + rr < nrow) {
-                        double* q = o + (int64_t)(16 * half + rr) * W;
-                        *q = accumulate ? *q + ct[rr * kProjPitch + lane] : ct[rr * kProjPitch + lane];   // (slices of E > 32)
-                    }
-            }
-        }
-        __syncthreads();   // every warp is done with this stage: refill it with group g + 2
-        if (tid == 0 && g + 2 < ngroups) load_group(g + 2, st);
-    }
-}
-
-template <int KS>
-cudaError_t launch_project(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd,
-                           const double* b_tiled, int E, int W, int Wp, double* out, int accumulate, cudaStream_t st) {
-    const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 8 * 16 * kProjPitch * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_project<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-    if (e != cudaSuccess) return e;
-    k_project<KS><<<(unsigned)((R + kProjRows - 1) / kProjRows), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd,
-                                                                                          b_tiled, E, W, Wp, out, accumulate);
-    return cudaGetLastError();
-}
+// ---- PCA back-projection: out (R, W) = A (R, E) . basis (E, W): kernels and launcher in project.cu ----------------
+constexpr int kProjCols = 128;   // columns per group of the pre-tiled basis image (project.cu)
 
 // ---- single-precision (tcgen05 / TF32) path ------------------------------------------------------------------
 uint32_t host_tf32_rna(float x) {   // round-to-nearest (ties away) to 10 mantissa bits, as cvt.rna.tf32.f32
@@ -1034,7 +925,7 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
     if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient,
                       // and the Hessian when every emulator qualifies for the fused Hessian)
         bool fuse_hess = hess != nullptr;
-        for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok;
+        for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok && !b->models[e]->symmetric;
         for (int64_t e = 0; e < E; ++e) {
             int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var + e, deriv ? deriv + e * D : nullptr,
                                     fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream);
@@ -1086,14 +977,10 @@ int bank_project_device(gpe_bank* b, const double* mu, const double* deriv, int6
     const int E = b->E, D = b->D, W = b->W;
     auto run = [&](const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, double* o) -> cudaError_t {
         for (int e0 = 0; e0 < E; e0 += 32) {
-            const int Es = std::min(32, E - e0), ks = (Es + 3) / 4, acc = e0 > 0;
-            const double* As = A + (int64_t)e0 * lde;
-            const double* bt = b->d_basis + (size_t)(e0 / 4) * b->Wp * 4;
+            const int Es = std::min(32, E - e0);
             g_launches.fetch_add(1);
-            cudaError_t e;
-            if (ks <= 3) e = launch_project<3>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
-            else if (ks <= 5) e = launch_project<5>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
-            else e = launch_project<8>(As, R, RD, ldn, lde, ldd, bt, Es, W, b->Wp, o, acc, st);
+            cudaError_t e = project_rows(A + (int64_t)e0 * lde, R, RD, ldn, lde, ldd, b->d_basis + (size_t)(e0 / 4) * b->Wp * 4, Es, W,
+                                         b->Wp, o, e0 > 0, st);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;

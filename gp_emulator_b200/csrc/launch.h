@@ -27,6 +27,10 @@ GPE_DECL_DP(32)
 cudaError_t launch_tf32(int DP, bool x3, const Tf32Params& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_tf32_big(int DP, bool x3, const Tf32BigParams& p, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_var_large(const VarLargeParams& p, int grid, size_t smem, cudaStream_t st);
+// out (R, W) [+]= A (R, E <= 32) . basis, basis pre-tiled as [ks][Wp][4]; row r of A at (r / RD) ldn + (r % RD) ldd, element e
+// at + e lde (project.cu)
+cudaError_t project_rows(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, const double* b_tiled, int E,
+                         int W, int Wp, double* out, int accumulate, cudaStream_t st);
 static const int kTfDpList[] = {4, 8, 12, 16, 32};
 
 // padded input dimensions that have compiled kernels, ascending

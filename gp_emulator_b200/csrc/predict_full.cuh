@@ -220,12 +220,16 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             }
         }
     };
-    auto issue_burst = [&]() {
-        int s = cs;
+    // start-of-tile burst: iteration i of the tile goes to stage (cs + i) % nstage, issued by lane 0 of warp i % NW (one
+    // thread doing all of them kept its warp ~100 cycles per stage behind the others: 0.8 k cycles per tile with 8 stages)
+    auto issue_burst = [&]() {   // called by every thread
         const int burst = min(nstage, nit_tot);
-        for (int i = 0; i < burst; ++i) {
-            issue(s, i);
-            if (++s == nstage) s = 0;
+        if (lane == 0) {
+            for (int i = warp; i < burst; i += NW) {
+                int s = cs + i;
+                if (s >= nstage) s -= nstage;
+                issue(s, i);
+            }
         }
     };
     auto refill = [&](int it) {   // called by every thread at the top of ring iteration `it` of the tile
@@ -259,7 +263,11 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     const int n_hi = warp % NHI, g_hi = warp / NHI;
     const int n_a = n_hi * 8 + n_low, n_b = n_a + 4;
     // phase-B warp coordinates
-    const int wrow = warp / WC, wcol = warp % WC;
+    // SYM: the fold leaves column warp c with fewer active tiles than column warp c + 1, and warp w runs on SM
+    // sub-partition w % 4 -- so every second group of four warps takes the column-warp indices in mirrored order, which
+    // gives each sub-partition (each DMMA pipe) the same number of active tiles in every ring step
+    const int wrow = warp / WC;
+    const int wcol = (SYM && ((warp >> 2) & 1)) ? (((warp % WC) & ~3) | (3 - ((warp % WC) & 3))) : warp % WC;
     const int nt_act = FULLNT ? NT : p.nt_act;  // FULLNT: every column tile active, no predicates around the DMMAs
 
     int buf = 0;
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         double* ts_s = reinterpret_cast<double*>(smem + p.off_ts + (size_t)buf * p.ts_bytes);
         GPE_TRACE(0);
         // (16-point tiles keep the B-operand burst here, before the row wait: see kLateChores below)
-        if (!kLateChores && nit_tot > 0 && tid == 0) issue_burst();
+        if (!kLateChores && nit_tot > 0) issue_burst();
 
         // ---- this tile's test rows: prefetched by TMA during the previous tile, or loaded in-line ------------
         if (rows_prefetched(tile)) {
@@ -312,10 +320,10 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         // Two serial chores, ~0.5 k and ~0.3 k cycles each, given to lane 0 of two different warps AFTER the barrier so
         // that nobody waits for them (they overlap the other warps' phase A): the B-operand burst for this tile's
         // contraction (lands while phase A runs), and the TMA prefetch of the next tile's test rows.
-        if (kLateChores && nit_tot > 0 && tid == 0) issue_burst();
+        if (kLateChores && nit_tot > 0) issue_burst();
         {
             const int64_t next = tile + gridDim.x;
-            if (tid == ((kLateChores && NW > 1) ? 32 : 0) && next < ntiles) prefetch_rows(next, buf ^ 1);
+            if (tid == ((kLateChores && NW > 4) ? 32 * (NW - 1) : 0) && next < ntiles) prefetch_rows(next, buf ^ 1);
         }
 
         GPE_TRACE(1);

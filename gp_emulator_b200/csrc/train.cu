@@ -11,9 +11,11 @@
 //   1. Z_ij = b exp(-1/2 sum_d w_d (x_id - x_jd)^2), Q = Z + noise I                      (:61-69)
 //   2. in-place block Gauss-Jordan inversion of Q without pivoting (Q is symmetric positive definite, so the
 //      pivots are the LDL^T pivots: log|Q| = sum log p_k, and a pivot <= 0 is the reference's LinAlgError from
-//      np.linalg.cholesky, :73-75).  M / 8 rank-8 updates of the whole matrix on the FP64 tensor cores
-//      (DMMA.8x8x4): M^3 FMA, 16 M^2 bytes of L2 traffic per 8 pivots.  ncu (profiles/r01_ncu_train_summary.md): bound by
-//      the dependency chain of the M / 8 block steps (stage -> 8 x 8 inverse -> coefficients -> update), not by a pipe.
+//      np.linalg.cholesky, :73-75).  NB pivots per pass (NB = 32 for M <= 256, 16 to 512, 8 beyond: what the staged
+//      pivot rows / columns / coefficients leave room for in shared memory): M / NB rank-NB updates of the whole matrix on
+//      the FP64 tensor cores (DMMA.8x8x4): M^3 FMA, 16 M^2 bytes of L2 traffic per NB pivots.  Round 1 ran NB = 8 and was
+//      bound by the dependency chain of its M / 8 block steps, each streaming the matrix through L2 once
+//      (profiles/r01_ncu_train_summary.md: DMMA pipe 15 %); NB = 32 makes 4x fewer, 4x heavier steps.
 //   3. alpha = invQ t, t.alpha, alpha.alpha, trace(invQ)                                   (:71-72, :118-121)
 //   4. g_d = -w_d/4 sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2,  g_D = 1/2 sum_ij (...) Z_ij,
 //      g_{D+1} = noise/2 (trace(invQ) - alpha.alpha)                                       (:108-122)
@@ -32,7 +34,7 @@
 
 namespace gpe {
 
-constexpr int kTrainThreads = 1024;
+constexpr int kTrainThreads = 512;    // 128 registers per thread: the rank-NB update keeps 8 accumulator tiles + 16 A fragments
 constexpr int kTrainWarps = kTrainThreads / 32;
 
 struct TrainParams {
@@ -45,7 +47,19 @@ struct TrainParams {
     double* grad;           // (B, D + 2)
     int* status;            // (B) 0 ok, 1 Q not positive definite / non-finite
     int M, D;
+    long long* trace;       // dev aid (normally null): CTA 0 adds its clock64() phase durations to trace[0..7]
 };
+
+// 1 / x for a positive, normal x without the division subroutine: hardware seed (>= 20 bits) + two Newton steps, ~60
+// cycles of latency instead of ~400 -- it sits on the critical path of every pivot of the block inverse.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -53,30 +67,32 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Sum over the CTA, result in every thread (kTrainWarps == 32: one partial per lane in the second stage).
+// Sum over the CTA, result in every thread (kTrainWarps <= 32: at most one partial per lane in the second stage).
 __device__ __forceinline__ double block_sum(double v, double* red, int lane, int wid) {
     v = warp_sum(v);
     __syncthreads();  // `red` is free again
     if (lane == 0) red[wid] = v;
     __syncthreads();
-    return warp_sum(red[lane]);
+    return warp_sum(lane < kTrainWarps ? red[lane] : 0.0);
 }
-
-constexpr int kNB = 8;  // pivots eliminated per pass over the matrix == DMMA tile edge
 
 // Work matrices are stored with pitch Mp = M rounded up to 8 and padded with the identity (Q_pad = diag(Q, I)), so
 // that every 8 x 8 tile is full: inv(Q_pad) = diag(inv(Q), I), the padded pivots are 1 and add log 1 = 0.
+// NB = pivots eliminated per pass over the matrix (8, 16 or 32; the last pass takes what is left, a multiple of 8).
+template <int NB>
 __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainParams p) {
+    constexpr int kNB = 8;            // DMMA tile edge
+    constexpr int KK = NB / 4;        // DMMA k-steps of a full pass
     extern __shared__ __align__(16) double sm[];
-    __shared__ double Ps[kNB * kNB];   // pivot block -> its inverse
+    __shared__ double Pbuf[NB * NB];   // inverse of the pivot block
     __shared__ int s_bad;
     const int M = p.M, D = p.D, Mp = (M + 7) & ~7, nb = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int un = max(M * D, 3 * kNB * Mp);
+    const int un = max(M * D, 3 * NB * Mp);
     double* xs = sm;                  // [M][D]                                    (phases 1 and 4)
-    double* RrT = sm;                 // [2][Mp][4]: RrT[kk][j][c] = A[k0 + 4 kk + c][j], the DMMA B operand (phase 2)
-    double* Cc = sm + kNB * Mp;       // [Mp][8] pivot columns, staged
-    double* CfT = sm + 2 * kNB * Mp;  // [2][Mp][4]: CfT[kk][i][c] = coef_i[4 kk + c], the DMMA A operand
+    double* RrT = sm;                 // [KK][Mp][4]: RrT[kk][j][c] = A[k0 + 4 kk + c][j], the DMMA B operand (phase 2)
+    double* Cc = sm + NB * Mp;        // [Mp][NB] pivot columns, staged
+    double* CfT = sm + 2 * NB * Mp;   // [KK][Mp][4]: CfT[kk][i][c] = coef_i[4 kk + c], the DMMA A operand
     double* tt = sm + un;             // [M] targets
     double* alpha = tt + M;           // [M]
     double* ew = alpha + M;           // [D + 2] exp(theta)
@@ -84,6 +100,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     double* A = p.work + (size_t)nb * 2 * Mp * Mp;
     double* Z = A + (size_t)Mp * Mp;
 
+    const bool tracing = p.trace != nullptr && nb == 0 && tid == 0;
+    long long tr_last = tracing ? clock64() : 0;
+#define GPE_TR(k) do { if (tracing) { const long long now_ = clock64(); p.trace[k] += now_ - tr_last; tr_last = now_; } } while (0)
     for (int i = tid; i < M * D; i += kTrainThreads) xs[i] = p.x[i];
     const double* t = p.targets + (size_t)p.tidx[nb] * M;
     for (int i = tid; i < M; i += kTrainThreads) tt[i] = t[i];
@@ -110,91 +129,164 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
         }
     __syncthreads();
 
-    // 2. block Gauss-Jordan, 8 pivots per pass.  With K the pivot index block, R = A[K, :], C = A[:, K], P = A[K, K]:
+    // 2. block Gauss-Jordan, NB pivots per pass.  With K the pivot index block, R = A[K, :], C = A[:, K], P = A[K, K]:
     //      A[K, K] <- inv(P),  A[K, J] <- inv(P) R,  A[I, K] <- -C inv(P),  A[I, J] <- A[I, J] - C inv(P) R
     //    i.e. every row i becomes  base_i + coef_i . R  with coef_i = inv(P)[i - k0, :] and base 0 for the pivot rows,
     //    coef_i = -C[i, :] inv(P) and base A[i, :] otherwise, except in the pivot columns where the new value is
-    //    coef_i[j - k0].  That rank-8 update of the whole matrix runs on the FP64 tensor cores: per 8 x 8 tile two
-    //    DMMA.8x8x4 with the accumulator fragment loaded from / stored to the L2-resident matrix (16 bytes per lane,
-    //    64 contiguous bytes per row), operands pre-arranged in shared memory in fragment order (conflict-free).
-    //    inv(P) by scalar Gauss-Jordan inside the block (warp 0): its pivots are the LDL^T pivots of Q.
+    //    coef_i[j - k0].  That rank-NB update of the whole matrix runs on the FP64 tensor cores: per 8 x 8 tile NB / 4
+    //    DMMA.8x8x4 with the accumulator fragment loaded from / stored to the L2-resident matrix ONCE per pass (16 bytes
+    //    per lane, 64 contiguous bytes per row), operands pre-arranged in shared memory in fragment order
+    //    (conflict-free); a warp owns two row tiles and half of the column tiles, so every B fragment it pulls from
+    //    shared memory feeds two DMMAs.  inv(P) by scalar Gauss-Jordan inside the block (warp 0, entries in registers):
+    //    its pivots are the LDL^T pivots of Q.
     double logdet = 0.0;
     bool bad = false;
     const int g = lane >> 2, c4 = lane & 3, ntile = Mp / kNB;
-    for (int k0 = 0; k0 < Mp; k0 += kNB) {
-        for (int e = tid; e < kNB * Mp; e += kTrainThreads) {
+    GPE_TR(0);   // [0] inputs + covariance
+    for (int k0 = 0; k0 < Mp; k0 += NB) {
+        const int nbk = min(NB, Mp - k0);     // pivots of this pass (multiple of 8)
+        const int kkn = nbk >> 2;             // its DMMA k-steps
+        for (int e = tid; e < nbk * Mp; e += kTrainThreads) {
             const int a = e / Mp, j = e - a * Mp;
             RrT[(a >> 2) * Mp * 4 + j * 4 + (a & 3)] = A[(k0 + a) * Mp + j];
         }
-        for (int e = tid; e < Mp * kNB; e += kTrainThreads) Cc[e] = A[(e >> 3) * Mp + k0 + (e & 7)];
+        for (int e = tid; e < Mp * NB; e += kTrainThreads) {
+            const int i = e / NB, a = e % NB;
+            if (a < nbk) Cc[e] = A[i * Mp + k0 + a];
+        }
         __syncthreads();
+        GPE_TR(1);   // [1] staging of pivot rows / columns
+        // inv(P) by scalar Gauss-Jordan in the registers of warp 0: the 32 lanes form a 4 x 8 grid, lane (lr, lc) owns the
+        // (NB/4) x (NB/8) sub-block of rows lr NB/4 + i, columns lc NB/8 + j.  Pivot step k needs the pivot, row k
+        // restricted to the lane's columns and column k restricted to its rows: 1 + NB/8 + NB/4 shuffles (13 for NB = 32),
+        // no shared memory and no barrier inside the 32-step dependency chain (the first blocked version kept the block in
+        // shared memory with one CTA barrier per pivot: 690 cycles per pivot, 15 % of the kernel).  The pivots are the
+        // LDL^T pivots of Q; their logarithms are taken after the loop, one per lane.
         if (wid == 0) {
-            // lane owns block entries (a0, b) and (a0 + 4, b)
-            const int a0 = lane >> 3, a1 = a0 + 4, b = lane & 7;
-            double v0 = RrT[(k0 + b) * 4 + a0];                  // A[k0 + a0][k0 + b]
-            double v1 = RrT[Mp * 4 + (k0 + b) * 4 + a0];         // A[k0 + a0 + 4][k0 + b]
-            Ps[a0 * kNB + b] = v0;
-            Ps[a1 * kNB + b] = v1;
-            __syncwarp();
+            constexpr int RB = NB / 4, CB = NB / 8;
+            const int lr = lane >> 3, lc = lane & 7;
+            double v[RB][CB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    const int ra = lr * RB + i, cb = lc * CB + j;
+                    v[i][j] = (ra < nbk && cb < nbk) ? RrT[(ra >> 2) * Mp * 4 + (k0 + cb) * 4 + (ra & 3)] : ((ra == cb) ? 1.0 : 0.0);
+                }
             bool wbad = false;
-            double mypiv = 1.0;   // lane k keeps pivot k: the logarithms are taken after the loop, in parallel
-            for (int k = 0; k < kNB; ++k) {
-                const double piv = Ps[k * kNB + k];
-                if (!(piv > 0.0) || !(piv < 1e300)) { wbad = true; break; }   // same value in every lane
-                const double ip = 1.0 / piv;
-                const double r = Ps[k * kNB + b], c0 = Ps[a0 * kNB + k] * ip, c1 = Ps[a1 * kNB + k] * ip;
-                __syncwarp();
-                v0 = (a0 == k) ? ((b == k) ? ip : r * ip) : ((b == k) ? -c0 : fma(-c0, r, v0));
-                v1 = (a1 == k) ? ((b == k) ? ip : r * ip) : ((b == k) ? -c1 : fma(-c1, r, v1));
-                Ps[a0 * kNB + b] = v0;
-                Ps[a1 * kNB + b] = v1;
-                if (lane == k) mypiv = piv;
-                __syncwarp();
+            double mypiv = 1.0;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                if (k < nbk && !wbad) {   // warp-uniform
+                    constexpr unsigned full = 0xffffffffu;
+                    const int kr = k / RB, ki = k % RB, kc = k / CB, kj = k % CB;
+                    const double piv = __shfl_sync(full, v[ki][kj], kr * 8 + kc);
+                    if (!(piv > 0.0) || !(piv < 1e300)) {
+                        wbad = true;
+                    } else {
+                        const double ip = fast_rcp(piv);     // piv in (0, 1e300): within an ulp or two of 1 / piv
+                        double r[CB], c[RB];
+#pragma unroll
+                        for (int j = 0; j < CB; ++j) r[j] = __shfl_sync(full, v[ki][j], kr * 8 + lc);        // P[k][my columns]
+#pragma unroll
+                        for (int i = 0; i < RB; ++i) c[i] = __shfl_sync(full, v[i][kj], lr * 8 + kc) * ip;   // P[my rows][k] / p
+#pragma unroll
+                        for (int i = 0; i < RB; ++i)
+#pragma unroll
+                            for (int j = 0; j < CB; ++j) {
+                                const bool in_row = (lr == kr) && (i == ki), in_col = (lc == kc) && (j == kj);
+                                v[i][j] = in_row ? (in_col ? ip : r[j] * ip) : (in_col ? -c[i] : fma(-c[i], r[j], v[i][j]));
+                            }
+                        if (lane == (k & 31)) mypiv = piv;
+                    }
+                }
             }
-            if (wbad) {
-                if (lane == 0) s_bad = 1;
-            } else {
-                logdet += warp_sum(lane < kNB ? log(mypiv) : 0.0);
-            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int j = 0; j < CB; ++j) Pbuf[(lr * RB + i) * NB + lc * CB + j] = v[i][j];
+            if (wbad) s_bad = 1;
+            else logdet += warp_sum(lane < nbk ? log(mypiv) : 0.0);
         }
         __syncthreads();
         if (s_bad) { bad = true; break; }   // uniform
-        for (int e = tid; e < Mp * kNB; e += kTrainThreads) {
-            const int i = e >> 3, bq = e & 7;
-            double s = 0.0;
+        const double* Ps = Pbuf;
+        GPE_TR(2);   // [2] pivot-block inverse
+        {   // coefficients: lane <-> column bq of inv(P) (kept in registers), 32 / NB rows per warp and sweep; the row of
+            // pivot-column entries is read with 16-byte broadcast loads (the first version re-read inv(P) from shared
+            // memory for every product and was bound by the shared-memory pipe)
+            constexpr int RPW = 32 / NB;
+            const int bq = lane % NB, sub = lane / NB;
+            double pc[NB];
 #pragma unroll
-            for (int a = 0; a < kNB; ++a) s = fma(Cc[i * kNB + a], Ps[a * kNB + bq], s);
-            const bool prow = (i & ~7) == k0;
-            CfT[(bq >> 2) * Mp * 4 + i * 4 + (bq & 3)] = prow ? Ps[(i & 7) * kNB + bq] : -s;
+            for (int a = 0; a < NB; ++a) pc[a] = (a < nbk) ? Ps[a * NB + bq] : 0.0;
+            for (int i = wid * RPW + sub; i < Mp; i += kTrainWarps * RPW) {
+                const double2* crow = reinterpret_cast<const double2*>(Cc + i * NB);
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int a2 = 0; a2 < NB / 2; ++a2) {
+                    if (2 * a2 < nbk) {        // (nbk is a multiple of 8: whole pairs)
+                        const double2 cv = crow[a2];
+                        s0 = fma(cv.x, pc[2 * a2], s0);
+                        s1 = fma(cv.y, pc[2 * a2 + 1], s1);
+                    }
+                }
+                const bool prow = i >= k0 && i < k0 + nbk;
+                if (bq < nbk) CfT[(bq >> 2) * Mp * 4 + i * 4 + (bq & 3)] = prow ? Ps[(i - k0) * NB + bq] : -(s0 + s1);
+            }
         }
         __syncthreads();
-        for (int rt = wid; rt < ntile; rt += kTrainWarps) {
-            const int i0 = rt * kNB;
-            const bool prow = (i0 == k0);
-            const double a_lo = CfT[(i0 + g) * 4 + c4], a_hi = CfT[Mp * 4 + (i0 + g) * 4 + c4];
-            double* arow = A + (i0 + g) * Mp + 2 * c4;   // this lane's two accumulator columns of tile 0
-            for (int ct0 = 0; ct0 < ntile; ct0 += 8) {
-                double2 c[8];
+        GPE_TR(3);   // [3] coefficients
+        const int nct_half = (ntile + 1) >> 1, half = wid & 1;
+        const int ct_begin = half * nct_half, ct_end = min(ntile, ct_begin + nct_half);
+        for (int rp = wid >> 1; 2 * rp < ntile; rp += kTrainWarps / 2) {
+            // two row tiles (the second may not exist: its rows are then never loaded or stored)
+            const int i0a = 2 * rp * kNB, i0b = i0a + kNB;
+            const bool has_b = 2 * rp + 1 < ntile;
+            const bool prow_a = i0a >= k0 && i0a < k0 + nbk, prow_b = i0b >= k0 && i0b < k0 + nbk;
+            double fa[KK], fb[KK];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    c[q] = make_double2(0.0, 0.0);
-                    if (ct0 + q < ntile && !prow) c[q] = *reinterpret_cast<const double2*>(arow + (ct0 + q) * kNB);
+            for (int kk = 0; kk < KK; ++kk) {
+                fa[kk] = (kk < kkn) ? CfT[kk * Mp * 4 + (i0a + g) * 4 + c4] : 0.0;
+                fb[kk] = (kk < kkn && has_b) ? CfT[kk * Mp * 4 + (i0b + g) * 4 + c4] : 0.0;
+            }
+            double* arow_a = A + (i0a + g) * Mp + 2 * c4;   // this lane's two accumulator columns of column tile 0
+            double* arow_b = arow_a + kNB * Mp;
+            for (int ct0 = ct_begin; ct0 < ct_end; ct0 += 4) {
+                double2 ca[4], cb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ca[q] = cb[q] = make_double2(0.0, 0.0);
+                    if (ct0 + q < ct_end) {
+                        if (!prow_a) ca[q] = *reinterpret_cast<const double2*>(arow_a + (ct0 + q) * kNB);
+                        if (has_b && !prow_b) cb[q] = *reinterpret_cast<const double2*>(arow_b + (ct0 + q) * kNB);
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     const int j0 = (ct0 + q) * kNB;
-                    if (ct0 + q < ntile) {   // warp-uniform
-                        const double b_lo = RrT[(j0 + g) * 4 + c4], b_hi = RrT[Mp * 4 + (j0 + g) * 4 + c4];
-                        dmma_m8n8k4(c[q].x, c[q].y, a_lo, b_lo);
-                        dmma_m8n8k4(c[q].x, c[q].y, a_hi, b_hi);
-                        if (j0 == k0)        // pivot columns: coef_i[2 c4], coef_i[2 c4 + 1]
-                            c[q] = *reinterpret_cast<const double2*>(CfT + (c4 >> 1) * Mp * 4 + (i0 + g) * 4 + ((2 * c4) & 3));
-                        *reinterpret_cast<double2*>(arow + j0) = c[q];
+                    if (ct0 + q < ct_end) {   // warp-uniform
+#pragma unroll
+                        for (int kk = 0; kk < KK; ++kk) {
+                            if (kk < kkn) {
+                                const double bf = RrT[kk * Mp * 4 + (j0 + g) * 4 + c4];
+                                dmma_m8n8k4(ca[q].x, ca[q].y, fa[kk], bf);
+                                dmma_m8n8k4(cb[q].x, cb[q].y, fb[kk], bf);
+                            }
+                        }
+                        if (j0 >= k0 && j0 < k0 + nbk) {   // pivot columns: coef_i[j - k0], two consecutive entries per lane
+                            const int bq = j0 - k0 + 2 * c4;
+                            ca[q] = *reinterpret_cast<const double2*>(CfT + (bq >> 2) * Mp * 4 + (i0a + g) * 4 + (bq & 3));
+                            if (has_b) cb[q] = *reinterpret_cast<const double2*>(CfT + (bq >> 2) * Mp * 4 + (i0b + g) * 4 + (bq & 3));
+                        }
+                        *reinterpret_cast<double2*>(arow_a + j0) = ca[q];
+                        if (has_b) *reinterpret_cast<double2*>(arow_b + j0) = cb[q];
                     }
                 }
             }
         }
         __syncthreads();
+        GPE_TR(4);   // [4] rank-NB update
     }
     const int G = D + 2;
     if (bad) {
@@ -233,6 +325,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     s_ta = block_sum(s_ta, red, lane, wid);
     s_aa = block_sum(s_aa, red, lane, wid);
     s_tr = block_sum(s_tr, red, lane, wid);
+    GPE_TR(5);   // [5] alpha and scalar sums
 
     // 4. gradient sums  S_d = sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2  (d < D)  and  S_D = sum_ij (...) Z_ij,
     //    kGS accumulators per pass over the two matrices (D = 10: two passes), four rows in flight per thread
@@ -282,6 +375,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
             }
         }
     }
+    GPE_TR(6);   // [6] gradient sums
+#undef GPE_TR
     if (tid == 0) {
         p.grad[(size_t)nb * G + D + 1] = 0.5 * noise * (s_tr - s_aa);
         const double ll = 0.5 * logdet + 0.5 * s_ta + 0.5 * (double)M * 1.8378770664093453;  // log(2 pi)
@@ -304,6 +399,7 @@ using namespace gpe;
 
 struct gpe_trainer {
     int device = 0, M = 0, D = 0, T = 0, sms = 0;
+    int NB = 8;                   // pivots per pass of the block Gauss-Jordan (k_train_eval<NB>)
     cudaStream_t st = nullptr;
     double* d_x = nullptr;
     double* d_targets = nullptr;
@@ -319,6 +415,8 @@ struct gpe_trainer {
 };
 
 namespace {
+
+long long* g_train_trace = nullptr;   // dev aid: gpe_debug_train_trace
 
 #define TR_TRY(expr)                                                                                              \
     do {                                                                                                          \
@@ -357,6 +455,10 @@ int reserve(gpe_trainer* t, int nb) {
 
 extern "C" {
 
+// Developer aid (not part of the public header): CTA 0 of k_train_eval adds the clock64() duration of each phase to
+// device_buf[0..7] (inputs + covariance, staging, pivot inverse, coefficients, update, alpha, gradient sums); NULL = off.
+void gpe_debug_train_trace(long long* device_buf) { g_train_trace = device_buf; }
+
 int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, const double* targets, gpe_trainer** out) {
     if (!out) return set_error(GPE_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -364,20 +466,28 @@ int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, co
     if (D > GPE_MAX_INPUTS) return set_error(GPE_ERR_UNSUPPORTED, "D = %d exceeds GPE_MAX_INPUTS = %d", D, GPE_MAX_INPUTS);
     if (M > GPE_TRAIN_MAX_M) return set_error(GPE_ERR_UNSUPPORTED, "M = %d exceeds GPE_TRAIN_MAX_M = %d", M, GPE_TRAIN_MAX_M);
     if (!inputs || !targets) return set_error(GPE_ERR_INVALID, "inputs / targets is NULL");
-    const size_t smem = (std::max((size_t)M * D, (size_t)24 * ((M + 7) / 8 * 8)) + 2 * (size_t)M + 40 + 32) * 8;
-    if (smem > 232448) return set_error(GPE_ERR_UNSUPPORTED, "M x D = %d x %d needs %zu bytes of shared memory per CTA", M, D, smem);
+    // pivots per pass: the largest of 32, 16, 8 whose staged pivot rows, columns and coefficients (3 NB Mp doubles) fit
+    // beside the vectors and the kernel's static shared memory (pivot block NB^2 doubles)
+    const size_t mp8 = ((size_t)M + 7) / 8 * 8;
+    int NB = 32;
+    size_t smem = 0;
+    for (;; NB /= 2) {
+        smem = (std::max((size_t)M * D, (size_t)3 * NB * mp8) + 2 * (size_t)M + 40 + 32) * 8;
+        if (smem + (size_t)NB * NB * 8 + 1024 <= 232448 || NB == 8) break;
+    }
+    if (smem + (size_t)NB * NB * 8 + 1024 > 232448)
+        return set_error(GPE_ERR_UNSUPPORTED, "M x D = %d x %d needs %zu bytes of shared memory per CTA", M, D, smem);
     int sms = 0;
     int rc = require_device(device, &sms);
     if (rc) return rc;
     TR_TRY(cudaSetDevice(device));
     gpe_trainer* t = new gpe_trainer;
-    t->device = device; t->M = M; t->D = D; t->T = T; t->sms = sms; t->smem = smem;
+    t->device = device; t->M = M; t->D = D; t->T = T; t->sms = sms; t->smem = smem; t->NB = NB;
     cudaError_t e = cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&t->d_x, (size_t)M * D * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&t->d_targets, (size_t)T * M * 8);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_x, inputs, (size_t)M * D * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->d_targets, targets, (size_t)T * M * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_train_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         gpe_trainer_destroy(t);
         return set_error(GPE_ERR_CUDA, "trainer setup failed: %s", cudaGetErrorString(e));
@@ -426,9 +536,11 @@ int gpe_trainer_eval(gpe_trainer* t, int B, const int* target_index, const doubl
         TrainParams p;
         p.x = t->d_x; p.targets = t->d_targets; p.thetas = t->d_theta; p.tidx = t->d_tidx; p.work = t->d_work;
         p.loglik = t->d_ll; p.grad = t->d_grad; p.status = t->d_status; p.M = t->M; p.D = t->D;
+        p.trace = g_train_trace;
         // per function AND per device: set on every launch so multi-device processes stay correct
-        TR_TRY(cudaFuncSetAttribute(k_train_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem));
-        k_train_eval<<<nb, kTrainThreads, t->smem, t->st>>>(p);
+        auto kern = t->NB == 32 ? k_train_eval<32> : (t->NB == 16 ? k_train_eval<16> : k_train_eval<8>);
+        TR_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem));
+        kern<<<nb, kTrainThreads, t->smem, t->st>>>(p);
         count_launch();
         TR_TRY(cudaGetLastError());
         TR_TRY(cudaMemcpyAsync(loglik + b0, t->d_ll, (size_t)nb * 8, cudaMemcpyDeviceToHost, t->st));

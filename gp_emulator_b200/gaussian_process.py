@@ -57,12 +57,14 @@ class GaussianProcess:
     _FULL_CHECK_BYTES = 1 << 20
     _FULL_CHECK_POINTS = 1000
 
-    def __init__(self, inputs, targets, device=0, symmetric_variance=False):
+    def __init__(self, inputs, targets, device=0, symmetric_variance="auto"):
         """``device``: a GPU index, a list of indices, or ``"all"`` -- with more than one device a host batch is spread
         over all of them inside ONE ``predict`` call (``MultiDeviceModel``); the reference API has no notion of ranks.
-        ``symmetric_variance``: False (default) evaluates the variance with the general dense formula, as the reference
-        does; ``"auto"`` / True let the device fold ``invQ`` onto its upper triangle when it is symmetric / always
-        (``DeviceModel``): same value to rounding, 1.29x the throughput at M = 250."""
+        ``symmetric_variance``: ``"auto"`` (default) lets the device fold ``invQ`` onto its upper triangle when it is
+        symmetric to 1e-6 -- any ``invQ`` that ``_prepare_likelihood`` produced -- which halves the tensor-core work of
+        the variance (1.4-1.5x the throughput; same value to the rounding of the summation order), and keeps the general
+        dense formula for a non-symmetric ``invQ`` such as the random one of the reference's benchmark
+        (tests/benchmark.py:11-15); False always uses the dense formula, True always folds (``DeviceModel``)."""
         self._version = 0
         self.inputs = inputs
         self.targets = targets
