@@ -172,6 +172,7 @@ cudaError_t launch_full(int DP, int cfg, const FullParams& p, int grid, size_t s
 }
 
 cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    if (p.smem_need == 0 || p.smem_need > smem) return cudaErrorInvalidConfiguration;   // carve-up vs launch (see MeanParams)
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (DP) {
         case 2: return launch_mean_dp2(hess, p, grid, smem, st);
@@ -269,6 +270,14 @@ MeanPlan plan_mean(int M, int D, int DP) {
     // Hessian staging: [TN][D][D] for the triangular kernel (D <= 12), [TN][HR][D] for the row-block kernel
     m.smem_hess = off + (uint32_t)kMeanTN * D * 8u * (uint32_t)(DP <= 12 ? D : (DP <= 16 ? 4 : 2));
     return m;
+}
+
+// Extent of the mean kernels' shared-memory carve-up, recomputed from the offsets the kernels use (checked against the
+// dynamic shared memory of the launch at kernel entry: MeanParams::smem_need).
+uint32_t mean_extent(const MeanPlan& mp, int D, int DP, bool hess) {
+    uint32_t ext = std::max(mp.off_xc + (uint32_t)mp.JC * (DP + 1) * 8u, mp.off_ts + (uint32_t)kMeanTN * (D + 1) * 8u);
+    if (hess) ext = std::max(ext, mp.off_out + (uint32_t)kMeanTN * D * 8u * (uint32_t)(DP <= 12 ? D : (DP <= 16 ? 4 : 2)));
+    return ext;
 }
 
 // [nchunks][ JC*DP sqrt(w)-scaled inputs | JC b*alpha ], zero padded
@@ -373,6 +382,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
             p.ld_mu = ld_mu; p.ld_deriv = ld_deriv;
             p.xchunks = m->d_xchunks_mean; p.M = m->M; p.D = m->D; p.JC = m->mean.JC; p.nchunks = m->mean.nchunks;
             p.off_xc = m->mean.off_xc; p.off_ts = m->mean.off_ts; p.off_out = m->mean.off_out;
+            p.smem_need = mean_extent(m->mean, m->D, m->DP, false);
             p.kstar = m->d_kscratch; p.kblk = m->large_kblk;
             memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
             const int64_t mtiles = (n + kMeanTN - 1) / kMeanTN;
@@ -437,6 +447,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.ld_mu = ld_mu; p.ld_deriv = ld_deriv; p.ld_hess = ld_hess;
         p.xchunks = m->d_xchunks_mean; p.M = m->M; p.D = m->D; p.JC = m->mean.JC; p.nchunks = m->mean.nchunks;
         p.off_xc = m->mean.off_xc; p.off_ts = m->mean.off_ts; p.off_out = m->mean.off_out;
+        p.smem_need = mean_extent(m->mean, m->D, m->DP, do_hess);
         memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
         const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
         // CTAs per SM: a multiple of what is resident (3 for the mean + gradient kernel, 2 / 4 for the Hessian ones)
@@ -962,6 +973,7 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
         p.bank = b->d_entries;
         p.M = m0->M; p.D = m0->D; p.JC = m0->mean.JC; p.nchunks = m0->mean.nchunks;
         p.off_xc = m0->mean.off_xc; p.off_ts = m0->mean.off_ts; p.off_out = m0->mean.off_out;
+        p.smem_need = mean_extent(m0->mean, m0->D, m0->DP, do_hess);
         const int64_t ntiles = (N + kMeanTN - 1) / kMeanTN;
         const int gx = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)m0->sms * 8 / E));
         const size_t smem = do_hess ? m0->mean.smem_hess : m0->mean.smem;

@@ -12,7 +12,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gpe_math.cuh"
-#include "gpe_ptx.cuh"
 
 namespace gpe {
 
@@ -40,6 +39,10 @@ struct MeanParams {
     int64_t eo_mu, eo_deriv, eo_hess;   // element offsets per emulator into the point-major bank outputs
     double* kstar;                      // k_predict_mean2<DP, true>: K* scratch [ceil(N/16)][kblk][16][4] (predict_var_large.cuh)
     int kblk;
+    uint32_t smem_need;                 // extent of the carve-up above, recomputed by the host from the same offsets and
+                                        // checked against the launch's dynamic shared memory in launch_mean (gpemu.cu).  Not
+                                        // at kernel entry like the other kernels: k_predict_mean2 sits at its register cap
+                                        // (3 CTAs/SM) and even a one-compare guard + trap made ptxas spill (-17 %)
 };
 
 template <int DP, bool HESS>
@@ -57,8 +60,6 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
     exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M, DV = D + 1;
-    smem_guard(umax2(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)DV * 8u),
-                     HESS ? p.off_out + (uint32_t)TN * (uint32_t)(D * D) * 8u : 0u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
@@ -224,7 +225,6 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
     exp_tab_load(exp_tab, tid);   // visible after the barrier at the first tile start
     const int g_low = lane & 7, n_a = warp * 8 + (lane >> 3), n_b = n_a + 4;
     const int D = p.D, M = p.M, DV = D + 1;
-    smem_guard(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)DV * 8u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
@@ -379,8 +379,6 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
     exp_tab_load(exp_tab, tid);
     const int g_low = lane & 3, n_loc = warp * 8 + (lane >> 2);
     const int D = p.D, M = p.M;
-    smem_guard(umax2(umax2(p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u, p.off_ts + (uint32_t)TN * (uint32_t)D * 8u),
-                     p.off_out + (uint32_t)TN * HR * (uint32_t)D * 8u));
     const int em = blockIdx.y;
     const double* xchunks = p.bank ? p.bank[em].xchunks : p.xchunks;
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];

@@ -23,7 +23,8 @@
 //                  instruction -- found the hard way), and with W odd an odd row starts 8 bytes off: its 16-byte aligned
 //                  columns are the odd ones.  So for odd W the odd rows' box is 126 columns wide and starts one column
 //                  later, and the two columns per row and group that fall outside (the first and the last of the group)
-//                  are written by the lanes that hold them, with plain stores.
+//                  are written by the lanes that hold them, with plain stores.  Clipping, too, happens in 16-byte units:
+//                  the even rows' tensor is declared W - 1 columns wide and their last column is a plain store as well.
 //   k_project      the first version: per-warp smem transposition, then st.global of 256 contiguous bytes per instruction.
 //                  Kept for outputs that are not 16-byte aligned, for slices that accumulate (banks of more than 32
 //                  emulators) and for a handful of rows.
@@ -153,8 +154,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 
-template <int KS>   // k-steps of 4: E <= 4 KS
-__global__ void __launch_bounds__(kProjThreads, (KS <= 5 ? 2 : 1)) k_project_tma(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
+// WRG = row groups of 32 rows (4 warps each) per CTA.  WRG = 1: 128 threads, 32-row tiles, three co-resident CTAs per SM whose
+// DMMA / staging / barrier phases drift apart (measured against WRG = 2)
+template <int KS, int WRG>   // k-steps of 4: E <= 4 KS
+__global__ void __launch_bounds__(WRG * 128, (KS <= 5 ? (WRG == 1 ? 3 : 2) : 1)) k_project_tma(const double* __restrict__ A, int64_t R, int RD, int64_t ldn,
                                                                  int64_t lde, int64_t ldd, const double* __restrict__ b_tiled,
                                                                  int E, int W, int Wp,
                                                                  const __grid_constant__ CUtensorMap map_even,
@@ -164,12 +167,13 @@ __global__ void __launch_bounds__(kProjThreads, (KS <= 5 ? 2 : 1)) k_project_tma
     constexpr uint32_t stage_doubles = (uint32_t)KS * kProjCols * 4, ks_bytes = kProjCols * 4 * 8;
     uint64_t* full = reinterpret_cast<uint64_t*>(psm);          // [2]
     double* stage = reinterpret_cast<double*>(psm + 128);       // [2][KS][128][4]
-    double* tile_even = stage + 2 * (size_t)stage_doubles;      // [32 row pairs][128]: rows 0, 2, 4, ... of the CTA tile
-    double* tile_odd = tile_even + 32 * kProjCols;              // [32 row pairs][128 - 2 shift]: rows 1, 3, 5, ...
+    constexpr int kRows = WRG * 32, kPairs = WRG * 16;
+    double* tile_even = stage + 2 * (size_t)stage_doubles;      // [kPairs row pairs][128]: rows 0, 2, 4, ... of the CTA tile
+    double* tile_odd = tile_even + kPairs * kProjCols;          // [kPairs row pairs][128 - 2 shift]: rows 1, 3, 5, ...
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = warp >> 2, wc = warp & 3;
-    smem_guard(128u + 2u * stage_doubles * 8u + 2u * 32u * kProjCols * 8u);
-    const int64_t r0 = (int64_t)blockIdx.x * kProjRows + wr * 32;
+    smem_guard(128u + 2u * stage_doubles * 8u + 2u * kPairs * kProjCols * 8u);
+    const int64_t r0 = (int64_t)blockIdx.x * kRows + wr * 32;
     const int ngroups = Wp / kProjCols;
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(kProjThreads, (KS <= 5 ? 2 : 1)) k_project_tma
     const int cl0 = wc * 32 + 2 * (lane & 3);                    // this lane's first column inside the group (tile j = 0)
     double* const dst_even = tile_even + (size_t)(rl0 >> 1) * kProjCols + cl0;
     double* const dst_odd = tile_odd + (size_t)(rl0 >> 1) * po + cl0 - shift;
-    const int pair0 = (int)(((int64_t)blockIdx.x * kProjRows) >> 1);
+    const int pair0 = (int)(((int64_t)blockIdx.x * kRows) >> 1);
     uint32_t par = 0;
     for (int g = 0; g < ngroups; ++g) {
         const int st = g & 1;
@@ -241,12 +245,26 @@ __global__ void __launch_bounds__(kProjThreads, (KS <= 5 ? 2 : 1)) k_project_tma
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<double2*>(d0 + (size_t)i * pitch4 + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (shift && g == (W - 1) / kProjCols) {
+                // odd W: the copy engine clips in 16-byte units, so the even rows' tensor ends at column W - 2 (an even
+                // number of columns) and their last column is written here, by the lane that holds it
+                const int jl = (W - 1) % kProjCols - cl0;        // 8 j for the owning lane (W - 1 is even, like cl0)
+                if (jl >= 0 && jl < 32 && (jl & 7) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t r = (int64_t)blockIdx.x * kRows + rl0 + 8 * i;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (8 * j == jl && r < R) out[r * W + W - 1] = acc[i][j][0];
+                    }
+                }
+            }
         } else {
             // odd row of an odd-W matrix: 8-byte stores into the shifted tile; the group's first and last column go
             // straight to global memory
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t r = (int64_t)blockIdx.x * kProjRows + rl0 + 8 * i;
+                const int64_t r = (int64_t)blockIdx.x * kRows + rl0 + 8 * i;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int cl = cl0 + 8 * j;
@@ -292,13 +310,14 @@ EncodeTiledFn encode_tiled() {
 }
 
 // Tensor maps of the even and the odd output rows (see the header comment).  false: not expressible -> LSU kernel.
-bool make_row_pair_maps(double* out, int64_t R, int W, CUtensorMap* even, CUtensorMap* odd) {
+bool make_row_pair_maps(double* out, int64_t R, int W, int pairs, CUtensorMap* even, CUtensorMap* odd) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || R < 2) return false;
     const cuuint64_t pitch[1] = {(cuuint64_t)W * 16};           // two rows, in bytes: a multiple of 16 for any W
-    const cuuint32_t box[2] = {(cuuint32_t)kProjCols, 32}, estr[2] = {1, 1};
-    const cuuint32_t box_odd[2] = {(cuuint32_t)(kProjCols - 2 * (W & 1)), 32};   // odd W: see the header comment
-    const cuuint64_t dim_even[2] = {(cuuint64_t)W, (cuuint64_t)((R + 1) / 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)kProjCols, (cuuint32_t)pairs}, estr[2] = {1, 1};
+    const cuuint32_t box_odd[2] = {(cuuint32_t)(kProjCols - 2 * (W & 1)), (cuuint32_t)pairs};   // odd W: see the header comment
+    // (odd W: W - 1 columns -- the engine clips in 16-byte units; the kernel writes the even rows' last column itself)
+    const cuuint64_t dim_even[2] = {(cuuint64_t)(W - (W & 1)), (cuuint64_t)((R + 1) / 2)};
     const cuuint64_t dim_odd[2] = {(cuuint64_t)2 * W, (cuuint64_t)(R / 2)};
     if (enc(even, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, out, dim_even, pitch, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -309,14 +328,14 @@ bool make_row_pair_maps(double* out, int64_t R, int W, CUtensorMap* even, CUtens
     return true;
 }
 
-template <int KS>
+template <int KS, int WRG>
 cudaError_t launch_project_tma(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, const double* b_tiled,
                                int E, int W, int Wp, const CUtensorMap& even, const CUtensorMap& odd, double* out, cudaStream_t st) {
-    const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 2 * 32 * (size_t)kProjCols * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_project_tma<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 2 * (size_t)WRG * 16 * kProjCols * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_project_tma<KS, WRG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     if (e != cudaSuccess) return e;
-    k_project_tma<KS><<<(unsigned)((R + kProjRows - 1) / kProjRows), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd, b_tiled, E,
-                                                                                              W, Wp, even, odd, out);
+    k_project_tma<KS, WRG><<<(unsigned)((R + WRG * 32 - 1) / (WRG * 32)), WRG * 128, psmem, st>>>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp,
+                                                                                           even, odd, out);
     return cudaGetLastError();
 }
 
@@ -327,11 +346,16 @@ cudaError_t project_rows(const double* A, int64_t R, int RD, int64_t ldn, int64_
     static const bool no_tma = getenv("GPE_PROJECT_NO_TMA") != nullptr;   // dev aid: time / test the LSU kernel
     const int ks = (E + 3) / 4;
     CUtensorMap even, odd;
+    static const int wrg = getenv("GPE_PROJECT_WR") ? atoi(getenv("GPE_PROJECT_WR")) : 1;   // dev aid: 2 = 64-row CTAs
     // (a few rows -- the reference's one-point call -- keep the LSU kernel: its stores may go straight to mapped host memory)
-    if (!accumulate && !no_tma && R >= 256 && make_row_pair_maps(out, R, W, &even, &odd)) {
-        if (ks <= 3) return launch_project_tma<3>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, even, odd, out, st);
-        if (ks <= 5) return launch_project_tma<5>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, even, odd, out, st);
-        return launch_project_tma<8>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, even, odd, out, st);
+    if (!accumulate && !no_tma && R >= 256 && make_row_pair_maps(out, R, W, wrg == 2 ? 32 : 16, &even, &odd)) {
+#define GPE_PROJ_TMA(KSV)                                                                                                   \
+        return wrg == 2 ? launch_project_tma<KSV, 2>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, even, odd, out, st)     \
+                        : launch_project_tma<KSV, 1>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, even, odd, out, st)
+        if (ks <= 3) GPE_PROJ_TMA(3);
+        if (ks <= 5) GPE_PROJ_TMA(5);
+        GPE_PROJ_TMA(8);
+#undef GPE_PROJ_TMA
     }
     if (ks <= 3) return launch_project<3>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, out, accumulate, st);
     if (ks <= 5) return launch_project<5>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, out, accumulate, st);

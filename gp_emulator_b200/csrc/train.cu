@@ -146,16 +146,23 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     for (int k0 = 0; k0 < Mp; k0 += NB) {
         const int nbk = min(NB, Mp - k0);     // pivots of this pass (multiple of 8)
         const int kkn = nbk >> 2;             // its DMMA k-steps
-        for (int e = tid; e < nbk * Mp; e += kTrainThreads) {
-            const int a = e / Mp, j = e - a * Mp;
-            RrT[(a >> 2) * Mp * 4 + j * 4 + (a & 3)] = A[(k0 + a) * Mp + j];
-        }
-        for (int e = tid; e < Mp * NB; e += kTrainThreads) {
-            const int i = e / NB, a = e % NB;
-            if (a < nbk) Cc[e] = A[i * Mp + k0 + a];
+        // pivot rows and columns, L2 -> shared memory (index arithmetic without integer division: Mp is a run-time value
+        // and `e / Mp`, `e % Mp` per element made this the third most expensive step of the pass)
+        for (int a = wid; a < nbk; a += kTrainWarps) {
+            const double* src = A + (k0 + a) * Mp;
+            double* dst = RrT + (a >> 2) * Mp * 4 + (a & 3);
+#pragma unroll 4
+            for (int j = lane; j < Mp; j += 32) dst[j * 4] = src[j];
         }
         __syncthreads();
-        GPE_TR(1);   // [1] staging of pivot rows / columns
+        GPE_TR(1);   // [1] staging of the pivot rows
+        // the pivot columns are staged by warps 1.. while warp 0 inverts the pivot block (which only needs the rows)
+        if (wid > 0) {
+            for (int e = tid - 32; e < Mp * NB; e += kTrainThreads - 32) {
+                const int i = e / NB, a = e % NB;      // NB is a compile-time power of two
+                if (a < nbk) Cc[e] = A[i * Mp + k0 + a];
+            }
+        }
         // inv(P) by scalar Gauss-Jordan in the registers of warp 0: the 32 lanes form a 4 x 8 grid, lane (lr, lc) owns the
         // (NB/4) x (NB/8) sub-block of rows lr NB/4 + i, columns lc NB/8 + j.  Pivot step k needs the pivot, row k
         // restricted to the lane's columns and column k restricted to its rows: 1 + NB/8 + NB/4 shuffles (13 for NB = 32),
@@ -190,13 +197,22 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
                         for (int j = 0; j < CB; ++j) r[j] = __shfl_sync(full, v[ki][j], kr * 8 + lc);        // P[k][my columns]
 #pragma unroll
                         for (int i = 0; i < RB; ++i) c[i] = __shfl_sync(full, v[i][kj], lr * 8 + kc) * ip;   // P[my rows][k] / p
+                        // every entry as if it were off the pivot row and column (one FMA each), then the pivot row /
+                        // column entries of the lanes that hold them are overwritten: k is a compile-time constant of the
+                        // unrolled loop, so those are fixed registers (the selects per entry cost 2x the instructions)
 #pragma unroll
                         for (int i = 0; i < RB; ++i)
 #pragma unroll
-                            for (int j = 0; j < CB; ++j) {
-                                const bool in_row = (lr == kr) && (i == ki), in_col = (lc == kc) && (j == kj);
-                                v[i][j] = in_row ? (in_col ? ip : r[j] * ip) : (in_col ? -c[i] : fma(-c[i], r[j], v[i][j]));
-                            }
+                            for (int j = 0; j < CB; ++j) v[i][j] = fma(-c[i], r[j], v[i][j]);
+                        if (lc == kc) {
+#pragma unroll
+                            for (int i = 0; i < RB; ++i) v[i][kj] = -c[i];
+                        }
+                        if (lr == kr) {
+#pragma unroll
+                            for (int j = 0; j < CB; ++j) v[ki][j] = r[j] * ip;
+                            if (lc == kc) v[ki][kj] = ip;
+                        }
                         if (lane == (k & 31)) mypiv = piv;
                     }
                 }
@@ -223,12 +239,21 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
             for (int i = wid * RPW + sub; i < Mp; i += kTrainWarps * RPW) {
                 const double2* crow = reinterpret_cast<const double2*>(Cc + i * NB);
                 double s0 = 0.0, s1 = 0.0;
+                if (nbk == NB) {               // full pass: no predicates, the broadcast loads are hoisted above the FMAs
 #pragma unroll
-                for (int a2 = 0; a2 < NB / 2; ++a2) {
-                    if (2 * a2 < nbk) {        // (nbk is a multiple of 8: whole pairs)
+                    for (int a2 = 0; a2 < NB / 2; ++a2) {
                         const double2 cv = crow[a2];
                         s0 = fma(cv.x, pc[2 * a2], s0);
                         s1 = fma(cv.y, pc[2 * a2 + 1], s1);
+                    }
+                } else {
+#pragma unroll
+                    for (int a2 = 0; a2 < NB / 2; ++a2) {
+                        if (2 * a2 < nbk) {    // (nbk is a multiple of 8: whole pairs)
+                            const double2 cv = crow[a2];
+                            s0 = fma(cv.x, pc[2 * a2], s0);
+                            s1 = fma(cv.y, pc[2 * a2 + 1], s1);
+                        }
                     }
                 }
                 const bool prow = i >= k0 && i < k0 + nbk;
@@ -254,6 +279,39 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
             double* arow_b = arow_a + kNB * Mp;
             for (int ct0 = ct_begin; ct0 < ct_end; ct0 += 4) {
                 double2 ca[4], cb[4];
+                if (kkn == KK && ct0 + 4 <= ct_end && has_b) {
+                    // full batch of a full pass (every batch at M = 250): no predicates, so the eight B-fragment loads of a
+                    // tile are hoisted above its sixteen DMMAs and the four tiles overlap
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ca[q] = prow_a ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(arow_a + (ct0 + q) * kNB);
+                        cb[q] = prow_b ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(arow_b + (ct0 + q) * kNB);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j0 = (ct0 + q) * kNB;
+                        double bf[KK];
+#pragma unroll
+                        for (int kk = 0; kk < KK; ++kk) bf[kk] = RrT[kk * Mp * 4 + (j0 + g) * 4 + c4];
+#pragma unroll
+                        for (int kk = 0; kk < KK; ++kk) {
+                            dmma_m8n8k4(ca[q].x, ca[q].y, fa[kk], bf[kk]);
+                            dmma_m8n8k4(cb[q].x, cb[q].y, fb[kk], bf[kk]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j0 = (ct0 + q) * kNB;
+                        if (j0 >= k0 && j0 < k0 + nbk) {   // pivot columns: coef_i[j - k0], two consecutive entries per lane
+                            const int bq = j0 - k0 + 2 * c4;
+                            ca[q] = *reinterpret_cast<const double2*>(CfT + (bq >> 2) * Mp * 4 + (i0a + g) * 4 + (bq & 3));
+                            cb[q] = *reinterpret_cast<const double2*>(CfT + (bq >> 2) * Mp * 4 + (i0b + g) * 4 + (bq & 3));
+                        }
+                        *reinterpret_cast<double2*>(arow_a + j0) = ca[q];
+                        *reinterpret_cast<double2*>(arow_b + j0) = cb[q];
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     ca[q] = cb[q] = make_double2(0.0, 0.0);
@@ -328,8 +386,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     GPE_TR(5);   // [5] alpha and scalar sums
 
     // 4. gradient sums  S_d = sum_ij (invQ_ij - alpha_i alpha_j) Z_ij (x_id - x_jd)^2  (d < D)  and  S_D = sum_ij (...) Z_ij,
-    //    kGS accumulators per pass over the two matrices (D = 10: two passes), four rows in flight per thread
-    constexpr int kGS = 8;
+    //    kGS accumulators per pass over the two matrices, four rows in flight per thread
+    constexpr int kGS = 12;   // D = 10: all eleven sums in ONE pass over the two matrices (the 64-register version took two)
     for (int d0 = 0; d0 <= D; d0 += kGS) {
         double acc[kGS];
 #pragma unroll
