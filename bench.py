@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--cpu-points", type=float, default=1e5, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg 1/3/4/5 block")
-    ap.add_argument("--multi-points", type=float, default=5e6, help="host-resident points per GPU of the one-process e2e (N > 1)")
+    ap.add_argument("--multi-points", type=float, default=1e7, help="host-resident points per GPU of the one-process e2e (N > 1)")
     ap.add_argument("--tripwire", type=int, default=100000, help="prefix and random-subset size of the oracle check")
     return ap.parse_args()
 
@@ -267,12 +267,19 @@ def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
     out["cfg4"] = {"workload": "MultivariateEmulator bank P=20 PCs, W=2101 wavelengths, M=250 D=10; 1e7 device-resident test inputs in "
                                "chunks of 2e5: PC means + PC gradients + back-projected spectra fwd (N, 2101)",
                    "points_per_s": pps4, "pc_space_only_points_per_s": pps4_pc,
-                   "kernel": "k_predict_mean2<10,false> (bank: blockIdx.y = PC) + k_project<5>",
-                   "roofline": {"bound": "hbm", "achieved": pps4 * W * 8 / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                                "frac": pps4 * W * 8 / 1e9 / hbm_gbs,
-                                "note": "algorithmic bytes = 8 W = 16,808 B of spectrum written per point (SURVEY 8d) over the whole "
-                                        "step (GP kernels + projection); peak = MEASURED_PEAKS.json hbm_gbs",
-                                "projection_only_GBps": W * 8 / proj_s / 1e9 if proj_s > 0 else None},
+                   "kernel": "k_predict_mean2<10,false> (bank: blockIdx.y = PC) + k_project_tma<5,1> (tensor-map TMA stores)",
+                   "roofline": {"bound": "hbm", "achieved": W * 8 / proj_s / 1e9 if proj_s > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
+                                "frac": (W * 8 / proj_s / 1e9 / hbm_gbs) if proj_s > 0 else None,
+                                "note": "the back-projection kernel alone: algorithmic bytes = 8 W = 16,808 B of spectrum written per "
+                                        "point (SURVEY 8d) / its time (step with projection - step without, CUDA events); peak = "
+                                        "MEASURED_PEAKS.json hbm_gbs"},
+                   "step_roofline": {"bound": "fp64 pipe (instruction issue)", "achieved": pps4_pc * P * M * 45 / 1e12,
+                                     "peak": peaks["dfma_tflops"] / 2.0, "unit": "T FP64 instr/s",
+                                     "frac": pps4_pc * P * M * 45 / 1e12 / (peaks["dfma_tflops"] / 2.0),
+                                     "spectra_GBps_whole_step": pps4 * W * 8 / 1e9,
+                                     "note": "the STEP is bound by the P = 20 mean + gradient evaluations, not by the projection "
+                                             "(%.0f %% of its time): 45 FP64 instructions per (test, train) pair and PC against the "
+                                             "measured DFMA instruction rate" % (100.0 * pps4 / pps4_pc)},
                    "parity_vs_oracle": par4}
     # host-resident: numpy in, PC-space outputs out (1,760 B per point back over PCIe), chunk walk below the C ABI
     Nh = 2_000_000
