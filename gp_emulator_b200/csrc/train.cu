@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
     constexpr int KK = NB / 4;        // DMMA k-steps of a full pass
     extern __shared__ __align__(16) double sm[];
     __shared__ double Pbuf[NB * NB];   // inverse of the pivot block
+    __shared__ double rowbuf[2][NB];   // pivot row handed between the four warps of the block inverse
     __shared__ int s_bad;
     const int M = p.M, D = p.D, Mp = (M + 7) & ~7, nb = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -156,73 +157,60 @@ __global__ void __launch_bounds__(kTrainThreads, 1) k_train_eval(const TrainPara
         }
         __syncthreads();
         GPE_TR(1);   // [1] staging of the pivot rows
-        // the pivot columns are staged by warps 1.. while warp 0 inverts the pivot block (which only needs the rows)
-        if (wid > 0) {
-            for (int e = tid - 32; e < Mp * NB; e += kTrainThreads - 32) {
+        // the pivot columns are staged by warps 4.. while warps 0-3 invert the pivot block (which only needs the rows)
+        if (wid >= 4) {
+            for (int e = tid - 128; e < Mp * NB; e += kTrainThreads - 128) {
                 const int i = e / NB, a = e % NB;      // NB is a compile-time power of two
                 if (a < nbk) Cc[e] = A[i * Mp + k0 + a];
             }
-        }
-        // inv(P) by scalar Gauss-Jordan in the registers of warp 0: the 32 lanes form a 4 x 8 grid, lane (lr, lc) owns the
-        // (NB/4) x (NB/8) sub-block of rows lr NB/4 + i, columns lc NB/8 + j.  Pivot step k needs the pivot, row k
-        // restricted to the lane's columns and column k restricted to its rows: 1 + NB/8 + NB/4 shuffles (13 for NB = 32),
-        // no shared memory and no barrier inside the 32-step dependency chain (the first blocked version kept the block in
-        // shared memory with one CTA barrier per pivot: 690 cycles per pivot, 15 % of the kernel).  The pivots are the
-        // LDL^T pivots of Q; their logarithms are taken after the loop, one per lane.
-        if (wid == 0) {
-            constexpr int RB = NB / 4, CB = NB / 8;
-            const int lr = lane >> 3, lc = lane & 7;
-            double v[RB][CB];
+        } else {
+            // inv(P) by scalar Gauss-Jordan in the registers of four warps (one per SM sub-partition): warp w owns rows
+            // [w NB/4, (w + 1) NB/4) of the block, lane b column b.  Pivot step k: the owner of row k publishes it through a
+            // double-buffered shared row + one 128-thread named barrier; column k restricted to a warp's rows sits in its lane
+            // k (shuffles).  Per pivot the dependent chain is store -> barrier -> load -> reciprocal -> shuffle -> FMA, ~200
+            // cycles; one warp holding the whole block (13 shuffles, 32 FMAs and the fix-ups per pivot) took 550, a CTA-wide
+            // version with the block in shared memory 690.  The pivots are the LDL^T pivots of Q; their logarithms are
+            // taken after the loop, one per lane of warp 0.  (A look-ahead variant -- one warp updates and inverts the NEXT
+            // pivot block during the rank-NB update -- was measured and dropped: DFMA and DMMA share one FP64 pipe on this
+            // GPU, so the inverse's dependent chain crawls behind the other warps' DMMAs: 366 k -> 545 k cycles in the
+            // update for 99 k saved.)
+            constexpr int RW = NB / 4;
+            constexpr unsigned full = 0xffffffffu;
+            double v[RW];
 #pragma unroll
-            for (int i = 0; i < RB; ++i)
-#pragma unroll
-                for (int j = 0; j < CB; ++j) {
-                    const int ra = lr * RB + i, cb = lc * CB + j;
-                    v[i][j] = (ra < nbk && cb < nbk) ? RrT[(ra >> 2) * Mp * 4 + (k0 + cb) * 4 + (ra & 3)] : ((ra == cb) ? 1.0 : 0.0);
-                }
+            for (int i = 0; i < RW; ++i) {
+                const int ra = wid * RW + i, cb = lane;
+                v[i] = (cb < NB) ? ((ra < nbk && cb < nbk) ? RrT[(ra >> 2) * Mp * 4 + (k0 + cb) * 4 + (ra & 3)] : ((ra == cb) ? 1.0 : 0.0)) : 0.0;
+            }
             bool wbad = false;
             double mypiv = 1.0;
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
-                if (k < nbk && !wbad) {   // warp-uniform
-                    constexpr unsigned full = 0xffffffffu;
-                    const int kr = k / RB, ki = k % RB, kc = k / CB, kj = k % CB;
-                    const double piv = __shfl_sync(full, v[ki][kj], kr * 8 + kc);
-                    if (!(piv > 0.0) || !(piv < 1e300)) {
-                        wbad = true;
-                    } else {
-                        const double ip = fast_rcp(piv);     // piv in (0, 1e300): within an ulp or two of 1 / piv
-                        double r[CB], c[RB];
+                if (k < nbk) {   // uniform over the four warps
+                    const int ow = k / RW, ki = k % RW;
+                    double* rb = rowbuf[k & 1];
+                    if (wid == ow && lane < NB) rb[lane] = v[ki];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const double r = (lane < NB) ? rb[lane] : 0.0;     // P[k][my column]
+                    const double piv = rb[k];
+                    if (!(piv > 0.0) || !(piv < 1e300)) wbad = true;   // same value in all 128 threads
+                    const double ip = fast_rcp(wbad ? 1.0 : piv);      // within an ulp or two of 1 / piv
 #pragma unroll
-                        for (int j = 0; j < CB; ++j) r[j] = __shfl_sync(full, v[ki][j], kr * 8 + lc);        // P[k][my columns]
-#pragma unroll
-                        for (int i = 0; i < RB; ++i) c[i] = __shfl_sync(full, v[i][kj], lr * 8 + kc) * ip;   // P[my rows][k] / p
-                        // every entry as if it were off the pivot row and column (one FMA each), then the pivot row /
-                        // column entries of the lanes that hold them are overwritten: k is a compile-time constant of the
-                        // unrolled loop, so those are fixed registers (the selects per entry cost 2x the instructions)
-#pragma unroll
-                        for (int i = 0; i < RB; ++i)
-#pragma unroll
-                            for (int j = 0; j < CB; ++j) v[i][j] = fma(-c[i], r[j], v[i][j]);
-                        if (lc == kc) {
-#pragma unroll
-                            for (int i = 0; i < RB; ++i) v[i][kj] = -c[i];
-                        }
-                        if (lr == kr) {
-#pragma unroll
-                            for (int j = 0; j < CB; ++j) v[ki][j] = r[j] * ip;
-                            if (lc == kc) v[ki][kj] = ip;
-                        }
-                        if (lane == (k & 31)) mypiv = piv;
+                    for (int i = 0; i < RW; ++i) {
+                        const double c = __shfl_sync(full, v[i], k & 31) * ip;   // P[my row i][k] / p
+                        v[i] = (lane == k) ? -c : fma(-c, r, v[i]);
                     }
+                    if (wid == ow) v[ki] = (lane == k) ? ip : r * ip;
+                    if (wid == 0 && lane == (k & 31)) mypiv = piv;
                 }
             }
 #pragma unroll
-            for (int i = 0; i < RB; ++i)
-#pragma unroll
-                for (int j = 0; j < CB; ++j) Pbuf[(lr * RB + i) * NB + lc * CB + j] = v[i][j];
-            if (wbad) s_bad = 1;
-            else logdet += warp_sum(lane < nbk ? log(mypiv) : 0.0);
+            for (int i = 0; i < RW; ++i)
+                if (lane < NB) Pbuf[(wid * RW + i) * NB + lane] = v[i];
+            if (wid == 0) {
+                if (wbad) { if (lane == 0) s_bad = 1; }
+                else logdet += warp_sum(lane < nbk ? log(mypiv) : 0.0);
+            }
         }
         __syncthreads();
         if (s_bad) { bad = true; break; }   // uniform
