@@ -295,7 +295,8 @@ def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
     del t, mu_b, der_b, fwd_b, bank, h_in, h_out
 
     # ---- cfg 5: per-band bank of 64 GPs sharing test inputs, mean + variance + gradient + Hessian --------------------
-    M, D, E, N, CH = 250, 10, 64, 10_000_000, 100_000
+    sms = torch.cuda.get_device_properties(dev_index).multi_processor_count
+    M, D, E, N, CH = 250, 10, 64, 10_000_000, 64 * sms * 10     # chunks of ten whole waves of 64-point tiles (94,720 points)
     thetas = rs.random_sample((E, D + 2)); invQts = rs.random_sample((E, M)); invQs = rs.random_sample((E, M, M))
     bank = gpe.DeviceBank(inputs, thetas, invQts, invQs, device=dev_index)
     tt = rs.random_sample((40, D))
@@ -308,15 +309,16 @@ def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
           "deriv": torch.empty(CH, E, D, dtype=torch.float64, device=dev), "hess": torch.empty(CH, E, D, D, dtype=torch.float64, device=dev)}
 
     def cfg5_pass(n_total):
-        for c0 in range(0, n_total, CH):   # 573 GB of outputs in total: produced chunk-wise into one 5.7 GB set of buffers
-            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + CH].data_ptr(), CH, ob["mu"].data_ptr(), ob["var"].data_ptr(),
+        for c0 in range(0, n_total, CH):   # 573 GB of outputs in total: produced chunk-wise into one 5.4 GB set of buffers
+            n = min(CH, n_total - c0)
+            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + n].data_ptr(), n, ob["mu"].data_ptr(), ob["var"].data_ptr(),
                                            ob["deriv"].data_ptr(), ob["hess"].data_ptr(), None, None, 0x0F, st))
     cfg5_pass(2 * CH)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); cfg5_pass(N); b.record(); torch.cuda.synchronize()
     pps5 = N / (a.elapsed_time(b) * 1e-3)
-    out["cfg5"] = {"workload": "bank of 64 S-model GPs sharing 1e7 device-resident test inputs (chunks of 1e5), M=250 D=10 FP64, "
+    out["cfg5"] = {"workload": "bank of 64 S-model GPs sharing 1e7 device-resident test inputs (chunks of 94,720 = ten whole waves of 64-point tiles), M=250 D=10 FP64, "
                                "mu+var+grad+Hessian = 112 doubles per point per emulator",
                    "points_per_s": pps5, "emulator_points_per_s": pps5 * E,
                    "kernel": "64 x k_predict_full<4,8,2,4,10,1,2,true,false,true> (fused Hessian, phase C) per chunk",
