@@ -1075,7 +1075,8 @@ int bank_cost_device(gpe_bank* b, const double* testing, int64_t N, const double
 // spectra / Jacobians; the PC means / gradients a projection consumes stay on the device as chunk intermediates when
 // the caller did not ask for them.  Caller holds b->host_mu.
 int bank_stream(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
-                double* fwd, double* deriv_full, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
+                double* fwd, double* deriv_full, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr,
+                const Relay* relay = nullptr) {
     const int64_t E = b->E, D = b->D, W = b->W;
     IoList in, out;
     in.add(testing, D);
@@ -1098,12 +1099,13 @@ int bank_stream(gpe_bank* b, const double* testing, int64_t N, double* mu, doubl
                            if (r == GPE_OK && (i_fwd >= 0 || i_dfl >= 0))
                                r = bank_project_device(b, at(i_mu), at(i_der), n, at(i_fwd), at(i_dfl), st);
                            return r;
-                       });
+                       }, relay);
 }
 
 // Host-resident gpe_bank_cost: test points (and per-point observations) stream in, cost / gradient stream out.
 int bank_cost_stream(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
-                     double* cost, double* grad, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr) {
+                     double* cost, double* grad, const StreamPlan* shared_plan = nullptr, ChunkSource* shared = nullptr,
+                     const Relay* relay = nullptr) {
     const int64_t E = b->E, D = b->D;
     if (obs_ld != 0 && obs_ld != E) return fail(GPE_ERR_INVALID, "host observations must be contiguous: obs_ld = E or 0");
     // the shared observation vector and the weights are small: one upload per call
@@ -1131,7 +1133,7 @@ int bank_cost_stream(gpe_bank* b, const double* testing, int64_t N, const double
                            return bank_cost_device(b, (const double*)di[0], n, i_obs >= 0 ? (const double*)di[i_obs] : d_obs1,
                                                    i_obs >= 0 ? E : 0, d_w, i_cost >= 0 ? (double*)dout[i_cost] : nullptr,
                                                    i_grad >= 0 ? (double*)dout[i_grad] : nullptr, st);
-                       });
+                       }, relay);
 }
 
 int bank_check_outputs(gpe_bank* b, int64_t N, const double* testing, double*& mu, double*& var, double*& deriv, double*& hess,
@@ -1508,6 +1510,14 @@ int gpe_multi_predict(gpe_multi* mm, const double* testing, int64_t N, double* m
     const int G = (int)mm->models.size();
     gpe_model* m0 = mm->models[0];
     const int64_t D = m0->D;
+    if (G == 1 || N <= 3 * 64 * (int64_t)m0->sms) {
+        // a call this small is one chunk: the first device serves it on the calling thread (no thread fan-out, and the
+        // mapped-buffer path for the reference's one-point calls stays available) -- same kernels, same result
+        DeviceRestore restore_device;
+        CUDA_TRY(cudaSetDevice(m0->device));
+        std::lock_guard<std::mutex> lock(m0->host_mu);
+        return model_stream(m0, testing, N, mu, var, deriv, hess);
+    }
     IoList in, out;
     in.add(testing, D);
     if (mu) out.add(mu, 1);
@@ -1574,6 +1584,12 @@ int gpe_multi_bank_predict(gpe_multi* mm, const double* testing, int64_t N, doub
     if (N == 0) return GPE_OK;
     const int G = (int)mm->banks.size();
     const int64_t E = b0->E, D = b0->D, W = b0->W;
+    if (G == 1 || N <= 64 * (int64_t)b0->models[0]->sms) {   // one chunk: served by the first device on the calling thread
+        DeviceRestore restore_device;
+        CUDA_TRY(cudaSetDevice(b0->device));
+        std::lock_guard<std::mutex> lock(b0->host_mu);
+        return bank_stream(b0, testing, N, mu, var, deriv, hess, fwd, deriv_full);
+    }
     IoList in, out;   // same arrays, same order as bank_stream builds them: the plan only needs widths and pinned-ness
     in.add(testing, D);
     if (mu || fwd) out.add(mu, E);
@@ -1585,10 +1601,15 @@ int gpe_multi_bank_predict(gpe_multi* mm, const double* testing, int64_t N, doub
     const StreamPlan pl = plan_shared(in, out, N, b0->models[0]->sms, G);
     std::atomic<int64_t> cursor{0};
     ChunkSource src{&cursor, N, pl.CH};
+    const bool relay_ok = pl.in_direct && pl.out_direct && N >= 4 * pl.CH;
+    if (relay_ok) multi_route(mm);
     return run_per_device(G, mm->devices.data(), [&](int g) {
         gpe_bank* b = mm->banks[g];
         std::lock_guard<std::mutex> lock(b->host_mu);
-        return bank_stream(b, testing, N, mu, var, deriv, hess, fwd, deriv_full, &pl, &src);
+        int rc = GPE_OK;
+        const Relay* relay = (relay_ok && mm->routed && !mm->relays.empty()) ? multi_relay(mm, g, pl, in, out, &rc) : nullptr;
+        if (rc) return rc;
+        return bank_stream(b, testing, N, mu, var, deriv, hess, fwd, deriv_full, &pl, &src, relay);
     });
 }
 
@@ -1611,10 +1632,15 @@ int gpe_multi_bank_cost(gpe_multi* mm, const double* testing, int64_t N, const d
     const StreamPlan pl = plan_shared(in, out, N, b0->models[0]->sms, G);
     std::atomic<int64_t> cursor{0};
     ChunkSource src{&cursor, N, pl.CH};
+    const bool relay_ok = pl.in_direct && pl.out_direct && N >= 4 * pl.CH;
+    if (relay_ok) multi_route(mm);
     return run_per_device(G, mm->devices.data(), [&](int g) {
         gpe_bank* b = mm->banks[g];
         std::lock_guard<std::mutex> lock(b->host_mu);
-        return bank_cost_stream(b, testing, N, obs, obs_ld, weights, cost, grad, &pl, &src);
+        int rc = GPE_OK;
+        const Relay* relay = (relay_ok && mm->routed && !mm->relays.empty()) ? multi_relay(mm, g, pl, in, out, &rc) : nullptr;
+        if (rc) return rc;
+        return bank_cost_stream(b, testing, N, obs, obs_ld, weights, cost, grad, &pl, &src, relay);
     });
 }
 

@@ -1195,6 +1195,20 @@ def test_multi_device_nvlink_relay_of_host_traffic(lib, gpemu, monkeypatch):
         for k in ("mu", "var", "deriv"):
             assert np.array_equal(got[k], ref[k]), k
     mm.close()
+    # banks take the same route (test points and per-point observations in, any bank output out)
+    rs = np.random.RandomState(6)
+    Mb, Db, E, Nb = 60, 4, 5, 300_000
+    binp = rs.random_sample((Mb, Db))
+    thetas = rs.random_sample((E, Db + 2)); invQts = rs.random_sample((E, Mb)); invQs = rs.random_sample((E, Mb, Mb))
+    tb = torch.rand(Nb, Db, dtype=torch.float64, generator=torch.Generator().manual_seed(4)).pin_memory().numpy()
+    obs = torch.rand(Nb, E, dtype=torch.float64, generator=torch.Generator().manual_seed(5)).pin_memory().numpy()
+    b1 = gpemu.DeviceBank(binp, thetas, invQts, invQs, device=0)
+    bn = gpemu.DeviceBank(binp, thetas, invQts, invQs, device=devices)
+    r1 = b1.predict(tb, pinned=True); rn = bn.predict(tb, pinned=True)
+    for k in r1:
+        assert np.array_equal(r1[k], rn[k]), k
+    c1 = b1.cost(tb, obs); cn = bn.cost(tb, obs)
+    assert np.array_equal(c1["cost"], cn["cost"]) and np.array_equal(c1["grad"], cn["grad"])
     monkeypatch.setenv("GPE_MULTI_RELAY", "off")
     mm = gpemu.MultiDeviceModel(inputs, theta, invQt, invQ, devices=devices)
     got = mm.predict(t, out=out)
