@@ -66,6 +66,8 @@ __device__ __forceinline__ void exp_tab_load(double* tab_s, int tid) {   // foll
     if (tid < 64) tab_s[tid] = kExp2Tab[tid];
 }
 
+// (Sixteen interleaved table copies -- every lane on its own bank pair, no look-up conflicts -- were measured in round 2:
+// 1 % SLOWER on k_bank_mean and k_predict_mean2; the conflicts cost LSU wavefronts, which these FP64-bound loops have to spare.)
 __device__ __forceinline__ double exp_neg_tab(double x, const double* tab_s) {
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
     const double t = fma(x, 92.33248261689366, kMagic);            // 64 / ln2
@@ -79,8 +81,11 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* tab_s) {
     q = fma(q, f, 0.5);
     q = fma(q, f, 1.0);
     const double r0 = fma(T, q * f, T);
-    const double r = __hiloint2double(__double2hiint(r0) + ((n >> 6) << 20), __double2loint(r0));
-    return (x < -708.0) ? 0.0 : r;
+    // flush below the normal range (x < -708, -inf included; NaN propagates) with an INTEGER range test on the high word of
+    // x: a DSETP would be one more instruction on the FP64 pipe, which is what bounds every kernel that calls this
+    const bool flush = ((unsigned)__double2hiint(x) - 0xC0862001u) <= (0xFFF00000u - 0xC0862001u);
+    const int hi = __double2hiint(r0) + ((n >> 6) << 20);
+    return __hiloint2double(flush ? 0 : hi, flush ? 0 : __double2loint(r0));
 }
 
 // One FP64 tensor-core op: D(8x8) += A(8x4) * B(4x8), warp-wide (SASS: DMMA.8x8x4).

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
+#include "predict_bank_mean.cuh"
 #include "predict_tf32.cuh"
 #include "predict_tf32_big.cuh"
 #include "predict_var_large.cuh"
@@ -11,7 +12,8 @@ namespace gpe {
 
 #define GPE_DECL_DP(DPV)                                                                                          \
     cudaError_t launch_full_dp##DPV(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st);         \
-    cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
+    cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st);   \
+    cudaError_t launch_bank_mean_dp##DPV(int G, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
 
 GPE_DECL_DP(2)
 GPE_DECL_DP(4)
@@ -31,6 +33,14 @@ cudaError_t launch_var_large(const VarLargeParams& p, int grid, size_t smem, cud
 // at + e lde (project.cu)
 cudaError_t project_rows(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, const double* b_tiled, int E,
                          int W, int Wp, double* out, int accumulate, cudaStream_t st);
+// group sizes the shared-difference bank kernel (predict_bank_mean.cuh) is compiled for: the G x (DP + 1) accumulators
+// of a thread have to stay in registers
+inline bool bank_group_ok(int DP, int G) {
+    if (DP <= 10) return G >= 3 && G <= 5;
+    if (DP == 12) return G == 3 || G == 4;
+    if (DP == 16) return G == 2 || G == 3;
+    return false;
+}
 static const int kTfDpList[] = {4, 8, 12, 16, 32};
 
 // padded input dimensions that have compiled kernels, ascending

@@ -2,6 +2,7 @@
 // Compiled once per DP (-DGPE_DP=..) so the variants build in parallel; see Makefile.
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
+#include "predict_bank_mean.cuh"
 #include "launch.h"
 #include <stdlib.h>
 
@@ -120,6 +121,31 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
     if (e != cudaSuccess) return e;
     kern<<<grid, kMeanThreads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_bank_g(const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    auto kern = k_bank_mean<GPE_DP, G>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kBankThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// group sizes per DP: launch.h::bank_group_ok
+cudaError_t GPE_CAT(launch_bank_mean_dp, GPE_DP)(int G, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+#if GPE_DP <= 10
+    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
+    if (G == 4) return launch_bank_g<4>(p, grid, smem, st);
+    if (G == 5) return launch_bank_g<5>(p, grid, smem, st);
+#elif GPE_DP == 12
+    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
+    if (G == 4) return launch_bank_g<4>(p, grid, smem, st);
+#elif GPE_DP == 16
+    if (G == 2) return launch_bank_g<2>(p, grid, smem, st);
+    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
+#endif
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace gpe

@@ -179,10 +179,15 @@ def test_bank_host_batches_are_chunked(gpemu, monkeypatch):
     for k in ref:
         for name, r in (("one", one), ("chunked", got), ("pinned", pin)):
             assert r[k].shape == ref[k].shape and np.array_equal(r[k], ref[k]), (name, k)
+    # without the variance the bank's means / gradients come from the shared-difference kernel (predict_bank_mean.cuh):
+    # bit-identical between host and device callers of the same request, equal to the variance path to rounding
+    ref_nv = {k: v.cpu().numpy() for k, v in bank.predict(torch.from_numpy(t).cuda(), want_var=False, want_deriv=True,
+                                                          project=True, project_deriv=True).items()}
+    assert orc.ref_err(ref_nv["fwd"], ref["fwd"]) < 1e-13 and orc.ref_err(ref_nv["deriv_full"], ref["deriv_full"]) < 1e-13
     fwd = bank.predict(t, want_var=False, want_deriv=False, want_mu=False, project=True)
-    assert set(fwd) == {"fwd"} and np.array_equal(fwd["fwd"], ref["fwd"])  # PC means stay on the device
+    assert set(fwd) == {"fwd"} and np.array_equal(fwd["fwd"], ref_nv["fwd"])  # PC means stay on the device
     f2, d2 = bank.forward(t)
-    assert np.array_equal(f2, ref["fwd"]) and np.array_equal(d2, ref["deriv_full"])
+    assert np.array_equal(f2, ref_nv["fwd"]) and np.array_equal(d2, ref_nv["deriv_full"])
     monkeypatch.delenv("GPE_SLOT_OUT_BYTES")
     models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
     mu_o, var_o, grad_o, hess_o = orc.bank_predict(models, t[:200], do_hess=True)
@@ -1239,3 +1244,44 @@ def test_smem_guard_traps():
     env.pop("GPE_DEBUG_SHRINK_SMEM")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
     assert "NO-ERROR" in r.stdout, (r.stdout, r.stderr[-500:])
+
+
+# ---- banks: mean + gradient on shared input differences (predict_bank_mean.cuh) ----
+@pytest.mark.parametrize("M,D,E,N", [
+    (250, 10, 20, 1037),   # BASELINE config 4's bank: groups of 5
+    (250, 10, 64, 333),    # config 5's bank without the variance: 13 groups, the last one padded
+    (37, 3, 7, 131),       # ragged everything, DP = 4
+    (60, 5, 3, 1),         # one group of 3, one point, D odd (DP = 6)
+    (300, 8, 11, 95),      # two training chunks (M > 256)
+    (530, 11, 6, 64),      # three chunks, DP = 12: groups of 3
+    (45, 14, 5, 77),       # DP = 16: groups of 3 and 2
+    (33, 2, 4, 4097),      # DP = 2, many tiles per CTA
+    (20, 20, 4, 50),       # DP = 24: no group kernel, one-emulator path
+    (50, 6, 2, 40),        # E < 3: one-emulator path
+])
+def test_bank_mean_gradient_shared_differences(gpemu, M, D, E, N):
+    """Mean and gradient of a bank without the variance (MultivariateEmulator.predict, multivariate_gp.py:195-222; per-band
+    banks): E oracle predicts on the same test points against one launch that shares x_j - t_n between the emulators of a
+    group.  Host and device callers; mean-only and gradient-only requests."""
+    import torch
+    rs = np.random.RandomState(7 * M + E)
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.randn(E, M); invQs = rs.random_sample((E, M, M))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+    t = rs.random_sample((N, D))
+    models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
+    mu_o, _, grad_o = orc.bank_predict(models, t)
+    host = bank.predict(t, want_var=False, want_deriv=True)
+    dev = bank.predict(torch.from_numpy(t).cuda(), want_var=False, want_deriv=True)
+    for name, got in (("host", host), ("device", {k: v.cpu().numpy() for k, v in dev.items()})):
+        assert got["mu"].shape == (N, E) and got["deriv"].shape == (N, E, D), name
+        assert orc.ref_err(got["mu"], mu_o) < TOL, name
+        assert orc.ref_err(got["deriv"], grad_o) < TOL, name
+        for e in range(E):   # per emulator too: a small-output emulator must not hide behind a large one
+            assert orc.ref_err(got["mu"][:, e], mu_o[:, e]) < TOL, (name, e)
+            assert orc.ref_err(got["deriv"][:, e], grad_o[:, e]) < TOL, (name, e)
+    mu_only = bank.predict(t, want_var=False, want_deriv=False)
+    assert np.array_equal(mu_only["mu"], host["mu"])
+    # the variance path (per-emulator fused launches) agrees with it to rounding
+    full = bank.predict(t, want_var=True, want_deriv=True)
+    assert orc.ref_err(full["mu"], host["mu"]) < 1e-13 and orc.ref_err(full["deriv"], host["deriv"]) < 1e-13
