@@ -227,6 +227,8 @@ BankMeanPlan plan_bank_mean(int E, int M, int D, int DP) {
     }
     if (const char* e = getenv("GPE_BANK_G"))   // developer aid: force a group size
         if (bank_group_ok(DP, atoi(e))) g.G = atoi(e);
+    if (const char* e = getenv("GPE_BANK_G"))   // developer aid: force a group size
+        if (bank_group_ok(DP, atoi(e))) g.G = atoi(e);
     if (g.G == 0) return g;
     const int GP = (g.G + 1) & ~1;
     g.ngroups = (E + g.G - 1) / g.G;

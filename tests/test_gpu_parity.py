@@ -571,10 +571,14 @@ def test_full_size_properties_linearity_and_kernel_bound(gpemu):
     assert orc.ref_err(o1["deriv"][ii].cpu().numpy(), deriv) < TOL
 
 
-@pytest.mark.parametrize("M,D,N", [(250, 10, 1500), (1000, 10, 100), (300, 6, 200), (37, 3, 70), (200, 8, 130)])
+@pytest.mark.parametrize("M,D,N", [(250, 10, 1500), (1000, 10, 100), (300, 6, 200), (37, 3, 70), (200, 8, 130),
+                                   (8, 2, 40), (30, 4, 9000), (64, 5, 8000), (100, 10, 7200), (129, 3, 300), (224, 10, 100),
+                                   (256, 7, 64), (257, 7, 33), (420, 4, 50), (512, 10, 40), (700, 2, 30), (1024, 6, 20)])
 def test_symmetric_variance_option(gpemu, M, D, N):
     """Opt-in k^T T k (upper-triangular fold of invQ): exact identity for ANY invQ, incl. the benchmark's
-    non-symmetric random matrix; same 1e-10 bar, mean / gradient bit-identical to the default path."""
+    non-symmetric random matrix; same 1e-10 bar, mean / gradient bit-identical to the default path.  The shapes cover the
+    tile counts of the three configurations (one tile, odd and even numbers of column tiles per warp, Mp = 256 / 512 / 1024
+    exactly) and both the 64-point and the small-batch (16-point, run-time tile count) plans."""
     inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M)
     m0 = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     m1 = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=True)
