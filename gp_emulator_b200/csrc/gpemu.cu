@@ -128,10 +128,11 @@ struct gpe_bank {
     int device = 0, E = 0, M = 0, D = 0, W = 0;
     std::vector<gpe_model*> models;
     MeanBankEntry* d_entries = nullptr;  // per-emulator phase-A data for the one-launch bank mean / Hessian kernel
-    BankMeanPlan gplan;                  // mean + gradient with shared input differences (k_bank_mean), when compiled for (DP, G)
+    // shared input differences (k_bank_mean), when compiled for (DP, G): [1] mean + gradient, [0] means only (larger groups)
+    BankMeanPlan gplan[2];
     double* d_gx = nullptr;              // raw training inputs [nchunks][JC][DP]
-    double* d_galpha = nullptr;          // [ngroups][nchunks][JC][GP]
-    double* d_gw = nullptr;              // [ngroups][2][G][DP]
+    double* d_galpha[2] = {nullptr, nullptr};   // [ngroups][nchunks][JC][GP]
+    double* d_gw[2] = {nullptr, nullptr};       // [ngroups][2][G][DP]
     double* d_basis = nullptr;   // basis pre-tiled as [ks][Wp][4] per slice of 32 emulators, Wp = W rounded up to 128
     int Wp = 0;
     // host-pointer calls (GPE_HOST_PTRS, gpe_bank_forward): the bank's own streaming slots, one call at a time
@@ -199,36 +200,35 @@ cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_
     }
 }
 
-cudaError_t launch_bank_mean(int DP, int G, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_bank_mean(int DP, int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     if (p.smem_need == 0 || p.smem_need > smem) return cudaErrorInvalidConfiguration;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (DP) {
-        case 2: return launch_bank_mean_dp2(G, p, grid, smem, st);
-        case 4: return launch_bank_mean_dp4(G, p, grid, smem, st);
-        case 6: return launch_bank_mean_dp6(G, p, grid, smem, st);
-        case 8: return launch_bank_mean_dp8(G, p, grid, smem, st);
-        case 10: return launch_bank_mean_dp10(G, p, grid, smem, st);
-        case 12: return launch_bank_mean_dp12(G, p, grid, smem, st);
-        case 16: return launch_bank_mean_dp16(G, p, grid, smem, st);
+        case 2: return launch_bank_mean_dp2(G, grad, p, grid, smem, st);
+        case 4: return launch_bank_mean_dp4(G, grad, p, grid, smem, st);
+        case 6: return launch_bank_mean_dp6(G, grad, p, grid, smem, st);
+        case 8: return launch_bank_mean_dp8(G, grad, p, grid, smem, st);
+        case 10: return launch_bank_mean_dp10(G, grad, p, grid, smem, st);
+        case 12: return launch_bank_mean_dp12(G, grad, p, grid, smem, st);
+        case 16: return launch_bank_mean_dp16(G, grad, p, grid, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
 // Group size and shared-memory carve-up of k_bank_mean for a bank of E emulators: the G that minimises the FP64
-// instruction count  ceil(E / G) (G (2D + 12) + 2D)  among the compiled ones; invalid when none is compiled for DP or
-// the one-emulator kernels (E (3D + 14)) would not be slower.
-BankMeanPlan plan_bank_mean(int E, int M, int D, int DP) {
+// instruction count  ceil(E / G) (G (2D + 12) + 2D)  (means only: G (D + 11) + 2D) among the compiled ones; invalid when
+// none is compiled for DP or the one-emulator kernels (E (3D + 13)) would not be slower.
+BankMeanPlan plan_bank_mean(int E, int M, int D, int DP, bool grad) {
     BankMeanPlan g;
-    long best = (long)E * (3 * D + 14);
-    for (int G = 2; G <= 5; ++G) {
-        if (!bank_group_ok(DP, G)) continue;
-        const long cost = (long)((E + G - 1) / G) * (G * (2 * D + 12) + 2 * D);
+    long best = (long)E * (3 * D + 13);
+    const int per_em = grad ? 2 * D + 12 : D + 11;
+    for (int G = 2; G <= 10; ++G) {
+        if (!bank_group_ok(DP, G, grad)) continue;
+        const long cost = (long)((E + G - 1) / G) * (G * per_em + 2 * D);
         if (cost < best) { best = cost; g.G = G; }
     }
-    if (const char* e = getenv("GPE_BANK_G"))   // developer aid: force a group size
-        if (bank_group_ok(DP, atoi(e))) g.G = atoi(e);
-    if (const char* e = getenv("GPE_BANK_G"))   // developer aid: force a group size
-        if (bank_group_ok(DP, atoi(e))) g.G = atoi(e);
+    if (const char* e = getenv(grad ? "GPE_BANK_G" : "GPE_BANK_G_MEAN"))   // developer aid: force a group size
+        if (bank_group_ok(DP, atoi(e), grad)) g.G = atoi(e);
     if (g.G == 0) return g;
     const int GP = (g.G + 1) & ~1;
     g.ngroups = (E + g.G - 1) / g.G;
@@ -239,7 +239,7 @@ BankMeanPlan plan_bank_mean(int E, int M, int D, int DP) {
     g.off_x = off; off += align_up((uint32_t)g.JC * DP * 8u, 16);
     g.off_a = off; off += align_up((uint32_t)g.JC * GP * 8u, 16);
     g.off_w = off; off += align_up(2u * g.G * DP * 8u, 16);
-    g.off_ts = off; off += align_up((uint32_t)kBankTN * (uint32_t)std::max(D, g.G * (DP + 1)) * 8u, 16);
+    g.off_ts = off; off += align_up((uint32_t)kBankTN * (uint32_t)std::max(D, g.G * (grad ? DP + 1 : 1)) * 8u, 16);
     g.smem = off;
     g.valid = true;
     return g;
@@ -1014,20 +1014,22 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
             return GPE_OK;
         }
     }
-    if (hess == nullptr && !with_var && (mu != nullptr || deriv != nullptr) && b->gplan.valid) {
-        // mean + gradient: groups of G emulators evaluated on shared input differences (blockIdx.y = group)
-        const BankMeanPlan& g = b->gplan;
+    if (hess == nullptr && !with_var && (mu != nullptr || deriv != nullptr) && b->gplan[deriv != nullptr].valid) {
+        // means (+ gradients): groups of G emulators evaluated on shared input differences (blockIdx.y = group)
+        const int grad = deriv != nullptr;
+        const BankMeanPlan& g = b->gplan[grad];
         gpe_model* m0 = b->models[0];
         if (g.ngroups > 65535) return fail(GPE_ERR_UNSUPPORTED, "bank size %d exceeds the grid limit", (int)E);
         BankMeanParams p;
         memset(&p, 0, sizeof(p));
         p.testing = testing; p.N = N; p.mu = mu; p.deriv = deriv;
-        p.xraw = b->d_gx; p.galpha = b->d_galpha; p.gw = b->d_gw;
+        p.xraw = b->d_gx; p.galpha = b->d_galpha[grad]; p.gw = b->d_gw[grad];
         p.M = m0->M; p.D = m0->D; p.E = (int)E; p.JC = g.JC; p.nchunks = g.nchunks;
         p.off_x = g.off_x; p.off_a = g.off_a; p.off_w = g.off_w; p.off_ts = g.off_ts; p.smem_need = g.smem;
         const int64_t ntiles = (N + kBankTN - 1) / kBankTN;
-        const int gx = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)m0->sms * 2 / g.ngroups));   // two resident CTAs per SM
-        CUDA_TRY(launch_bank_mean(m0->DP, g.G, p, dim3(gx, (unsigned)g.ngroups), g.smem, stream));
+        const int resident = grad ? 2 : 3;   // CTAs per SM (launch bounds of k_bank_mean)
+        const int gx = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)m0->sms * resident / g.ngroups));
+        CUDA_TRY(launch_bank_mean(m0->DP, g.G, grad != 0, p, dim3(gx, (unsigned)g.ngroups), g.smem, stream));
         return GPE_OK;
     }
     if (hess != nullptr || (!with_var && (mu != nullptr || deriv != nullptr))) {
@@ -1417,35 +1419,39 @@ int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const
         if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "bank upload failed: %s", cudaGetErrorString(e)); }
     }
     {
-        // operands of the shared-difference mean + gradient kernel (predict_bank_mean.cuh)
+        // operands of the shared-difference kernels (predict_bank_mean.cuh): [1] mean + gradient, [0] means only
         static const bool off = []{ const char* e = getenv("GPE_BANK_SHARED"); return e && !strcmp(e, "off"); }();
         const int DP = b->models[0]->DP;
-        BankMeanPlan g = off ? BankMeanPlan() : plan_bank_mean(E, M, D, DP);
-        if (g.valid) {
+        for (int grad = 0; grad < 2 && !off; ++grad) {
+            BankMeanPlan g = plan_bank_mean(E, M, D, DP, grad != 0);
+            if (!g.valid) continue;
             const int G = g.G, GP = (G + 1) & ~1;
-            std::vector<double> gx((size_t)g.nchunks * g.JC * DP, 0.0);
             std::vector<double> galpha((size_t)g.ngroups * g.nchunks * g.JC * GP, 0.0);
             std::vector<double> gw((size_t)g.ngroups * 2 * G * DP, 0.0);
-            for (int j = 0; j < M; ++j)
-                for (int d = 0; d < D; ++d) gx[(size_t)j * DP + d] = inputs[(size_t)j * D + d];   // chunks are contiguous: c JC + jl = j
             for (int e2 = 0; e2 < E; ++e2) {
                 const int grp = e2 / G, el = e2 - grp * G;
                 const double* ex = expX + (size_t)e2 * (D + 1);
-                for (int j = 0; j < M; ++j)
+                for (int j = 0; j < M; ++j)   // chunks are contiguous: c JC + jl = j
                     galpha[((size_t)grp * g.nchunks * g.JC + j) * GP + el] = ex[D] * invQt[(size_t)e2 * M + j];
                 for (int d = 0; d < D; ++d) {
                     gw[((size_t)grp * 2 * G + el) * DP + d] = -0.5 * ex[d];
                     gw[((size_t)grp * 2 * G + G + el) * DP + d] = ex[d];
                 }
             }
-            cudaError_t e = cudaMalloc((void**)&b->d_gx, gx.size() * 8);
-            if (e == cudaSuccess) e = cudaMemcpy(b->d_gx, gx.data(), gx.size() * 8, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_galpha, galpha.size() * 8);
-            if (e == cudaSuccess) e = cudaMemcpy(b->d_galpha, galpha.data(), galpha.size() * 8, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_gw, gw.size() * 8);
-            if (e == cudaSuccess) e = cudaMemcpy(b->d_gw, gw.data(), gw.size() * 8, cudaMemcpyHostToDevice);
+            cudaError_t e = cudaSuccess;
+            if (!b->d_gx) {
+                std::vector<double> gx((size_t)g.nchunks * g.JC * DP, 0.0);
+                for (int j = 0; j < M; ++j)
+                    for (int d = 0; d < D; ++d) gx[(size_t)j * DP + d] = inputs[(size_t)j * D + d];
+                e = cudaMalloc((void**)&b->d_gx, gx.size() * 8);
+                if (e == cudaSuccess) e = cudaMemcpy(b->d_gx, gx.data(), gx.size() * 8, cudaMemcpyHostToDevice);
+            }
+            if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_galpha[grad], galpha.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(b->d_galpha[grad], galpha.data(), galpha.size() * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_gw[grad], gw.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(b->d_gw[grad], gw.data(), gw.size() * 8, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) { gpe_bank_destroy(b); return fail(GPE_ERR_CUDA, "bank upload failed: %s", cudaGetErrorString(e)); }
-            b->gplan = g;
+            b->gplan[grad] = g;
         }
     }
     if (basis) {
@@ -1472,8 +1478,10 @@ int gpe_bank_destroy(gpe_bank* b) {
     if (b->d_basis) cudaFree(b->d_basis);
     if (b->d_entries) cudaFree(b->d_entries);
     if (b->d_gx) cudaFree(b->d_gx);
-    if (b->d_galpha) cudaFree(b->d_galpha);
-    if (b->d_gw) cudaFree(b->d_gw);
+    for (int i = 0; i < 2; ++i) {
+        if (b->d_galpha[i]) cudaFree(b->d_galpha[i]);
+        if (b->d_gw[i]) cudaFree(b->d_gw[i]);
+    }
     if (b->d_aux) cudaFree(b->d_aux);
     if (b->cost_d) cudaFree(b->cost_d);
     if (b->cost_free) cudaEventDestroy(b->cost_free);

@@ -13,7 +13,7 @@ namespace gpe {
 #define GPE_DECL_DP(DPV)                                                                                          \
     cudaError_t launch_full_dp##DPV(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st);         \
     cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st);   \
-    cudaError_t launch_bank_mean_dp##DPV(int G, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
+    cudaError_t launch_bank_mean_dp##DPV(int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
 
 GPE_DECL_DP(2)
 GPE_DECL_DP(4)
@@ -34,8 +34,9 @@ cudaError_t launch_var_large(const VarLargeParams& p, int grid, size_t smem, cud
 cudaError_t project_rows(const double* A, int64_t R, int RD, int64_t ldn, int64_t lde, int64_t ldd, const double* b_tiled, int E,
                          int W, int Wp, double* out, int accumulate, cudaStream_t st);
 // group sizes the shared-difference bank kernel (predict_bank_mean.cuh) is compiled for: the G x (DP + 1) accumulators
-// of a thread have to stay in registers
-inline bool bank_group_ok(int DP, int G) {
+// of a thread (G without the gradient) have to stay in registers
+inline bool bank_group_ok(int DP, int G, bool grad) {
+    if (!grad) return DP <= 16 && (G == 4 || G == 5 || G == 8 || G == 10);
     if (DP <= 10) return G >= 3 && G <= 5;
     if (DP == 12) return G == 3 || G == 4;
     if (DP == 16) return G == 2 || G == 3;

@@ -47,11 +47,14 @@ struct BankMeanParams {
     uint32_t off_x, off_a, off_w, off_ts, smem_need;   // shared-memory byte offsets / extent (host: plan_bank_mean)
 };
 
-template <int DP, int G>
-__global__ void __launch_bounds__(kBankThreads, 2) k_bank_mean(const BankMeanParams p) {
+// GRAD = false: means only (MultivariateEmulator.predict(do_deriv=False), forward modelling): the accumulators shrink to one
+// per emulator, so groups of up to 10 fit and D + 11 + 2D / G = 23 operations per (pair, emulator) remain at D = 10.
+template <int DP, int G, bool GRAD>
+__global__ void __launch_bounds__(kBankThreads, GRAD ? 2 : 3) k_bank_mean(const BankMeanParams p) {
     constexpr int TN = kBankTN;
     constexpr int GP = (G + 1) & ~1;
-    constexpr int NV = G * (DP + 1);          // values per point: G x [mu, g_0 .. g_{DP-1}]
+    constexpr int AV = GRAD ? DP + 1 : 1;     // accumulators per emulator: mu [, g_0 .. g_{DP-1}]
+    constexpr int NV = G * AV;                // values per point
     constexpr int H1 = (NV + 1) / 2, H2 = (H1 + 1) / 2;
     extern __shared__ __align__(128) unsigned char smem_bm[];
     double* Xs = reinterpret_cast<double*>(smem_bm + p.off_x);     // [JC][DP]
@@ -104,11 +107,11 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_bank_mean(const BankMeanPar
         for (int d = 0; d < DP; ++d) t[d] = (d < D) ? ts_s[n_loc * D + d] : 0.0;
         if (tile + gridDim.x < ntiles) fetch_rows(tile + gridDim.x);
 
-        double acc[G][DP + 1];
+        double acc[G][AV];
 #pragma unroll
         for (int e = 0; e < G; ++e)
 #pragma unroll
-            for (int i = 0; i <= DP; ++i) acc[e][i] = 0.0;
+            for (int i = 0; i < AV; ++i) acc[e][i] = 0.0;
 
         for (int c = 0; c < p.nchunks; ++c) {
             if (!resident) {
@@ -162,8 +165,10 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_bank_mean(const BankMeanPar
                                 }
                                 const double cj = exp_neg_tab(r, exp_tab) * (h ? a2.y : a2.x);
                                 acc[e][0] += cj;
+                                if constexpr (GRAD) {
 #pragma unroll
-                                for (int d = 0; d < DP; ++d) acc[e][1 + d] = fma(cj, u[d], acc[e][1 + d]);
+                                    for (int d = 0; d < DP; ++d) acc[e][1 + d] = fma(cj, u[d], acc[e][1 + d]);
+                                }
                             }
                         }
                     }
@@ -179,8 +184,8 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_bank_mean(const BankMeanPar
 #pragma unroll
             for (int i = 0; i < H1; ++i) {
                 const int ia = i, ib = H1 + i;
-                const int ea = ia / (DP + 1), va = ia % (DP + 1);
-                const int eb = ib / (DP + 1), vb = ib % (DP + 1);
+                const int ea = ia / AV, va = ia % AV;
+                const int eb = ib / AV, vb = ib % AV;
                 const double lo = acc[ea][va];
                 const double hi = (ib < NV) ? acc[eb < G ? eb : 0][vb] : 0.0;
                 const double send = b1 ? lo : hi, keep = b1 ? hi : lo;
@@ -208,15 +213,15 @@ __global__ void __launch_bounds__(kBankThreads, 2) k_bank_mean(const BankMeanPar
         if (p.mu != nullptr) {
             for (int e = tid; e < npts * gact; e += kBankThreads) {
                 const int r = e / gact, em = e - r * gact;
-                p.mu[(n0 + r) * (int64_t)p.E + e0 + em] = outs[r * NV + em * (DP + 1)];
+                p.mu[(n0 + r) * (int64_t)p.E + e0 + em] = outs[r * NV + em * AV];
             }
         }
-        if (p.deriv != nullptr) {
+        if (GRAD && p.deriv != nullptr) {
             const int gd = gact * D;
             const double* wout = Ws + G * DP;
             for (int e = tid; e < npts * gd; e += kBankThreads) {
                 const int r = e / gd, q = e - r * gd, em = q / D, d = q - em * D;
-                p.deriv[((n0 + r) * (int64_t)p.E + e0 + em) * D + d] = wout[em * DP + d] * outs[r * NV + em * (DP + 1) + 1 + d];
+                p.deriv[((n0 + r) * (int64_t)p.E + e0 + em) * D + d] = wout[em * DP + d] * outs[r * NV + em * AV + 1 + d];
             }
         }
     }

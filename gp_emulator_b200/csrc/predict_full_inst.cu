@@ -123,9 +123,9 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
     return cudaGetLastError();
 }
 
-template <int G>
+template <int G, bool GRAD>
 static cudaError_t launch_bank_g(const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    auto kern = k_bank_mean<GPE_DP, G>;
+    auto kern = k_bank_mean<GPE_DP, G, GRAD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kBankThreads, smem, st>>>(p);
@@ -133,17 +133,26 @@ static cudaError_t launch_bank_g(const BankMeanParams& p, dim3 grid, size_t smem
 }
 
 // group sizes per DP: launch.h::bank_group_ok
-cudaError_t GPE_CAT(launch_bank_mean_dp, GPE_DP)(int G, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+cudaError_t GPE_CAT(launch_bank_mean_dp, GPE_DP)(int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+#if GPE_DP <= 16
+    if (!grad) {
+        if (G == 4) return launch_bank_g<4, false>(p, grid, smem, st);
+        if (G == 5) return launch_bank_g<5, false>(p, grid, smem, st);
+        if (G == 8) return launch_bank_g<8, false>(p, grid, smem, st);
+        if (G == 10) return launch_bank_g<10, false>(p, grid, smem, st);
+        return cudaErrorInvalidValue;
+    }
+#endif
 #if GPE_DP <= 10
-    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
-    if (G == 4) return launch_bank_g<4>(p, grid, smem, st);
-    if (G == 5) return launch_bank_g<5>(p, grid, smem, st);
+    if (G == 3) return launch_bank_g<3, true>(p, grid, smem, st);
+    if (G == 4) return launch_bank_g<4, true>(p, grid, smem, st);
+    if (G == 5) return launch_bank_g<5, true>(p, grid, smem, st);
 #elif GPE_DP == 12
-    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
-    if (G == 4) return launch_bank_g<4>(p, grid, smem, st);
+    if (G == 3) return launch_bank_g<3, true>(p, grid, smem, st);
+    if (G == 4) return launch_bank_g<4, true>(p, grid, smem, st);
 #elif GPE_DP == 16
-    if (G == 2) return launch_bank_g<2>(p, grid, smem, st);
-    if (G == 3) return launch_bank_g<3>(p, grid, smem, st);
+    if (G == 2) return launch_bank_g<2, true>(p, grid, smem, st);
+    if (G == 3) return launch_bank_g<3, true>(p, grid, smem, st);
 #endif
     return cudaErrorInvalidValue;
 }
