@@ -257,28 +257,35 @@ def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
     fwd_b = torch.empty(CH, W, dtype=torch.float64, device=dev)
     st = torch.cuda.current_stream(dev_index).cuda_stream
 
-    def cfg4_pass(project=True):
+    def cfg4_pass(project=True, grad=True):
         for c0 in range(0, N, CH):      # the 168 GB of spectra are produced chunk-wise into one 3.4 GB buffer
-            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + CH].data_ptr(), CH, mu_b.data_ptr(), None, der_b.data_ptr(), None,
-                                           fwd_b.data_ptr() if project else None, None, 0x01 | 0x04 | (0x10 if project else 0), st))
+            _check(lib.gpe_bank_predict_ex(bank._h, t[c0:c0 + CH].data_ptr(), CH, mu_b.data_ptr(), None,
+                                           der_b.data_ptr() if grad else None, None, fwd_b.data_ptr() if project else None, None,
+                                           0x01 | (0x04 if grad else 0) | (0x10 if project else 0), st))
     pps4 = rate(cfg4_pass, N, reps=1, warm=1)
     pps4_pc = rate(lambda: cfg4_pass(False), N, reps=1, warm=0)
+    pps4_fwd = rate(lambda: cfg4_pass(True, False), N, reps=1, warm=0)   # MultivariateEmulator.predict(do_deriv=False)
     proj_s = 1.0 / pps4 - 1.0 / pps4_pc
     out["cfg4"] = {"workload": "MultivariateEmulator bank P=20 PCs, W=2101 wavelengths, M=250 D=10; 1e7 device-resident test inputs in "
                                "chunks of 2e5: PC means + PC gradients + back-projected spectra fwd (N, 2101)",
                    "points_per_s": pps4, "pc_space_only_points_per_s": pps4_pc,
-                   "kernel": "k_predict_mean2<10,false> (bank: blockIdx.y = PC) + k_project_tma<5,1> (tensor-map TMA stores)",
+                   "forward_only_points_per_s": pps4_fwd,
+                   "forward_only_note": "PC means (no gradients) + spectra: k_bank_mean<10,10,false>, 23 FP64 instructions per "
+                                        "(pair, PC); MultivariateEmulator.predict(do_deriv=False) on a batch",
+                   "kernel": "k_bank_mean<10,5,true> (groups of 5 PCs share x_j - t_n; blockIdx.y = group) + k_project_tma<5,1> "
+                             "(tensor-map TMA stores)",
                    "roofline": {"bound": "hbm", "achieved": W * 8 / proj_s / 1e9 if proj_s > 0 else None, "peak": hbm_gbs, "unit": "GB/s",
                                 "frac": (W * 8 / proj_s / 1e9 / hbm_gbs) if proj_s > 0 else None,
                                 "note": "the back-projection kernel alone: algorithmic bytes = 8 W = 16,808 B of spectrum written per "
                                         "point (SURVEY 8d) / its time (step with projection - step without, CUDA events); peak = "
                                         "MEASURED_PEAKS.json hbm_gbs"},
-                   "step_roofline": {"bound": "fp64 pipe (instruction issue)", "achieved": pps4_pc * P * M * 45 / 1e12,
+                   "step_roofline": {"bound": "fp64 pipe (instruction issue)", "achieved": pps4_pc * P * M * 36 / 1e12,
                                      "peak": peaks["dfma_tflops"] / 2.0, "unit": "T FP64 instr/s",
-                                     "frac": pps4_pc * P * M * 45 / 1e12 / (peaks["dfma_tflops"] / 2.0),
+                                     "frac": pps4_pc * P * M * 36 / 1e12 / (peaks["dfma_tflops"] / 2.0),
                                      "spectra_GBps_whole_step": pps4 * W * 8 / 1e9,
                                      "note": "the STEP is bound by the P = 20 mean + gradient evaluations, not by the projection "
-                                             "(%.0f %% of its time): 45 FP64 instructions per (test, train) pair and PC against the "
+                                             "(%.0f %% of its time): 36 FP64 instructions per (test, train) pair and PC (2D + 12 + 2D/5: the "
+                                             "differences are shared by 5 PCs; 43 in the one-emulator kernel) against the "
                                              "measured DFMA instruction rate" % (100.0 * pps4 / pps4_pc)},
                    "parity_vs_oracle": par4}
     # host-resident: numpy in, PC-space outputs out (1,760 B per point back over PCIe), chunk walk below the C ABI

@@ -1,4 +1,4 @@
-// Variance contraction for 1024 < M <= 4096 training points (FP64, sm_100a).
+// Variance contraction for 1024 < M <= GPE_MAX_TRAIN (16384) training points (FP64, sm_100a).
 //
 // The fused kernel (predict_full.cuh) keeps the whole K* tile in shared memory and the whole TN x Mp accumulator
 // tile in registers; neither fits beyond M = 1024.  Here the work is split in two launches per batch of points:

@@ -45,7 +45,8 @@ typedef enum gpe_status {
 #define GPE_F32_FAST_TF32 0x200u /* gpe_predict_f32 only: one TF32 pass for the variance instead of the 3xTF32 split */
 #define GPE_F32_FORCE_3X  0x400u /* gpe_predict_f32 only: 3xTF32 split also for M > 256 (default there: one pass) */
 
-#define GPE_MAX_TRAIN 4096     /* largest M with a variance path: fused kernel to 1024, K*-scratch + column passes above */
+#define GPE_MAX_TRAIN 16384    /* largest M with a variance path: fused kernel to 1024, K*-scratch + column passes above
+                                  (a bound on the packed invQ image, 2 GB at 16384; mean / gradient / Hessian have no limit) */
 #define GPE_MAX_INPUTS 32      /* largest D */
 
 typedef struct gpe_model gpe_model;  /* one trained GP resident on one device */

@@ -627,12 +627,12 @@ def test_symmetric_variance_auto_mode(gpemu):
 def test_documented_limits_raise_cleanly(gpemu):
     """M > GPE_MAX_TRAIN (variance) is reported as GPE_ERR_UNSUPPORTED, never a wrong answer."""
     rs = np.random.RandomState(1)
-    M = 4100
+    M = 16400
     inputs = rs.random_sample((M, 3)); theta = rs.random_sample(5); invQt = rs.random_sample(M)
-    invQ = rs.random_sample((M, M))
+    invQ = np.zeros((M, M))          # never read: the limit is checked first
     testing = rs.random_sample((20, 3))
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
-    with pytest.raises(gpemu.GpemuError, match="M <= 4096"):
+    with pytest.raises(gpemu.GpemuError, match="M <= 16384"):
         m.predict(testing)
     o = m.predict(testing, want_var=False)               # mean + gradient have no M limit
     mu, _, deriv = orc.predict(inputs, theta, invQ, invQt, testing, do_unc=False)
@@ -640,9 +640,9 @@ def test_documented_limits_raise_cleanly(gpemu):
 
 
 @pytest.mark.parametrize("M,D,N", [(1025, 4, 300), (1100, 3, 20), (1500, 10, 2500), (2048, 6, 777), (2500, 10, 100),
-                                   (4096, 2, 50)])
+                                   (4096, 2, 50), (4500, 3, 40), (6000, 2, 17)])
 def test_large_m_variance(gpemu, M, D, N):
-    """1024 < M <= 4096: K* goes through a scratch buffer and the contraction runs in column passes
+    """1024 < M <= GPE_MAX_TRAIN: K* goes through a scratch buffer and the contraction runs in column passes
     (predict_var_large.cuh).  Same formula as GaussianProcess.py:232-247, same tolerance."""
     import torch
     inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M % 97)
