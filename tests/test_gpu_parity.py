@@ -1297,3 +1297,44 @@ def test_bank_mean_gradient_shared_differences(gpemu, M, D, E, N):
     # the variance path (per-emulator fused launches) agrees with it to rounding
     full = bank.predict(t, want_var=True, want_deriv=True)
     assert orc.ref_err(full["mu"], host["mu"]) < 1e-13 and orc.ref_err(full["deriv"], host["deriv"]) < 1e-13
+
+
+def test_non_finite_and_far_away_test_points_follow_numpy(gpemu):
+    """Edge rows the reference handles by IEEE arithmetic (GaussianProcess.py:228-247): a test point so far away that every
+    covariance underflows (mu = 0, var = b, deriv = 0), one with a NaN coordinate (its outputs are NaN, nobody else's) and
+    one with an infinite coordinate (exp(-inf) = 0: mu = 0, var = b; the gradient is 0 * inf = NaN in that dimension).
+    Same pattern of non-finite values as numpy, same finite values, for the fused, the mean-only and the bank kernels."""
+    rs = np.random.RandomState(77)
+    M, D, E = 120, 5, 6
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, 70, seed=5)
+    testing = testing.copy()
+    testing[3] = 1e3                       # exponent ~ -1e6: underflow
+    testing[10] = 40.0                     # exponent ~ -2e3: below the normal range
+    testing[17, 2] = np.nan
+    testing[33, 0] = np.inf
+    testing[34, 4] = -np.inf
+    testing[50] = 1e200                    # squares overflow to inf
+
+    def same(got, ref, what):
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), what
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), ok), what
+        assert orc.ref_err(got[ok], ref[ok]) < TOL, what
+
+    with np.errstate(all="ignore"):
+        mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    assert mu[3] == 0.0 and mu[50] == 0.0 and np.isnan(mu[17]) and np.isnan(deriv[33, 0]) and mu[33] == 0.0
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    full = m.predict(testing)
+    mean_only = m.predict(testing, want_var=False)
+    for k, r in (("mu", mu), ("var", var), ("deriv", deriv)):
+        same(full[k], r, ("fused", k))
+        if k != "var":
+            same(mean_only[k], r, ("mean", k))
+    thetas = rs.random_sample((E, D + 2)); invQts = rs.randn(E, M)
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, None)
+    with np.errstate(all="ignore"):
+        mu_b, _, grad_b = orc.bank_predict([(inputs, thetas[e], invQ, invQts[e]) for e in range(E)], testing)
+    got = bank.predict(testing, want_var=False, want_deriv=True)
+    same(got["mu"], mu_b, "bank mu"); same(got["deriv"], grad_b, "bank deriv")
+    same(bank.predict(testing, want_var=False, want_deriv=False)["mu"], mu_b, "bank means only")
