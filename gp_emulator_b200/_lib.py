@@ -19,7 +19,7 @@ WANT_FWD, WANT_DERIV_FULL = 0x10, 0x20
 OPT_SYMMETRIC_VARIANCE = 0x1
 F32_FAST_TF32 = 0x200
 F32_FORCE_3X = 0x400
-MAX_TRAIN, MAX_INPUTS = 16384, 32
+MAX_TRAIN, MAX_INPUTS = 16384, 256
 TRAIN_MAX_M = 1024
 
 # every symbol include/gpemu.h declares (tests/test_abi.py checks the header against this list and the .so)

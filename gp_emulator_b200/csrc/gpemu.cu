@@ -27,6 +27,7 @@
 
 #include "../../include/gpemu.h"
 #include "launch.h"
+#include "predict_generic.cuh"
 #include "gpe_math.cuh"
 #include "host_common.h"
 #include "host_stream.h"
@@ -114,6 +115,12 @@ struct gpe_model {
     double centre[32];
     bool hess_fused_ok = false;
     double* d_xchunks_mean = nullptr;
+    // D > 32: generic kernels (predict_generic.cuh) + the large-M variance kernel on the same K* scratch
+    bool generic = false;
+    double* d_gen_xs = nullptr;     // (M, D) inputs scaled by sqrt(w)
+    double* d_gen_alpha = nullptr;  // (M) b * invQt
+    double* d_gen_sqw = nullptr;    // (D)
+    double* d_gen_mu = nullptr;     // (large_chunk) means of the sub-batch in flight
     Tf32Plan tf, tfx;            // single-precision tcgen05 paths: fast (1 x TF32) and precise (3 x TF32); lazy
     float* d_xa_f32 = nullptr;
     uint32_t* d_bslabs = nullptr;
@@ -406,6 +413,59 @@ int build_hessian_operand(gpe_model* m, const double* inputs, const double* invQ
     return GPE_OK;
 }
 
+// D > 32 (predict_generic.cuh): K* of a sub-batch into the model's scratch, then gradient / variance / Hessian from it.
+int predict_generic(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
+                    int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess, cudaStream_t st) {
+    if (var != nullptr && !m->has_invQ) return fail(GPE_ERR_INVALID, "variance requested but the model was created without invQ");
+    if (var != nullptr && !m->large_valid)
+        return fail(GPE_ERR_UNSUPPORTED, "variance contraction supports M <= %d (got M = %d)", GPE_MAX_TRAIN, m->M);
+    const int D = m->D;
+    const size_t smem_k = ((size_t)(kGenTN + kGenJC) * (D + 1) + 128) * 8;
+    CUDA_TRY(cudaFuncSetAttribute(k_generic_kstar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+    std::lock_guard<std::mutex> scratch_lock(m->scratch_mu);   // one caller at a time between wait and record (see below)
+    CUDA_TRY(cudaStreamWaitEvent(st, m->scratch_free, 0));
+    for (int64_t n0 = 0; n0 < N; n0 += m->large_chunk) {
+        const int64_t n = std::min(m->large_chunk, N - n0);
+        GenericParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing + n0 * D; p.N = n;
+        p.mu = mu ? mu + n0 * ld_mu : nullptr;
+        p.deriv = deriv ? deriv + n0 * ld_deriv : nullptr;
+        p.hess = hess ? hess + n0 * ld_hess : nullptr;
+        p.ld_mu = ld_mu; p.ld_deriv = ld_deriv; p.ld_hess = ld_hess;
+        p.xs = m->d_gen_xs; p.alpha = m->d_gen_alpha; p.sqw = m->d_gen_sqw;
+        p.kstar = m->d_kscratch; p.mu_tmp = m->d_gen_mu;
+        p.M = m->M; p.D = D; p.kblk = m->large_kblk;
+        const int64_t tiles = (n + kGenTN - 1) / kGenTN;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        k_generic_kstar<<<(unsigned)std::min<int64_t>(tiles, (int64_t)m->sms * 4), kGenThreads, smem_k, st>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        if (deriv != nullptr) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            k_generic_grad<<<dim3((unsigned)std::min<int64_t>(tiles, (int64_t)m->sms * 8), (unsigned)std::min((D + 15) / 16, 16)),
+                             kGenThreads, 0, st>>>(p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (var != nullptr) {
+            VarLargeParams v;
+            memset(&v, 0, sizeof(v));
+            v.kstar = m->d_kscratch; v.s_tiled = m->d_stiled; v.var = var + n0 * ld_var; v.ld_var = ld_var; v.N = n;
+            v.Mp = m->large_Mp; v.kblk = m->large_kblk; v.npass = (m->large_Mp + kVlPass - 1) / kVlPass;
+            v.nstage = m->large_nstage; v.b = m->b;
+            const size_t smem = 128 + kVlWarps * kVlTN * 8 + (size_t)v.nstage * kVlStageBytes;
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(launch_var_large(v, (int)std::min<int64_t>((n + kVlTN - 1) / kVlTN, m->sms), smem, st));
+        }
+        if (hess != nullptr) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            k_generic_hess<<<(unsigned)std::min<int64_t>(n, (int64_t)m->sms * 8), kGenThreads, 0, st>>>(p);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    CUDA_TRY(cudaEventRecord(m->scratch_free, st));
+    return GPE_OK;
+}
+
 // Launch the kernels for device-resident data on `st`.  Output strides allow bank (point-major) layouts.
 int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                    double* hess, int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess,
@@ -414,6 +474,7 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     // summation order depend on it, not on the chunk, so that one call is internally consistent
     if (call_N < 0) call_N = N;
     if (N == 0) return GPE_OK;
+    if (m->generic) return predict_generic(m, testing, N, mu, var, deriv, hess, ld_mu, ld_var, ld_deriv, ld_hess, st);
     bool mean_done = false;
     static const bool force_full = getenv("GPE_FORCE_FULL") != nullptr;  // dev aid: time phase A alone
     // the Hessian rides on the fused kernel when the model qualifies (build_hessian_operand); without a variance
@@ -776,7 +837,7 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
     *out = nullptr;
     if (!inputs || !expX || !invQt) return fail(GPE_ERR_INVALID, "inputs, expX and invQt must be non-NULL");
     if (M < 1) return fail(GPE_ERR_INVALID, "M must be >= 1 (got %d)", M);
-    if (D < 1 || D > GPE_MAX_INPUTS) return fail(GPE_ERR_INVALID, "D must be in [1, %d] (got %d)", GPE_MAX_INPUTS, D);
+    if (D < 1 || D > GPE_MAX_INPUTS) return fail(GPE_ERR_INVALID, "D must be in [1, %d] (got %d)", GPE_MAX_INPUTS, D);   // 256
     int sms = 0;
     int rc = check_device(device, &sms);
     if (rc) return rc;
@@ -787,6 +848,45 @@ int gpe_model_create_ex(int device, int M, int D, const double* inputs, const do
     for (int d = 0; d < 32; ++d) m->sqrt_w[d] = (d < D) ? std::sqrt(expX[d]) : 0.0;
     m->has_invQ = invQ != nullptr;
     m->symmetric = (options & GPE_OPT_SYMMETRIC_VARIANCE) != 0;
+    if (D > 32) {
+        // no per-D compiled kernels beyond 32 inputs: generic kernels on the K* scratch of the large-M path
+        // (predict_generic.cuh); the symmetric fold does not apply (k_var_large reads the plain operand)
+        m->generic = true;
+        m->symmetric = false;
+        m->large_Mp = (M + 63) / 64 * 64;
+        m->large_kblk = m->large_Mp / 4;
+        m->large_nstage = 6;
+        m->large_chunk = 16 * (int64_t)m->sms * 4;
+        std::vector<double> xs((size_t)M * D), al(M), sq(D);
+        for (int d = 0; d < D; ++d) sq[d] = std::sqrt(expX[d]);
+        for (int j = 0; j < M; ++j) {
+            for (int d = 0; d < D; ++d) xs[(size_t)j * D + d] = sq[d] * inputs[(size_t)j * D + d];
+            al[j] = m->b * invQt[j];
+        }
+        const size_t scratch = (size_t)(m->large_chunk / 16) * m->large_kblk * 64 * 8;
+        cudaError_t e = cudaMalloc((void**)&m->d_gen_xs, xs.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_gen_xs, xs.data(), xs.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_gen_alpha, al.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_gen_alpha, al.data(), al.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_gen_sqw, sq.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_gen_sqw, sq.data(), sq.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_gen_mu, (size_t)m->large_chunk * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m->d_kscratch, scratch);
+        if (e == cudaSuccess) e = cudaMemset(m->d_kscratch, 0, scratch);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->scratch_free, cudaEventDisableTiming);
+        if (e == cudaSuccess && invQ && M <= GPE_MAX_TRAIN) {
+            const size_t Mp = (size_t)m->large_Mp;
+            std::vector<double> st((size_t)m->large_kblk * Mp * 4, 0.0);
+            for (int j = 0; j < M; ++j)
+                for (int i = 0; i < M; ++i) st[((size_t)(i >> 2) * Mp + j) * 4 + (i & 3)] = invQ[(size_t)j * M + i];
+            e = cudaMalloc((void**)&m->d_stiled, st.size() * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(m->d_stiled, st.data(), st.size() * 8, cudaMemcpyHostToDevice);
+            m->large_valid = e == cudaSuccess;
+        }
+        if (e != cudaSuccess) { gpe_model_destroy(m); return fail(GPE_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(e)); }
+        *out = m;
+        return GPE_OK;
+    }
     m->h_inputs.assign(inputs, inputs + (size_t)M * D);
     m->h_invQt.assign(invQt, invQt + M);
     if (invQ && M <= 1024) m->h_invQ.assign(invQ, invQ + (size_t)M * M);
@@ -858,6 +958,10 @@ int gpe_model_destroy(gpe_model* m) {
     if (m->d_kscratch) cudaFree(m->d_kscratch);
     if (m->scratch_free) cudaEventDestroy(m->scratch_free);
     if (m->d_xchunks_mean) cudaFree(m->d_xchunks_mean);
+    if (m->d_gen_xs) cudaFree(m->d_gen_xs);
+    if (m->d_gen_alpha) cudaFree(m->d_gen_alpha);
+    if (m->d_gen_sqw) cudaFree(m->d_gen_sqw);
+    if (m->d_gen_mu) cudaFree(m->d_gen_mu);
     if (m->d_xa_f32) cudaFree(m->d_xa_f32);
     if (m->d_bslabs) cudaFree(m->d_bslabs);
     if (m->d_bslabs_lo) cudaFree(m->d_bslabs_lo);
@@ -878,6 +982,9 @@ int gpe_model_plan(gpe_model* m, int64_t N, char* buf, int len) {
                         MT[f.cfg], nt_inst, WR[f.cfg], WC[f.cfg], m->DP, MINB[f.cfg], KB[f.cfg], nt_inst == f.nt_act ? "true" : "false",
                         m->symmetric ? "true" : "false", f.cfg, f.TN, f.Mp, f.nstage, f.smem);
     };
+    if (m->generic)
+        return snprintf(buf, len, "k_generic_kstar + k_generic_grad%s (D = %d > 32: generic kernels on the K* scratch)",
+                        m->large_valid ? " + k_var_large" : "", m->D);
     if (m->full.valid) {
         const bool small = m->full_small.valid && N <= 3 * 16 * (int64_t)m->sms;
         return full_name(small ? m->full_small : m->full, buf, len);
@@ -990,6 +1097,14 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
                         cudaStream_t stream) {
     const int64_t E = b->E, D = b->D;
     const bool with_var = var != nullptr;
+    if (b->models[0]->generic) {   // D > 32: one generic pass per emulator (predict_generic.cuh)
+        for (int64_t e = 0; e < E; ++e) {
+            int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var ? var + e : nullptr,
+                                    deriv ? deriv + e * D : nullptr, hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream);
+            if (rc) return rc;
+        }
+        return GPE_OK;
+    }
     if (with_var) {   // the variance contraction is per emulator: one fused launch each (also yields mean + gradient,
                       // and the Hessian when every emulator qualifies for the fused Hessian)
         bool fuse_hess = hess != nullptr;
@@ -1422,7 +1537,7 @@ int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const
         // operands of the shared-difference kernels (predict_bank_mean.cuh): [1] mean + gradient, [0] means only
         static const bool off = []{ const char* e = getenv("GPE_BANK_SHARED"); return e && !strcmp(e, "off"); }();
         const int DP = b->models[0]->DP;
-        for (int grad = 0; grad < 2 && !off; ++grad) {
+        for (int grad = 0; grad < 2 && !off && !b->models[0]->generic; ++grad) {
             BankMeanPlan g = plan_bank_mean(E, M, D, DP, grad != 0);
             if (!g.valid) continue;
             const int G = g.G, GP = (G + 1) & ~1;

@@ -509,7 +509,7 @@ int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, co
     if (!out) return set_error(GPE_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (M < 1 || D < 1 || T < 1) return set_error(GPE_ERR_INVALID, "need M >= 1, D >= 1, T >= 1 (got %d, %d, %d)", M, D, T);
-    if (D > GPE_MAX_INPUTS) return set_error(GPE_ERR_UNSUPPORTED, "D = %d exceeds GPE_MAX_INPUTS = %d", D, GPE_MAX_INPUTS);
+    if (D > GPE_TRAIN_MAX_D) return set_error(GPE_ERR_UNSUPPORTED, "D = %d exceeds GPE_TRAIN_MAX_D = %d", D, GPE_TRAIN_MAX_D);
     if (M > GPE_TRAIN_MAX_M) return set_error(GPE_ERR_UNSUPPORTED, "M = %d exceeds GPE_TRAIN_MAX_M = %d", M, GPE_TRAIN_MAX_M);
     if (!inputs || !targets) return set_error(GPE_ERR_INVALID, "inputs / targets is NULL");
     // pivots per pass: the largest of 32, 16, 8 whose staged pivot rows, columns and coefficients (3 NB Mp doubles) fit

@@ -227,7 +227,7 @@ class GaussianProcess:
         dm = self._device_model(testing.shape[0])
         is_t = hasattr(testing, "dim")
         f32_in = (is_t and str(testing.dtype) == "torch.float32") or (not is_t and precision is np.float32)
-        if f32_in and dm.M <= 1024 and out is None:
+        if f32_in and dm.M <= 1024 and dm.D <= 32 and out is None:
             # the reference's FP32 GPU build (precision=np.float32, GaussianProcess.py:289-316): single precision
             # end to end, variance contraction on the tensor cores (tcgen05, TF32 inputs)
             o = dm.predict_f32(testing, want_var=do_unc, want_deriv=do_deriv)

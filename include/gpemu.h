@@ -47,7 +47,7 @@ typedef enum gpe_status {
 
 #define GPE_MAX_TRAIN 16384    /* largest M with a variance path: fused kernel to 1024, K*-scratch + column passes above
                                   (a bound on the packed invQ image, 2 GB at 16384; mean / gradient / Hessian have no limit) */
-#define GPE_MAX_INPUTS 32      /* largest D */
+#define GPE_MAX_INPUTS 256     /* largest D; up to 32 the per-D compiled kernels run, above that generic ones (FP64 only) */
 
 typedef struct gpe_model gpe_model;  /* one trained GP resident on one device */
 typedef struct gpe_bank gpe_bank;    /* E GPs sharing training inputs (MultivariateEmulator / per-band bank) */
@@ -223,6 +223,7 @@ int gpe_measure_fp64_peaks(int device, double* out9);
  *                        np.linalg.cholesky, :73-75): loglik and grad of that problem are NaN
  */
 #define GPE_TRAIN_MAX_M 1024
+#define GPE_TRAIN_MAX_D 32    /* the batched training kernel keeps exp(theta) for D + 2 <= 40 hyper-parameters on chip */
 typedef struct gpe_trainer gpe_trainer;
 int gpe_trainer_create(int device, int M, int D, int T, const double* inputs, const double* targets, gpe_trainer** out);
 int gpe_trainer_eval(gpe_trainer* t, int B, const int* target_index, const double* thetas, double* loglik, double* grad,

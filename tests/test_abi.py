@@ -30,7 +30,7 @@ def test_header_constants_match_python_binding():
     text = open(os.path.join(ROOT, "include", "gpemu.h")).read()
     defs = {k: int(v, 0) for k, v in re.findall(r"#define\s+(GPE_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+|\d+)", text)}
     assert defs["GPE_MAX_TRAIN"] == _lib.MAX_TRAIN and defs["GPE_MAX_INPUTS"] == _lib.MAX_INPUTS
-    assert defs["GPE_TRAIN_MAX_M"] == _lib.TRAIN_MAX_M
+    assert defs["GPE_TRAIN_MAX_M"] == _lib.TRAIN_MAX_M and defs["GPE_TRAIN_MAX_D"] == 32
     for cname, pyname in [("GPE_WANT_MU", "WANT_MU"), ("GPE_WANT_VAR", "WANT_VAR"), ("GPE_WANT_DERIV", "WANT_DERIV"),
                           ("GPE_WANT_HESS", "WANT_HESS"), ("GPE_HOST_PTRS", "HOST_PTRS"),
                           ("GPE_F32_FAST_TF32", "F32_FAST_TF32"), ("GPE_F32_FORCE_3X", "F32_FORCE_3X"),
@@ -69,7 +69,7 @@ def test_argument_validation(lib):
     h = C.c_void_p()
     x = np.zeros((4, 2)); e = np.ones(3); a = np.zeros(4)
     assert lib.gpe_model_create(0, 0, 2, x.ctypes.data, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
-    assert lib.gpe_model_create(0, 4, 33, x.ctypes.data, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
+    assert lib.gpe_model_create(0, 4, 257, x.ctypes.data, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
     assert lib.gpe_model_create(0, 4, 2, None, e.ctypes.data, a.ctypes.data, None, C.byref(h)) == -1
     assert lib.gpe_predict(None, None, 1, None, None, None, None, 1, None) == -1
     assert lib.gpe_bank_cost(None, None, 1, None, 0, None, None, None, None) == -1

@@ -1338,3 +1338,46 @@ def test_non_finite_and_far_away_test_points_follow_numpy(gpemu):
     got = bank.predict(testing, want_var=False, want_deriv=True)
     same(got["mu"], mu_b, "bank mu"); same(got["deriv"], grad_b, "bank deriv")
     same(bank.predict(testing, want_var=False, want_deriv=False)["mu"], mu_b, "bank means only")
+
+
+@pytest.mark.parametrize("M,D,N", [(60, 33, 37), (250, 40, 300), (7, 64, 1), (130, 100, 50), (1100, 36, 20), (40, 256, 33)])
+def test_more_than_32_inputs_generic_path(gpemu, M, D, N):
+    """D > 32 (the reference loops `for d in range(self.D)`, no limit: GaussianProcess.py:228-247, :345-366): generic
+    kernels on the K* scratch + the column-pass variance kernel (predict_generic.cuh).  Mean, variance, gradient and
+    Hessian against the oracle, host and device callers, more points than one sub-batch, and through the drop-in class."""
+    import torch
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=D)
+    theta = theta.copy(); theta[:D] -= np.log(D / 8.0)        # keep sum_d w_d (x - t)^2 in a range where K* is not ~ 0
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    hess = orc.hessian(inputs, theta, invQt, testing[:8])
+    assert np.max(np.abs(mu)) > 1e-3
+    host = m.predict(testing, want_hess=True)
+    dev = {k: v.cpu().numpy() for k, v in m.predict(torch.from_numpy(testing).cuda(), want_hess=True).items()}
+    for name, got in (("host", host), ("device", dev)):
+        assert orc.ref_err(got["mu"], mu) < TOL and orc.ref_err(got["var"], var) < TOL, name
+        assert orc.ref_err(got["deriv"], deriv) < TOL and orc.ref_err(got["hess"][:8], hess) < TOL, name
+    o = m.predict(testing, want_var=False, want_mu=False)
+    assert set(o) == {"deriv"} and np.array_equal(o["deriv"], host["deriv"])
+    gp = gpemu.GaussianProcess(inputs, np.zeros(M))
+    gp.theta, gp.invQ, gp.invQt = theta, invQ, invQt
+    r = gp.predict(testing)
+    assert orc.ref_err(r[0], mu) < TOL and orc.ref_err(r[1], var) < TOL and orc.ref_err(r[2], deriv) < TOL
+    assert orc.ref_err(gp.hessian(testing[:8]), hess) < TOL
+
+
+def test_more_than_32_inputs_many_points_and_bank(gpemu):
+    """Sub-batches of the K* scratch (N > 16 * 4 * #SMs) and a bank of D = 35 emulators (strided point-major outputs)."""
+    rs = np.random.RandomState(35)
+    M, D, E, N = 90, 35, 3, 12_001
+    inputs = rs.random_sample((M, D))
+    thetas = rs.random_sample((E, D + 2)) - np.log(D / 8.0); invQts = rs.randn(E, M); invQs = rs.random_sample((E, M, M))
+    t = rs.random_sample((N, D))
+    bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+    got = bank.predict(t, want_var=True, want_deriv=True)
+    idx = np.r_[0:40, N - 40:N, rs.randint(0, N, 60)]
+    mu_o, var_o, grad_o = orc.bank_predict([(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)], t[idx])
+    assert orc.ref_err(got["mu"][idx], mu_o) < TOL and orc.ref_err(got["var"][idx], var_o) < TOL
+    assert orc.ref_err(got["deriv"][idx], grad_o) < TOL
+    nv = bank.predict(t[:500], want_var=False, want_deriv=True)
+    assert np.array_equal(nv["mu"], got["mu"][:500]) and np.array_equal(nv["deriv"], got["deriv"][:500])
