@@ -4,6 +4,12 @@
 
 namespace gpe {
 
+// Row pitch (doubles) of the training-input chunks the FP64 predict kernels keep in shared memory.  The 8 (or 4)
+// training-point lanes of a quarter-warp read consecutive rows with LDS.128, so the pitch counted in 16-byte units has to
+// be odd, or rows share banks: at pitch = DP the loads were 4-way conflicted for DP = 8, 2-way for 12, 8-way for 16
+// (round 2, tools/d_sweep_probe.py: D = 8 ran SLOWER than D = 10).  DP = 2, 6, 10 are conflict-free as they are.
+__host__ __device__ constexpr int x_pitch(int DP) { return ((DP / 2) & 1) ? DP : DP + 2; }
+
 // exp(x) for x <= 0 in FP64, branch-free.
 //
 // The squared-exponential covariance only ever needs exp of a non-positive argument

@@ -243,7 +243,7 @@ BankMeanPlan plan_bank_mean(int E, int M, int D, int DP, bool grad) {
     g.JC = std::min(m4, 256);
     g.nchunks = (M + g.JC - 1) / g.JC;
     uint32_t off = 0;
-    g.off_x = off; off += align_up((uint32_t)g.JC * DP * 8u, 16);
+    g.off_x = off; off += align_up((uint32_t)g.JC * x_pitch(DP) * 8u, 16);
     g.off_a = off; off += align_up((uint32_t)g.JC * GP * 8u, 16);
     g.off_w = off; off += align_up(2u * g.G * DP * 8u, 16);
     g.off_ts = off; off += align_up((uint32_t)kBankTN * (uint32_t)std::max(D, g.G * (grad ? DP + 1 : 1)) * 8u, 16);
@@ -298,7 +298,7 @@ FullPlan plan_full(int M, int D, int DP, int small_Mp = 0) {
     off = align_up(off, 128);
     const uint32_t fixed = off;
     const int m4 = (M + 3) / 4 * 4;
-    const uint32_t row = (uint32_t)(DP + 1) * 8u;
+    const uint32_t row = (uint32_t)(x_pitch(DP) + 1) * 8u;
     // resident training set if it fits beside a ring of >= 3 stages, else chunks of <= 256 points; the ring then
     // takes every stage that still fits (at most 8: the barrier arrays)
     {
@@ -327,7 +327,7 @@ MeanPlan plan_mean(int M, int D, int DP) {
     m.JC = std::min(m4, 256);
     m.nchunks = (M + m.JC - 1) / m.JC;
     uint32_t off = 0;
-    m.off_xc = off; off += align_up((uint32_t)m.JC * (DP + 1) * 8u, 16);
+    m.off_xc = off; off += align_up((uint32_t)m.JC * (x_pitch(DP) + 1) * 8u, 16);
     m.off_ts = off; off += align_up((uint32_t)kMeanTN * (D + 1) * 8u, 16);
     m.off_out = off;
     m.smem = off;
@@ -339,7 +339,7 @@ MeanPlan plan_mean(int M, int D, int DP) {
 // Extent of the mean kernels' shared-memory carve-up, recomputed from the offsets the kernels use (checked against the
 // dynamic shared memory of the launch at kernel entry: MeanParams::smem_need).
 uint32_t mean_extent(const MeanPlan& mp, int D, int DP, bool hess) {
-    uint32_t ext = std::max(mp.off_xc + (uint32_t)mp.JC * (DP + 1) * 8u, mp.off_ts + (uint32_t)kMeanTN * (D + 1) * 8u);
+    uint32_t ext = std::max(mp.off_xc + (uint32_t)mp.JC * (x_pitch(DP) + 1) * 8u, mp.off_ts + (uint32_t)kMeanTN * (D + 1) * 8u);
     if (hess) ext = std::max(ext, mp.off_out + (uint32_t)kMeanTN * D * 8u * (uint32_t)(DP <= 12 ? D : (DP <= 16 ? 4 : 2)));
     return ext;
 }
@@ -347,12 +347,13 @@ uint32_t mean_extent(const MeanPlan& mp, int D, int DP, bool hess) {
 // [nchunks][ JC*DP sqrt(w)-scaled inputs | JC b*alpha ], zero padded
 std::vector<double> pack_xchunks(int M, int D, int DP, int JC, int nchunks, const double* inputs,
                                  const double* sqrt_w, const double* invQt, double b) {
-    std::vector<double> buf((size_t)nchunks * JC * (DP + 1), 0.0);
+    const int XP = x_pitch(DP);   // row pitch: conflict-free LDS.128 in the kernels (gpe_math.cuh)
+    std::vector<double> buf((size_t)nchunks * JC * (XP + 1), 0.0);
     for (int j = 0; j < M; ++j) {
         const int c = j / JC, jl = j - c * JC;
-        double* base = buf.data() + (size_t)c * JC * (DP + 1);
-        for (int d = 0; d < D; ++d) base[(size_t)jl * DP + d] = sqrt_w[d] * inputs[(size_t)j * D + d];
-        base[(size_t)JC * DP + jl] = b * invQt[j];
+        double* base = buf.data() + (size_t)c * JC * (XP + 1);
+        for (int d = 0; d < D; ++d) base[(size_t)jl * XP + d] = sqrt_w[d] * inputs[(size_t)j * D + d];
+        base[(size_t)JC * XP + jl] = b * invQt[j];
     }
     return buf;
 }
@@ -1555,9 +1556,10 @@ int gpe_bank_create(int device, int E, int M, int D, const double* inputs, const
             }
             cudaError_t e = cudaSuccess;
             if (!b->d_gx) {
-                std::vector<double> gx((size_t)g.nchunks * g.JC * DP, 0.0);
+                const int XP = x_pitch(DP);
+                std::vector<double> gx((size_t)g.nchunks * g.JC * XP, 0.0);
                 for (int j = 0; j < M; ++j)
-                    for (int d = 0; d < D; ++d) gx[(size_t)j * DP + d] = inputs[(size_t)j * D + d];
+                    for (int d = 0; d < D; ++d) gx[(size_t)j * XP + d] = inputs[(size_t)j * D + d];
                 e = cudaMalloc((void**)&b->d_gx, gx.size() * 8);
                 if (e == cudaSuccess) e = cudaMemcpy(b->d_gx, gx.data(), gx.size() * 8, cudaMemcpyHostToDevice);
             }

@@ -40,7 +40,7 @@ struct BankMeanParams {
     int64_t N;
     double* mu;              // (N, E) or null
     double* deriv;           // (N, E, D) or null
-    const double* xraw;      // [nchunks][JC][DP]   raw training inputs, pad rows / dims zero
+    const double* xraw;      // [nchunks][JC][x_pitch(DP)]   raw training inputs, pad rows / dims zero
     const double* galpha;    // [ngroups][nchunks][JC][GP]  b_e alpha_ej, pad emulators / rows zero (GP = G rounded up to 2)
     const double* gw;        // [ngroups][2][G][DP]  first -w_ed / 2, then w_ed; pads zero
     int M, D, E, JC, nchunks;
@@ -53,11 +53,12 @@ template <int DP, int G, bool GRAD>
 __global__ void __launch_bounds__(kBankThreads, GRAD ? 2 : 3) k_bank_mean(const BankMeanParams p) {
     constexpr int TN = kBankTN;
     constexpr int GP = (G + 1) & ~1;
+    constexpr int XP = x_pitch(DP);           // row pitch of the training chunk (conflict-free LDS.128)
     constexpr int AV = GRAD ? DP + 1 : 1;     // accumulators per emulator: mu [, g_0 .. g_{DP-1}]
     constexpr int NV = G * AV;                // values per point
     constexpr int H1 = (NV + 1) / 2, H2 = (H1 + 1) / 2;
     extern __shared__ __align__(128) unsigned char smem_bm[];
-    double* Xs = reinterpret_cast<double*>(smem_bm + p.off_x);     // [JC][DP]
+    double* Xs = reinterpret_cast<double*>(smem_bm + p.off_x);     // [JC][XP]
     double* As = reinterpret_cast<double*>(smem_bm + p.off_a);     // [JC][GP]
     double* Ws = reinterpret_cast<double*>(smem_bm + p.off_w);     // [2][G][DP]
     double* ts_s = reinterpret_cast<double*>(smem_bm + p.off_ts);  // [TN][D] test rows, then [TN][NV] results
@@ -116,9 +117,9 @@ __global__ void __launch_bounds__(kBankThreads, GRAD ? 2 : 3) k_bank_mean(const 
         for (int c = 0; c < p.nchunks; ++c) {
             if (!resident) {
                 __syncthreads();
-                const double2* sx = reinterpret_cast<const double2*>(p.xraw + (size_t)c * p.JC * DP);
+                const double2* sx = reinterpret_cast<const double2*>(p.xraw + (size_t)c * p.JC * XP);
                 double2* dx = reinterpret_cast<double2*>(Xs);
-                for (int e = tid; e < p.JC * DP / 2; e += kBankThreads) dx[e] = __ldg(sx + e);
+                for (int e = tid; e < p.JC * XP / 2; e += kBankThreads) dx[e] = __ldg(sx + e);
                 const double2* sa = reinterpret_cast<const double2*>(ga + (size_t)c * p.JC * GP);
                 double2* da = reinterpret_cast<double2*>(As);
                 for (int e = tid; e < p.JC * GP / 2; e += kBankThreads) da[e] = __ldg(sa + e);
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kBankThreads, GRAD ? 2 : 3) k_bank_mean(const 
             if (jl < jn) {
                 double2 xn[DP / 2];
                 {
-                    const double2* xr = reinterpret_cast<const double2*>(Xs + jl * DP);
+                    const double2* xr = reinterpret_cast<const double2*>(Xs + jl * XP);
 #pragma unroll
                     for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                 }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kBankThreads, GRAD ? 2 : 3) k_bank_mean(const 
                         s[2 * q + 1] = u[2 * q + 1] * u[2 * q + 1];
                     }
                     {
-                        const double2* xr = reinterpret_cast<const double2*>(Xs + min(jl + 4, jn - 1) * DP);
+                        const double2* xr = reinterpret_cast<const double2*>(Xs + min(jl + 4, jn - 1) * XP);
 #pragma unroll
                         for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                     }

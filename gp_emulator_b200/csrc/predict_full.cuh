@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
     constexpr int GH = NW / NHI;          // warps along j in phase A
     constexpr int TPR = NTHR / TN;        // threads per test row when writing outputs
     constexpr int NV = DP + 1;            // values reduced per point: mean + DP gradient sums
+    constexpr int XP = x_pitch(DP);       // row pitch of the training chunk (conflict-free LDS.128)
     static_assert((NW & (NW - 1)) == 0, "warp count must be a power of two");
     static_assert(NHI * GH == NW && NHI >= 1 && GH >= 1, "TN must be 8 * (a divisor of the warp count)");
     static_assert(TPR >= 1 && TPR * TN == NTHR, "TN must divide the thread count");
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         ext = umax2(ext, p.off_vred + (uint32_t)WC * TN * 8u);
         if (want_hess) ext = umax2(ext, p.off_hts + (uint32_t)TN * (uint32_t)D * 8u);
         if (nit_tot > 0) ext = umax2(ext, p.off_bst + (uint32_t)nstage * p.stage_bytes);
-        ext = umax2(ext, p.off_xc + (uint32_t)p.JC * (DP + 1) * 8u);
+        ext = umax2(ext, p.off_xc + (uint32_t)p.JC * (XP + 1) * 8u);
         smem_guard(ext);
     }
     // ---- one-time setup -------------------------------------------------------------------------
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         }
         // phase-A chunk 0 (unless resident) is requested before the barrier so its latency overlaps the barrier
         if (!x_resident && tid == 0) {
-            const uint32_t bytes = (uint32_t)p.JC * (DP + 1) * 8u;
+            const uint32_t bytes = (uint32_t)p.JC * (XP + 1) * 8u;
             mbar_arrive_expect_tx(bar_x, bytes);
             tma_bulk_g2s(Xc, p.xchunks, bytes, bar_x);
         }
@@ -335,16 +336,16 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         for (int c = 0; c < p.nchunks; ++c) {
             if (!x_resident) {
                 if (c > 0 && tid == 0) {
-                    const uint32_t bytes = (uint32_t)p.JC * (DP + 1) * 8u;
+                    const uint32_t bytes = (uint32_t)p.JC * (XP + 1) * 8u;
                     mbar_arrive_expect_tx(bar_x, bytes);
-                    tma_bulk_g2s(Xc, p.xchunks + (size_t)c * p.JC * (DP + 1), bytes, bar_x);
+                    tma_bulk_g2s(Xc, p.xchunks + (size_t)c * p.JC * (XP + 1), bytes, bar_x);
                 }
                 mbar_wait(bar_x, xpar);
                 xpar ^= 1;
                 if (p.nchunks == 1) x_resident = true;
             }
             const int jn = min(p.JC, M - c * p.JC);
-            const double* al = Xc + p.JC * DP;
+            const double* al = Xc + p.JC * XP;
             double* krow_a = Ks + n_a * pitch + c * p.JC;
             double* krow_b = krow_a + 4 * pitch;
             int jl = 8 * g_hi + g_low;
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 double2 xn[DP / 2];
                 double aln;
                 {
-                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * DP);
+                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * XP);
 #pragma unroll
                     for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                     aln = al[jl];
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                     const double alj = aln;
                     {
                         const int jnx = min(jl + 8 * GH, jn - 1);
-                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * DP);
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * XP);
 #pragma unroll
                         for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                         aln = al[jnx];

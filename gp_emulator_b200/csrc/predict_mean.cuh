@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
 
     const int64_t ntiles = (p.N + TN - 1) / TN;
     bool x_resident = false;
-    const int chunk_doubles = p.JC * (DP + 1);
+    constexpr int XP = x_pitch(DP);   // row pitch of the training chunk (conflict-free LDS.128)
+    const int chunk_doubles = p.JC * (XP + 1);
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = tile * TN;
@@ -103,12 +104,12 @@ __global__ void __launch_bounds__(kMeanThreads) k_predict_mean(const MeanParams 
                 if (p.nchunks == 1) x_resident = true;
             }
             const int jn = min(p.JC, M - c * p.JC);
-            const double* al = Xc + p.JC * DP;
+            const double* al = Xc + p.JC * XP;
             // Software pipeline over this lane's training points: the distance + exp chain of point i + 1 (a long
             // dependent FP64 sequence) is issued in the same iteration as the independent accumulate FMAs of point i
             // (D for the gradient, D (D + 1) / 2 for the Hessian), so the FP64 pipe always has ready work.
             auto stage1 = [&](int jl, double (&u)[DP]) -> double {
-                const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
+                const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * XP);
                 double r2 = 0.0;
 #pragma unroll
                 for (int d = 0; d < DP; d += 2) {
@@ -232,7 +233,8 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
     double* const o_deriv = p.deriv ? p.deriv + em * p.eo_deriv : nullptr;
     const int64_t ntiles = (p.N + TN - 1) / TN;
     bool x_resident = false;
-    const int chunk_doubles = p.JC * (DP + 1);
+    constexpr int XP = x_pitch(DP);   // row pitch of the training chunk (conflict-free LDS.128)
+    const int chunk_doubles = p.JC * (XP + 1);
 
     // The test rows of the NEXT tile are fetched into registers while the current tile computes (the global-load
     // latency at every tile start showed up as 0.4 long-scoreboard + 0.2 barrier stall cycles per issue in ncu).
@@ -282,13 +284,13 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
                 if (p.nchunks == 1) x_resident = true;
             }
             const int jn = min(p.JC, M - c * p.JC);
-            const double* al = Xc + p.JC * DP;
+            const double* al = Xc + p.JC * XP;
             int jl = g_low;
             if (jl < jn) {
                 double2 xn[DP / 2];
                 double aln;
                 {
-                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * DP);
+                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * XP);
 #pragma unroll
                     for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                     aln = al[jl];
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(kMeanThreads, (DP <= 12 ? 3 : 1)) k_predict_me
                     const double alj = aln;
                     {
                         const int jnx = min(jl + 8, jn - 1);
-                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * DP);
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * XP);
 #pragma unroll
                         for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
                         aln = al[jnx];
@@ -384,7 +386,8 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
     if (tid < 32) sqw_s[tid] = p.bank ? p.bank[em].sqrt_w[tid] : p.sqrt_w[tid];
     double* const o_hess = p.hess + em * p.eo_hess;
     const int64_t ntiles = (p.N + TN - 1) / TN;
-    const int chunk_doubles = p.JC * (DP + 1);
+    constexpr int XP = x_pitch(DP);   // row pitch of the training chunk (conflict-free LDS.128)
+    const int chunk_doubles = p.JC * (XP + 1);
     bool x_resident = false;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = tile * TN;
@@ -416,9 +419,9 @@ __global__ void __launch_bounds__(kMeanThreads) k_hessian_rows(const MeanParams 
                     if (p.nchunks == 1) x_resident = true;
                 }
                 const int jn = min(p.JC, M - c * p.JC);
-                const double* al = Xc + p.JC * DP;
+                const double* al = Xc + p.JC * XP;
                 for (int jl = g_low; jl < jn; jl += 4) {
-                    const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * DP);
+                    const double2* x1 = reinterpret_cast<const double2*>(Xc + jl * XP);
                     double u[DP];
                     double r2 = 0.0;
 #pragma unroll
