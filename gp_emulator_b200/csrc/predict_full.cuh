@@ -297,19 +297,28 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             }
             __syncthreads();
         }
-        double tsa[DP], tsb[DP];
+        // DP > 16: two rows of test coordinates, differences and gradient sums (6 DP + 2 doubles) do not fit the register
+        // file -- phase A then sweeps the training points twice, once per row (kTwoPass), and the first row's sums wait in
+        // registers; the training rows are read from shared memory twice, which the FP64-bound loop does not notice
+        // (measured at M = 250: D = 24 1.17e8 -> see DESIGN 4.1; the two-row loop spilled 1-3 KB per thread there)
+        constexpr bool kTwoPass = DP > 16;
+        double tsa[kTwoPass ? 1 : DP], tsb[kTwoPass ? 1 : DP];
+        if constexpr (!kTwoPass) {
 #pragma unroll
-        for (int d = 0; d < DP; ++d) {
-            tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
-            tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
+            for (int d = 0; d < DP; ++d) {
+                tsa[d] = (d < D) ? ts_s[n_a * D + d] * sqw_s[d] : 0.0;
+                tsb[d] = (d < D) ? ts_s[n_b * D + d] * sqw_s[d] : 0.0;
+            }
         }
-        if (HESS && want_hess && g_hi == 0) {   // the 8 training-point lanes of a row share its D stores
+        if constexpr (HESS) {
+            if (want_hess && g_hi == 0) {   // the 8 training-point lanes of a row share its D stores
 #pragma unroll
-            for (int d = 0; d < DP; ++d)
-                if ((d & 7) == g_low && d < D) {
-                    hts[n_a * D + d] = tsa[d] - cen_s[d];
-                    hts[n_b * D + d] = tsb[d] - cen_s[d];
-                }
+                for (int d = 0; d < DP; ++d)
+                    if ((d & 7) == g_low && d < D) {
+                        hts[n_a * D + d] = tsa[d] - cen_s[d];
+                        hts[n_b * D + d] = tsb[d] - cen_s[d];
+                    }
+            }
         }
         // phase-A chunk 0 (unless resident) is requested before the barrier so its latency overlaps the barrier
         if (!x_resident && tid == 0) {
@@ -348,54 +357,84 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
             const double* al = Xc + p.JC * XP;
             double* krow_a = Ks + n_a * pitch + c * p.JC;
             double* krow_b = krow_a + 4 * pitch;
+            if constexpr (kTwoPass) {
+                auto sweep = [&](int n_r, double (&v1)[NV]) {
+                    double* krow = Ks + n_r * pitch + c * p.JC;
+                    double ts1[DP];
+#pragma unroll
+                    for (int d = 0; d < DP; ++d) ts1[d] = (d < D) ? ts_s[n_r * D + d] * sqw_s[d] : 0.0;
+                    for (int jl = 8 * g_hi + g_low; jl < jn; jl += 8 * GH) {
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jl * XP);
+                        double u[DP];
+                        double r = 0.0;
+#pragma unroll
+                        for (int q = 0; q < DP / 2; ++q) {
+                            const double2 x2 = xr[q];
+                            u[2 * q] = x2.x - ts1[2 * q];
+                            u[2 * q + 1] = x2.y - ts1[2 * q + 1];
+                            r = fma(u[2 * q], u[2 * q], r);
+                            r = fma(u[2 * q + 1], u[2 * q + 1], r);
+                        }
+                        const double k = exp_neg_tab(-0.5 * r, exp_tab);
+                        krow[jl] = k;
+                        const double cj = k * al[jl];
+                        v1[0] += cj;
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) v1[1 + d] = fma(cj, u[d], v1[1 + d]);
+                    }
+                };
+                sweep(n_a, va);
+                sweep(n_b, vb);
+            } else {
             int jl = 8 * g_hi + g_low;
-            if (jl < jn) {
-                // software pipeline: the next training row and alpha are in flight while this one is consumed
-                double2 xn[DP / 2];
-                double aln;
-                {
-                    const double2* xr = reinterpret_cast<const double2*>(Xc + jl * XP);
-#pragma unroll
-                    for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
-                    aln = al[jl];
-                }
-                for (; jl < jn; jl += 8 * GH) {
-                    double2 x[DP / 2];
-#pragma unroll
-                    for (int q = 0; q < DP / 2; ++q) x[q] = xn[q];
-                    const double alj = aln;
+                if (jl < jn) {
+                    // software pipeline: the next training row and alpha are in flight while this one is consumed
+                    double2 xn[DP / 2];
+                    double aln;
                     {
-                        const int jnx = min(jl + 8 * GH, jn - 1);
-                        const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * XP);
-#pragma unroll
+                        const double2* xr = reinterpret_cast<const double2*>(Xc + jl * XP);
+    #pragma unroll
                         for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
-                        aln = al[jnx];
+                        aln = al[jl];
                     }
-                    double ua[DP], ub[DP];
-                    double ra = 0.0, rb = 0.0;
-#pragma unroll
-                    for (int q = 0; q < DP / 2; ++q) {
-                        const int d = 2 * q;
-                        ua[d] = x[q].x - tsa[d];
-                        ub[d] = x[q].x - tsb[d];
-                        ua[d + 1] = x[q].y - tsa[d + 1];
-                        ub[d + 1] = x[q].y - tsb[d + 1];
-                        ra = fma(ua[d], ua[d], ra);
-                        rb = fma(ub[d], ub[d], rb);
-                        ra = fma(ua[d + 1], ua[d + 1], ra);
-                        rb = fma(ub[d + 1], ub[d + 1], rb);
-                    }
-                    const double ka = exp_neg_tab(-0.5 * ra, exp_tab);
-                    const double kb = exp_neg_tab(-0.5 * rb, exp_tab);
-                    krow_a[jl] = ka;
-                    krow_b[jl] = kb;
-                    const double ca = ka * alj, cb = kb * alj;
-                    va[0] += ca;
-                    vb[0] += cb;
-#pragma unroll
-                    for (int d = 0; d < DP; ++d) {
-                        va[1 + d] = fma(ca, ua[d], va[1 + d]);
-                        vb[1 + d] = fma(cb, ub[d], vb[1 + d]);
+                    for (; jl < jn; jl += 8 * GH) {
+                        double2 x[DP / 2];
+    #pragma unroll
+                        for (int q = 0; q < DP / 2; ++q) x[q] = xn[q];
+                        const double alj = aln;
+                        {
+                            const int jnx = min(jl + 8 * GH, jn - 1);
+                            const double2* xr = reinterpret_cast<const double2*>(Xc + jnx * XP);
+    #pragma unroll
+                            for (int q = 0; q < DP / 2; ++q) xn[q] = xr[q];
+                            aln = al[jnx];
+                        }
+                        double ua[DP], ub[DP];
+                        double ra = 0.0, rb = 0.0;
+    #pragma unroll
+                        for (int q = 0; q < DP / 2; ++q) {
+                            const int d = 2 * q;
+                            ua[d] = x[q].x - tsa[d];
+                            ub[d] = x[q].x - tsb[d];
+                            ua[d + 1] = x[q].y - tsa[d + 1];
+                            ub[d + 1] = x[q].y - tsb[d + 1];
+                            ra = fma(ua[d], ua[d], ra);
+                            rb = fma(ub[d], ub[d], rb);
+                            ra = fma(ua[d + 1], ua[d + 1], ra);
+                            rb = fma(ub[d + 1], ub[d + 1], rb);
+                        }
+                        const double ka = exp_neg_tab(-0.5 * ra, exp_tab);
+                        const double kb = exp_neg_tab(-0.5 * rb, exp_tab);
+                        krow_a[jl] = ka;
+                        krow_b[jl] = kb;
+                        const double ca = ka * alj, cb = kb * alj;
+                        va[0] += ca;
+                        vb[0] += cb;
+    #pragma unroll
+                        for (int d = 0; d < DP; ++d) {
+                            va[1 + d] = fma(ca, ua[d], va[1 + d]);
+                            vb[1 + d] = fma(cb, ub[d], vb[1 + d]);
+                        }
                     }
                 }
             }
@@ -405,6 +444,7 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
         GPE_TRACE(2);
         // combine the 8 j-lanes of each point (reduce-scatter), then (GH > 1) the j-warps through smem
         double* outs = ts_s;  // [TN][D+1]: mean, then unscaled gradient sums
+        if constexpr (kTwoPass) __syncthreads();   // the second sweep read its test row from ts_s: everyone is done with it
         {
             RS<NV> rs;
             rs.run(va, vb, lane);

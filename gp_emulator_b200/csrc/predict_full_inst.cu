@@ -113,8 +113,11 @@ cudaError_t GPE_CAT(launch_mean_dp, GPE_DP)(bool hess, const MeanParams& p, dim3
         return cudaGetLastError();
 #endif
     }
-    // mean + gradient: two-rows-per-thread kernel (k_predict_mean2); GPE_MEAN_V1=1 selects the first version
-    static const bool v1 = getenv("GPE_MEAN_V1") != nullptr;
+    // mean + gradient: the two-rows-per-thread kernel (k_predict_mean2) up to DP = 10 and at DP = 16; the one-row kernel
+    // (k_predict_mean) where two rows of test coordinates, differences and gradient sums no longer fit the register file
+    // (measured, tools/d_sweep_probe.py, M = 250: D = 12 9.3e8 vs 8.2e8 points/s, D = 16 7.5e8 vs 8.0e8, D = 24 5.1e8 vs
+    // 3.1e8, D = 32 3.6e8 vs 1.2e8).  GPE_MEAN_V1=1 / GPE_MEAN_V2=1 force one or the other.
+    static const bool v1 = getenv("GPE_MEAN_V1") != nullptr || ((GPE_DP == 12 || GPE_DP >= 24) && getenv("GPE_MEAN_V2") == nullptr);
     auto kern = p.kstar != nullptr ? k_predict_mean2<GPE_DP, true>
                                    : (v1 ? k_predict_mean<GPE_DP, false> : k_predict_mean2<GPE_DP, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
