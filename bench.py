@@ -344,7 +344,7 @@ def run_configs(torch, gpe, orc, dev_index, peaks, hbm_gbs, bf16_tflops):
     t0 = time.perf_counter()
     bank.cost(h_in, obs_v)
     out["cfg5"]["on_the_fly_cost"] = {"device_resident_points_per_s": pps5b, "host_resident_points_per_s": Nc / (time.perf_counter() - t0),
-                                      "kernel": "k_predict_mean2<10,false> (bank) + k_bank_cost", "bytes_out_per_point": 8 * (1 + D),
+                                      "kernel": "k_bank_mean<10,5,true> (groups of 5 emulators on shared differences) + k_bank_cost", "bytes_out_per_point": 8 * (1 + D),
                                       "parity_vs_oracle": {"cost": orc.ref_err(oc["cost"], c_o), "grad": orc.ref_err(oc["grad"], g_o)},
                                       "note": "gpe_bank_cost / gpe_bank_cost_host: least-squares misfit of the 64 means against one observed "
                                               "vector + its gradient, reduced on the device (88 B per point instead of 5.6 KB)"}
