@@ -535,6 +535,11 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
         p.M = m->M; p.D = m->D; p.Mp = f.Mp; p.nt_act = f.nt_act; p.kblk = f.kblk;
         p.nit = f.nit; p.nstage = f.nstage; p.lag = (f.nstage >= 3) ? 2 : 1; p.symmetric = (m->symmetric && var != nullptr) ? 1 : 0;
         if (const char* e = getenv("GPE_RING_LAG")) p.lag = std::max(1, std::min(atoi(e), f.nstage - 1));
+        // 64-point tiles, full width (Mp = 256): the second warp of every sub-partition starts its ring steps ~300 cycles
+        // late (measured: M = 250 2.170e8 -> 2.193e8 points/s for 200 ... 600 cycles, M = 256 +1 %; neutral for narrower
+        // tiles, -3 % at M = 32, nothing for the 16-point tiles of M = 1000: tools/m_sweep_probe.py, GPE_SKEW)
+        p.skew = (f.cfg == 0 && f.nt_act == 8) ? 300 : 0;
+        if (const char* e = getenv("GPE_SKEW")) p.skew = atoi(e);
         p.JC = f.JC; p.nchunks = f.nchunks; p.b = m->b;
         p.off_bar = f.off_bar; p.off_sqw = f.off_sqw; p.off_ks = f.off_ks; p.off_bst = f.off_bst;
         p.off_xc = f.off_xc; p.off_ts = f.off_ts; p.off_pa = f.off_pa; p.off_vred = f.off_vred;

@@ -54,6 +54,7 @@ struct FullParams {
     int lag;        // refill distance behind the consumer (1 or 2, < nstage)
     int JC;         // training points per phase-A chunk (multiple of 4)
     int symmetric;  // 1: s_tiled holds the upper-triangular fold of invQ (opt-in, half the DMMAs)
+    int skew;       // cycles the second warp of every SM sub-partition waits before its first ring step (0: none)
     int nchunks;
     double b;       // signal variance exp(theta[D])
     // shared-memory carve-up (byte offsets)
@@ -524,6 +525,13 @@ __global__ void __launch_bounds__(WR * WC * 32, MINB) k_predict_full(const FullP
                 if (lane == 0) mbar_arrive(&bar_empty[cs]);
                 if (++cs == nstage) { cs = 0; cpar ^= 1; }
             };
+            // The two warps of an SM sub-partition (w and w + 4) otherwise run their ring steps in lockstep: both fetch A
+            // fragments and wait on the stage barrier while the DMMA pipe idles, then both queue for it.  Holding one of
+            // them back by a fraction of a step lets each warp's step prologue run under the other's DMMAs.
+            if (p.skew > 0 && ((warp >> 2) & 1)) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < p.skew) {}
+            }
             if constexpr (!SYM) {
                 for (int it = 0; it < nit_b; ++it) ring_step(std::integral_constant<int, 0>{}, it);
             } else {
