@@ -1100,13 +1100,16 @@ namespace {
 
 // Device-resident bank prediction on `st`; outputs point-major: mu (N, E), var (N, E), deriv (N, E, D), hess (N, E, D, D).
 int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* mu, double* var, double* deriv, double* hess,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int64_t call_N = -1) {
+    // call_N: size of the API call this launch is a chunk of -- the choice between kernels with different summation
+    // orders depends on it, not on the chunk, so that one call is internally consistent (as in predict_device)
+    if (call_N < 0) call_N = N;
     const int64_t E = b->E, D = b->D;
     const bool with_var = var != nullptr;
     if (b->models[0]->generic) {   // D > 32: one generic pass per emulator (predict_generic.cuh)
         for (int64_t e = 0; e < E; ++e) {
             int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var ? var + e : nullptr,
-                                    deriv ? deriv + e * D : nullptr, hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream);
+                                    deriv ? deriv + e * D : nullptr, hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream, call_N);
             if (rc) return rc;
         }
         return GPE_OK;
@@ -1117,11 +1120,11 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
         for (int64_t e = 0; e < E && fuse_hess; ++e) fuse_hess = b->models[e]->hess_fused_ok && !b->models[e]->symmetric;
         for (int64_t e = 0; e < E; ++e) {
             int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, var + e, deriv ? deriv + e * D : nullptr,
-                                    fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream);
+                                    fuse_hess ? hess + e * D * D : nullptr, E, E, E * D, E * D * D, stream, call_N);
             if (rc) return rc;
         }
         if (fuse_hess) hess = nullptr;
-    } else if (hess != nullptr && N >= 16384) {
+    } else if (hess != nullptr && call_N >= 16384) {
         // Hessian without variance on a large batch: per-emulator fused launches (phase A + phase C) beat the
         // one-launch direct kernel when every emulator qualifies and tiles are 64 points (cfg 0)
         bool fuse_hess = true;
@@ -1129,13 +1132,16 @@ int bank_predict_device(gpe_bank* b, const double* testing, int64_t N, double* m
         if (fuse_hess) {
             for (int64_t e = 0; e < E; ++e) {
                 int rc = predict_device(b->models[e], testing, N, mu ? mu + e : nullptr, nullptr, deriv ? deriv + e * D : nullptr,
-                                        hess + e * D * D, E, E, E * D, E * D * D, stream);
+                                        hess + e * D * D, E, E, E * D, E * D * D, stream, call_N);
                 if (rc) return rc;
             }
             return GPE_OK;
         }
     }
-    if (hess == nullptr && !with_var && (mu != nullptr || deriv != nullptr) && b->gplan[deriv != nullptr].valid) {
+    // (small calls stay on the one-emulator kernel below: a thread of the group kernel does G emulators' work in sequence,
+    // which only pays once its CTAs fill the machine -- one-point MultivariateEmulator.predict: 107 us against 122 us)
+    if (hess == nullptr && !with_var && (mu != nullptr || deriv != nullptr) && b->gplan[deriv != nullptr].valid &&
+        (call_N + kBankTN - 1) / kBankTN * b->gplan[deriv != nullptr].ngroups >= b->models[0]->sms) {
         // means (+ gradients): groups of G emulators evaluated on shared input differences (blockIdx.y = group)
         const int grad = deriv != nullptr;
         const BankMeanPlan& g = b->gplan[grad];
@@ -1230,7 +1236,8 @@ __global__ void __launch_bounds__(128) k_bank_cost(const double* __restrict__ mu
 }
 
 int bank_cost_device(gpe_bank* b, const double* testing, int64_t N, const double* obs, int64_t obs_ld, const double* weights,
-                     double* cost, double* grad, cudaStream_t st) {
+                     double* cost, double* grad, cudaStream_t st, int64_t call_N = -1) {
+    if (call_N < 0) call_N = N;
     const int64_t E = b->E, D = b->D;
     const int64_t per_point = E * (1 + (grad ? D : 0));
     // points per chunk: whole waves of 64-point tiles, scratch bounded by 256 MB
@@ -1254,7 +1261,7 @@ int bank_cost_device(gpe_bank* b, const double* testing, int64_t N, const double
     const int sms = b->models[0]->sms;
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
         const int64_t n = std::min(chunk, N - n0);
-        int rc = bank_predict_device(b, testing + n0 * D, n, d_mu, nullptr, d_der, nullptr, st);
+        int rc = bank_predict_device(b, testing + n0 * D, n, d_mu, nullptr, d_der, nullptr, st, call_N);
         if (rc) return rc;
         const int grid = (int)std::min<int64_t>((n + 3) / 4, (int64_t)sms * 16);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1291,7 +1298,7 @@ int bank_stream(gpe_bank* b, const double* testing, int64_t N, double* mu, doubl
     return stream_host(b->slots, b->device, pl, src, 8, in.v, in.n, out.v, out.n,
                        [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
                            auto at = [&](int i) { return i >= 0 ? (double*)dout[i] : nullptr; };
-                           int r = bank_predict_device(b, (const double*)di[0], n, at(i_mu), at(i_var), at(i_der), at(i_hes), st);
+                           int r = bank_predict_device(b, (const double*)di[0], n, at(i_mu), at(i_var), at(i_der), at(i_hes), st, N);
                            if (r == GPE_OK && (i_fwd >= 0 || i_dfl >= 0))
                                r = bank_project_device(b, at(i_mu), at(i_der), n, at(i_fwd), at(i_dfl), st);
                            return r;
@@ -1328,7 +1335,7 @@ int bank_cost_stream(gpe_bank* b, const double* testing, int64_t N, const double
                        [&](int64_t, int64_t n, void* const* di, void* const* dout, cudaStream_t st) {
                            return bank_cost_device(b, (const double*)di[0], n, i_obs >= 0 ? (const double*)di[i_obs] : d_obs1,
                                                    i_obs >= 0 ? E : 0, d_w, i_cost >= 0 ? (double*)dout[i_cost] : nullptr,
-                                                   i_grad >= 0 ? (double*)dout[i_grad] : nullptr, st);
+                                                   i_grad >= 0 ? (double*)dout[i_grad] : nullptr, st, N);
                        }, relay);
 }
 

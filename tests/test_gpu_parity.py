@@ -1278,6 +1278,10 @@ def test_bank_mean_gradient_shared_differences(gpemu, M, D, E, N):
     inputs = rs.random_sample((M, D))
     thetas = rs.random_sample((E, D + 2)); invQts = rs.randn(E, M); invQs = rs.random_sample((E, M, M))
     bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+    # the group kernel serves calls whose CTAs fill the machine (tiles x groups >= #SMs); smaller calls stay on the
+    # one-emulator kernel: the first N points are also run as a call of their own
+    n_small = N
+    N = N + 32 * torch.cuda.get_device_properties(0).multi_processor_count
     t = rs.random_sample((N, D))
     models = [(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)]
     mu_o, _, grad_o = orc.bank_predict(models, t)
@@ -1290,6 +1294,8 @@ def test_bank_mean_gradient_shared_differences(gpemu, M, D, E, N):
         for e in range(E):   # per emulator too: a small-output emulator must not hide behind a large one
             assert orc.ref_err(got["mu"][:, e], mu_o[:, e]) < TOL, (name, e)
             assert orc.ref_err(got["deriv"][:, e], grad_o[:, e]) < TOL, (name, e)
+    small = bank.predict(t[:n_small], want_var=False, want_deriv=True)
+    assert orc.ref_err(small["mu"], mu_o[:n_small]) < TOL and orc.ref_err(small["deriv"], grad_o[:n_small]) < TOL
     mu_only = bank.predict(t, want_var=False, want_deriv=False)      # means-only variant: larger groups
     assert orc.ref_err(mu_only["mu"], mu_o) < TOL
     for e in range(E):
@@ -1335,9 +1341,12 @@ def test_non_finite_and_far_away_test_points_follow_numpy(gpemu):
     bank = gpemu.DeviceBank(inputs, thetas, invQts, None)
     with np.errstate(all="ignore"):
         mu_b, _, grad_b = orc.bank_predict([(inputs, thetas[e], invQ, invQts[e]) for e in range(E)], testing)
-    got = bank.predict(testing, want_var=False, want_deriv=True)
+    got = bank.predict(testing, want_var=False, want_deriv=True)          # small call: one-emulator kernel
     same(got["mu"], mu_b, "bank mu"); same(got["deriv"], grad_b, "bank deriv")
-    same(bank.predict(testing, want_var=False, want_deriv=False)["mu"], mu_b, "bank means only")
+    big = np.tile(testing, (80, 1))                                        # enough tiles for the group kernels
+    got = bank.predict(big, want_var=False, want_deriv=True)
+    same(got["mu"], np.tile(mu_b, (80, 1)), "bank mu, groups"); same(got["deriv"], np.tile(grad_b, (80, 1, 1)), "bank deriv, groups")
+    same(bank.predict(big, want_var=False, want_deriv=False)["mu"], np.tile(mu_b, (80, 1)), "bank means only, groups")
 
 
 @pytest.mark.parametrize("M,D,N", [(60, 33, 37), (250, 40, 300), (7, 64, 1), (130, 100, 50), (1100, 36, 20), (40, 256, 33)])
