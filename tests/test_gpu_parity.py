@@ -519,11 +519,16 @@ def test_legacy_predict_wrap_entry_point(lib, gpemu):
 def test_multivariate_emulator_single_point_and_batch(gpemu):
     g = golden("P")
     mv = gpemu.MultivariateEmulator(X=None, y=None, dump=_write_prosail_dump(g))
+    host_models = [(gp.inputs, gp.theta, gp.invQ, gp.invQt) for gp in mv.emulators]
     for k in range(3):
         fwd, d = mv.predict(g["points"][k])
         assert fwd.shape == (2101,) and d.shape == (10, 2101)
-        assert orc.ref_err(fwd, g["fwd"][k]) < 1e-6      # invQ re-derived on this host: cond(Q) ~ 3.5e7
+        # against the reference's frozen outputs: invQ is re-derived on this host and cond(Q) ~ 3.5e7, so 1e-6 ...
+        assert orc.ref_err(fwd, g["fwd"][k]) < 1e-6
         assert orc.ref_err(d[:, g["wsub"]], g["deriv_sub"][k]) < 1e-6
+        # ... and against the oracle on the SAME state at the full bar, so that a regression of the device path shows
+        f_o, d_o = orc.mv_predict_point(host_models, mv.basis_functions, g["points"][k])
+        assert orc.ref_err(fwd, f_o) < TOL and orc.ref_err(d, d_o) < TOL
     fwd_b, d_b = mv.predict(g["points"])
     assert fwd_b.shape == (3, 2101) and d_b.shape == (3, 10, 2101)
     models = [(gp.inputs, gp.theta, gp.invQ, gp.invQt) for gp in mv.emulators]
