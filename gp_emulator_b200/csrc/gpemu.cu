@@ -207,6 +207,19 @@ cudaError_t launch_mean(int DP, bool hess, const MeanParams& p, dim3 grid, size_
     }
 }
 
+cudaError_t launch_tiny(int DP, const TinyParams& p, int grid, size_t smem, cudaStream_t st) {
+    switch (DP) {
+        case 2: return launch_tiny_dp2(p, grid, smem, st);
+        case 4: return launch_tiny_dp4(p, grid, smem, st);
+        case 6: return launch_tiny_dp6(p, grid, smem, st);
+        case 8: return launch_tiny_dp8(p, grid, smem, st);
+        case 10: return launch_tiny_dp10(p, grid, smem, st);
+        case 12: return launch_tiny_dp12(p, grid, smem, st);
+        case 16: return launch_tiny_dp16(p, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_bank_mean(int DP, int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     if (p.smem_need == 0 || p.smem_need > smem) return cudaErrorInvalidConfiguration;
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -467,6 +480,17 @@ int predict_generic(gpe_model* m, const double* testing, int64_t N, double* mu, 
     return GPE_OK;
 }
 
+// Whether a mean + variance + gradient call of call_N points takes the cluster path (predict_tiny.cuh): the fused plan's
+// resident training chunk, a compiled DP, and few enough points (GPE_TINY_MAX overrides the threshold, GPE_NO_TINY disables).
+bool tiny_ok(const gpe_model* m, int64_t call_N) {
+    static const bool no_tiny = getenv("GPE_NO_TINY") != nullptr;
+    static const int64_t env_max = getenv("GPE_TINY_MAX") ? atoll(getenv("GPE_TINY_MAX")) : -1;
+    // two clusters per 8 SMs: measured at M = 250 (tools/tiny_threshold_probe.py, synchronous device calls) the cluster path
+    // takes 37.9 us against 49.3 us at 500 points and draws level with the 16-point plan at 1000
+    const int64_t n_max = env_max >= 0 ? env_max : kTinyTN * (int64_t)(2 * m->sms / kTinyCluster);
+    return !no_tiny && m->full.valid && m->full.cfg == 0 && m->full.nchunks == 1 && m->DP <= 16 && call_N <= n_max;
+}
+
 // Launch the kernels for device-resident data on `st`.  Output strides allow bank (point-major) layouts.
 int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, double* var, double* deriv,
                    double* hess, int64_t ld_mu, int64_t ld_var, int64_t ld_deriv, int64_t ld_hess,
@@ -483,7 +507,10 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
     // 0.98e8 vs 1.10e8 at M = 1000), so larger M keeps the direct kernel for Hessian-only calls
     // (the HESS variants are built on the plain variance operand: with a symmetric-folded model the Hessian only rides
     // along when no variance is requested -- phase B is then skipped and the fold does not matter)
-    const bool fuse_hess = hess != nullptr && m->hess_fused_ok && (var != nullptr ? !m->symmetric : m->full.cfg == 0);
+    // (calls small enough for the cluster path below take the variance from it whatever else is requested, and the Hessian
+    // from the direct kernel: every output of a call of a given size comes from the same kernel for any combination of flags)
+    const bool tiny = m->has_invQ && tiny_ok(m, call_N);
+    const bool fuse_hess = hess != nullptr && m->hess_fused_ok && !tiny && (var != nullptr ? !m->symmetric : m->full.cfg == 0);
     if (var != nullptr && m->has_invQ && !m->full.valid && m->large_valid) {
         // 1024 < M <= GPE_MAX_TRAIN: per sub-batch, K* + mean + gradient (k_predict_mean2<DP, true>) into the scratch,
         // then the column-pass contraction (k_var_large).  The scratch is per model: streams take turns.
@@ -517,6 +544,27 @@ int predict_device(gpe_model* m, const double* testing, int64_t N, double* mu, d
             CUDA_TRY(launch_var_large(v, (int)std::min<int64_t>(vtiles, m->sms), smem, st));
         }
         CUDA_TRY(cudaEventRecord(m->scratch_free, st));
+        mean_done = true;
+        var = nullptr;
+    }
+    // A handful of points (up to two clusters per 8 SMs): the latency path, one 8-CTA cluster per 16-point tile
+    // (predict_tiny.cuh).  Needs the fused plan's resident training chunk; a Hessian request goes the usual way.
+    if (var != nullptr && tiny) {
+        const FullPlan& f = m->full;
+        TinyParams p;
+        memset(&p, 0, sizeof(p));
+        p.testing = testing; p.N = N; p.mu = mu; p.var = var; p.deriv = deriv;
+        p.ld_mu = ld_mu; p.ld_var = ld_var; p.ld_deriv = ld_deriv;
+        p.xchunks = m->d_xchunks_full; p.s_tiled = m->d_stiled;
+        p.M = m->M; p.D = m->D; p.JC = f.JC; p.Mp = f.Mp; p.kblk = f.kblk; p.b = m->b;
+        memcpy(p.sqrt_w, m->sqrt_w, sizeof(p.sqrt_w));
+        const size_t work = std::max<size_t>({(size_t)f.JC * (x_pitch(m->DP) + 1) + (size_t)kTinyTN * m->D,
+                                              (size_t)16 * 16 * (m->DP + 1), (size_t)8 * 16 * 32});
+        const size_t smem = ((size_t)kTinyTN * (f.Mp + 4) + work) * 8;
+        const int grid = (int)((N + kTinyTN - 1) / kTinyTN) * kTinyCluster;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        static const uint32_t shrink_t = getenv("GPE_DEBUG_SHRINK_SMEM") ? (uint32_t)atoi(getenv("GPE_DEBUG_SHRINK_SMEM")) : 0u;
+        CUDA_TRY(launch_tiny(m->DP, p, grid, smem - std::min<size_t>(shrink_t, smem), st));   // (dev aid: see the fused launch)
         mean_done = true;
         var = nullptr;
     }
@@ -991,6 +1039,8 @@ int gpe_model_plan(gpe_model* m, int64_t N, char* buf, int len) {
     if (m->generic)
         return snprintf(buf, len, "k_generic_kstar + k_generic_grad%s (D = %d > 32: generic kernels on the K* scratch)",
                         m->large_valid ? " + k_var_large" : "", m->D);
+    if (m->has_invQ && tiny_ok(m, N))
+        return snprintf(buf, len, "k_predict_tiny<%d> (one 8-CTA cluster per 16-point tile, Mp=%d)", m->DP, m->full.Mp);
     if (m->full.valid) {
         const bool small = m->full_small.valid && N <= 3 * 16 * (int64_t)m->sms;
         return full_name(small ? m->full_small : m->full, buf, len);

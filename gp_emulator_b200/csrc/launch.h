@@ -4,6 +4,7 @@
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
 #include "predict_bank_mean.cuh"
+#include "predict_tiny.cuh"
 #include "predict_tf32.cuh"
 #include "predict_tf32_big.cuh"
 #include "predict_var_large.cuh"
@@ -13,7 +14,8 @@ namespace gpe {
 #define GPE_DECL_DP(DPV)                                                                                          \
     cudaError_t launch_full_dp##DPV(int cfg, const FullParams& p, int grid, size_t smem, cudaStream_t st);         \
     cudaError_t launch_mean_dp##DPV(bool hess, const MeanParams& p, dim3 grid, size_t smem, cudaStream_t st);   \
-    cudaError_t launch_bank_mean_dp##DPV(int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st);
+    cudaError_t launch_bank_mean_dp##DPV(int G, bool grad, const BankMeanParams& p, dim3 grid, size_t smem, cudaStream_t st); \
+    cudaError_t launch_tiny_dp##DPV(const TinyParams& p, int grid, size_t smem, cudaStream_t st);
 
 GPE_DECL_DP(2)
 GPE_DECL_DP(4)

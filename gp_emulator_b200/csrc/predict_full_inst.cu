@@ -3,6 +3,7 @@
 #include "predict_full.cuh"
 #include "predict_mean.cuh"
 #include "predict_bank_mean.cuh"
+#include "predict_tiny.cuh"
 #include "launch.h"
 #include <stdlib.h>
 
@@ -158,6 +159,18 @@ cudaError_t GPE_CAT(launch_bank_mean_dp, GPE_DP)(int G, bool grad, const BankMea
     if (G == 3) return launch_bank_g<3, true>(p, grid, smem, st);
 #endif
     return cudaErrorInvalidValue;
+}
+
+cudaError_t GPE_CAT(launch_tiny_dp, GPE_DP)(const TinyParams& p, int grid, size_t smem, cudaStream_t st) {
+#if GPE_DP <= 16
+    auto kern = k_predict_tiny<GPE_DP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kTinyThreads, smem, st>>>(p);   // cluster dimensions are part of the kernel (__cluster_dims__)
+    return cudaGetLastError();
+#else
+    return cudaErrorInvalidValue;
+#endif
 }
 
 }  // namespace gpe

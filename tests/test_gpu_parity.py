@@ -124,7 +124,10 @@ def test_empty_and_tiny_inputs(gpemu):
 
 def test_device_pointers_equal_host_streaming_and_shard_invariance(gpemu):
     import torch
-    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 3001, seed=8)
+    # (60,001 points: every shard below stays on the plan of the whole call -- the 64-point tiles; the plans for a few
+    # thousand and for a few hundred points have summation orders of their own and agree with it to rounding only)
+    NP = 60_001
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, NP, seed=8)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     host = m.predict(testing)
     t = torch.from_numpy(testing).cuda()
@@ -135,7 +138,7 @@ def test_device_pointers_equal_host_streaming_and_shard_invariance(gpemu):
     # 1-way result must equal any G-way contiguous split bit for bit (points are independent)
     from gp_emulator_b200.sharding import shard_range
     for world in (2, 3, 8):
-        parts = [m.predict(t[slice(*shard_range(3001, r, world))]) for r in range(world)]
+        parts = [m.predict(t[slice(*shard_range(NP, r, world))]) for r in range(world)]
         for k in ("mu", "var", "deriv"):
             assert torch.equal(torch.cat([p[k] for p in parts]), dev[k]), (world, k)
 
@@ -694,6 +697,7 @@ def test_hessian_large_d(gpemu, M, D, N):
 def test_fused_hessian(gpemu, M, D, N):
     """mean + variance + gradient + Hessian in one launch: the Hessian is a second tensor-path contraction against
     the K* tile (predict_full.cuh phase C).  Reference GaussianProcess.py:345-366 for the values."""
+    N += 600          # above the few-hundred-point cluster path (predict_tiny.cuh), which pairs with the direct Hessian kernel
     inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, N, seed=M + D)
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     before = gpemu._lib.load().gpe_launch_count()
@@ -741,7 +745,7 @@ def test_fused_hessian_short_length_scales(gpemu):
     inputs = rs.random_sample((M, D))
     theta = np.concatenate([np.full(D, np.log(3600.0)), [0.3, -6.0]])
     invQ, invQt = orc.prepare_likelihood(inputs, np.sin(4 * inputs.sum(1)), theta)
-    testing = inputs[:200] + 0.01 * rs.standard_normal((200, D))
+    testing = np.tile(inputs, (3, 1)) + 0.01 * rs.standard_normal((3 * M, D))     # 750 points: the fused plan
     m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
     before = lib.gpe_launch_count()
     out = m.predict(testing, want_hess=True)
@@ -1395,3 +1399,34 @@ def test_more_than_32_inputs_many_points_and_bank(gpemu):
     assert orc.ref_err(got["deriv"][idx], grad_o) < TOL
     nv = bank.predict(t[:500], want_var=False, want_deriv=True)
     assert np.array_equal(nv["mu"], got["mu"][:500]) and np.array_equal(nv["deriv"], got["deriv"][:500])
+
+
+@pytest.mark.parametrize("M,D", [(250, 10), (8, 2), (37, 3), (100, 1), (129, 16), (200, 7), (256, 12), (31, 5)])
+def test_handful_of_points_cluster_path(gpemu, M, D):
+    """Calls of a few points with variance (what the reference is mostly used for, GaussianProcess.py:327-341) run one
+    8-CTA cluster per 16-point tile (predict_tiny.cuh).  Parity at every size around the tile and the switch to the
+    16-point plan, host and device callers, strided bank outputs, a symmetric-folded model, outputs requested one by one."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n_max = 16 * (2 * sms // 8)
+    inputs, theta, invQ, invQt, testing = orc.make_S_model(M, D, n_max + 40, seed=M + D)
+    mu, var, deriv = orc.predict(inputs, theta, invQ, invQt, testing)
+    m = gpemu.DeviceModel(inputs, theta, invQt, invQ)
+    assert "k_predict_tiny" in m.plan(1) and "k_predict_tiny" in m.plan(n_max) and "k_predict_tiny" not in m.plan(n_max + 1)
+    for n in (1, 2, 15, 16, 17, 33, n_max - 1, n_max, n_max + 1):
+        o = m.predict(testing[:n])
+        assert orc.ref_err(o["mu"], mu[:n]) < TOL and orc.ref_err(o["var"], var[:n]) < TOL, n
+        assert orc.ref_err(o["deriv"], deriv[:n]) < TOL, n
+    d = m.predict(torch.from_numpy(testing[:19]).cuda(), want_mu=False, want_deriv=False)
+    assert set(d) == {"var"} and orc.ref_err(d["var"].cpu().numpy(), var[:19]) < TOL
+    ms = gpemu.DeviceModel(inputs, theta, invQt, invQ, symmetric_variance=True)
+    assert orc.ref_err(ms.predict(testing[:21])["var"], var[:21]) < TOL
+    if M == 250:
+        rs = np.random.RandomState(3)
+        E = 3
+        thetas = rs.random_sample((E, D + 2)); invQts = rs.randn(E, M); invQs = rs.random_sample((E, M, M))
+        bank = gpemu.DeviceBank(inputs, thetas, invQts, invQs)
+        mu_b, var_b, grad_b = orc.bank_predict([(inputs, thetas[e], invQs[e], invQts[e]) for e in range(E)], testing[:20])
+        got = bank.predict(testing[:20], want_var=True, want_deriv=True)
+        assert orc.ref_err(got["mu"], mu_b) < TOL and orc.ref_err(got["var"], var_b) < TOL
+        assert orc.ref_err(got["deriv"], grad_b) < TOL
