@@ -34,6 +34,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "gpe_math.cuh"
@@ -70,9 +71,13 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
             tma_bulk_g2s(stage + (size_t)st * stage_doubles + (size_t)ks * kProjCols * 4,
                          b_tiled + ((size_t)ks * Wp + (size_t)g * kProjCols) * 4, ks_bytes, &full[st]);
     };
+    // column groups g = blockIdx.y, blockIdx.y + gridDim.y, ...: with a handful of rows (the reference's one-point call:
+    // 1 row of spectrum, D rows of Jacobian) the launcher spreads the W / 128 groups over gridDim.y CTAs instead of
+    // walking them one after the other in a single CTA
+    const int gy = (int)gridDim.y, g_first = (int)blockIdx.y;
     if (tid == 0) {
-        load_group(0, 0);
-        if (ngroups > 1) load_group(1, 1);
+        if (g_first < ngroups) load_group(g_first, 0);
+        if (g_first + gy < ngroups) load_group(g_first + gy, 1);
     }
     // A fragments: lane holds A[row = 8 i + lane / 4][k = 4 ks + lane % 4]
     double a[4][KS];
@@ -89,8 +94,8 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
     const int nrow = (int)max((int64_t)0, min((int64_t)32, R - r0));
     double* ct = ctile + (size_t)warp * (16 * kProjPitch);
     uint32_t par = 0;
-    for (int g = 0; g < ngroups; ++g) {
-        const int st = g & 1;
+    for (int g = g_first, it = 0; g < ngroups; g += gy, ++it) {
+        const int st = it & 1;
         mbar_wait(&full[st], (par >> st) & 1u);
         par ^= 1u << st;
         const double* bs = stage + (size_t)st * stage_doubles + (size_t)(wc * 32 + (lane >> 2)) * 4 + (lane & 3);
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(kProjThreads, 2) k_project(const double* __res
             }
         }
         __syncthreads();   // every warp is done with this stage: refill it with group g + 2
-        if (tid == 0 && g + 2 < ngroups) load_group(g + 2, st);
+        if (tid == 0 && g + 2 * gy < ngroups) load_group(g + 2 * gy, st);
     }
 }
 
@@ -140,8 +145,13 @@ cudaError_t launch_project(const double* A, int64_t R, int RD, int64_t ldn, int6
     const size_t psmem = 128 + 2 * (size_t)KS * kProjCols * 4 * 8 + 8 * 16 * kProjPitch * 8;
     cudaError_t e = cudaFuncSetAttribute(k_project<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     if (e != cudaSuccess) return e;
-    k_project<KS><<<(unsigned)((R + kProjRows - 1) / kProjRows), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd,
-                                                                                          b_tiled, E, W, Wp, out, accumulate);
+    // few row blocks: spread the column groups over gridDim.y so that about one wave of CTAs is in flight
+    const int64_t nrb = (R + kProjRows - 1) / kProjRows;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int gy = (int)std::max<int64_t>(1, std::min<int64_t>(Wp / kProjCols, (int64_t)sms / nrb));
+    k_project<KS><<<dim3((unsigned)nrb, (unsigned)gy), kProjThreads, psmem, st>>>(A, R, RD, ldn, lde, ldd, b_tiled, E, W, Wp, out,
+                                                                                accumulate);
     return cudaGetLastError();
 }
 
