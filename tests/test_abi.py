@@ -107,3 +107,29 @@ def test_header_is_plain_c_and_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("100 -1 ")
+
+
+def test_training_chunk_pitch_is_bank_conflict_free(tmp_path):
+    """The FP64 predict kernels read 8 (or 4) consecutive training rows per quarter-warp with 16-byte loads; the row pitch
+    x_pitch(DP) of gpe_math.cuh must put them on disjoint groups of four shared-memory banks for every compiled DP
+    (at pitch = DP, D = 8 ran slower than D = 10: DESIGN 4.1c).  Host-only: the constexpr is evaluated by nvcc's host pass."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dps = [int(x) for x in re.search(r"^DPS\s*:=\s*(.*)$", open(os.path.join(root, "Makefile")).read(), re.M).group(1).split()]
+    src = tmp_path / "pitch.cu"
+    src.write_text('#include <cstdio>\n#include "gpe_math.cuh"\nint main() { const int dps[] = {%s};\n'
+                   '  for (int dp : dps) printf("%%d %%d\\n", dp, gpe::x_pitch(dp)); return 0; }\n' % ", ".join(map(str, dps)))
+    exe = tmp_path / "pitch"
+    subprocess.run(["nvcc", "-std=c++17", "-I", os.path.join(root, "gp_emulator_b200", "csrc"), "-o", str(exe), str(src)],
+                   check=True, capture_output=True, timeout=300)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    pitches = dict(zip(map(int, out[0::2]), map(int, out[1::2])))
+    assert sorted(pitches) == sorted(dps)
+    for dp, xp in pitches.items():
+        assert xp >= dp and xp % 2 == 0 and xp - dp <= 2                      # 16-byte aligned rows, at most one pad pair
+        groups = {(r * xp * 8 // 16) % 8 for r in range(8)}                   # 16-byte bank group of the first load of row r
+        assert len(groups) == 8, (dp, xp)
