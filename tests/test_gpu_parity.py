@@ -1430,3 +1430,45 @@ def test_handful_of_points_cluster_path(gpemu, M, D):
         got = bank.predict(testing[:20], want_var=True, want_deriv=True)
         assert orc.ref_err(got["mu"], mu_b) < TOL and orc.ref_err(got["var"], var_b) < TOL
         assert orc.ref_err(got["deriv"], grad_b) < TOL
+
+
+def test_concurrent_device_calls_on_shared_handles(gpemu):
+    """include/gpemu.h allows device-pointer calls on one handle from several threads, each on its own stream.  The paths
+    added in round 2 under that contract: the cluster path (no shared state), the generic D > 32 path (one K* scratch per
+    model: mutex + event), and a bank on the shared-difference kernel.  Every thread must get exactly the serial result."""
+    import threading
+    import torch
+    rs = np.random.RandomState(21)
+    cases = []
+    inputs, theta, invQ, invQt, t = orc.make_S_model(250, 10, 300, seed=3)            # cluster path
+    cases.append((gpemu.DeviceModel(inputs, theta, invQt, invQ), t, dict()))
+    inputs, theta, invQ, invQt, t = orc.make_S_model(120, 40, 5000, seed=4)           # generic path, several sub-batches
+    theta = theta.copy(); theta[:40] -= np.log(5.0)
+    cases.append((gpemu.DeviceModel(inputs, theta, invQt, invQ), t, dict()))
+    M, D, E = 100, 6, 7                                                                # bank, group kernel (N large enough)
+    binp = rs.random_sample((M, D)); thetas = rs.random_sample((E, D + 2)); invQts = rs.randn(E, M)
+    cases.append((gpemu.DeviceBank(binp, thetas, invQts), rs.random_sample((6000, D)), dict(want_var=False, want_deriv=True)))
+    for handle, t, kw in cases:
+        td = torch.from_numpy(np.ascontiguousarray(t)).cuda()
+        serial = {k: v.clone() for k, v in handle.predict(td, **kw).items()}
+        torch.cuda.synchronize()
+        results, errors = [None] * 6, []
+
+        def work(i):
+            try:
+                s = torch.cuda.Stream()
+                with torch.cuda.stream(s):
+                    outs = [handle.predict(td, **kw) for _ in range(4)]
+                s.synchronize()
+                results[i] = outs
+            except Exception as e:     # noqa: BLE001 -- reported below
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+        for th in threads: th.start()
+        for th in threads: th.join()
+        assert not errors, errors
+        for outs in results:
+            for o in outs:
+                for k in serial:
+                    assert torch.equal(o[k], serial[k]), (type(handle).__name__, k)
