@@ -1,6 +1,6 @@
 import os, sys, time
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gp_emulator_b200 as g
 from oracle import gp_oracle as orc
 inputs, theta, invQ, invQt, testing = orc.make_S_model(250, 10, 100000, seed=0)
